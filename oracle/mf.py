@@ -1,0 +1,93 @@
+"""CPU ORACLE glue (test infrastructure only): ctypes driver of oracle/mf_ldlt.c on a symbolic structure exported by
+the product's host-side analysis (pipsgpu_symbolic_export). Used to validate that analysis on CPU and as the
+multi-frontal CPU baseline in bench.py's cpu_baseline leg."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    """gcc-compile oracle/mf_ldlt.c into oracle/_build/libmf_oracle.so"""
+    out = os.path.join(_HERE, "_build", "libmf_oracle.so")
+    src = os.path.join(_HERE, "mf_ldlt.c")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", out, src, "-lm"])
+    return out
+
+
+class _MfSym(C.Structure):
+    _fields_ = [("n", C.c_int), ("nB", C.c_int), ("ns", C.c_int),
+                ("sn_col", C.c_void_p), ("sn_rowptr", C.c_void_p), ("rowidx", C.c_void_p), ("relidx", C.c_void_p),
+                ("sn_na", C.c_void_p), ("sn_nb", C.c_void_p), ("sn_parent", C.c_void_p), ("Loff", C.c_void_p),
+                ("Coff", C.c_void_p), ("ptype", C.c_void_p), ("sgn", C.c_void_p)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.mf_factorize.restype = C.c_int
+        _LIB.mf_solve.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def leaf_kkt_and_border(lp, i):
+    """lower CSR of the leaf KKT (create_kkt) and the border triplets in the compressed border index space
+    [0,n0) | myl | mzl  (SC index = b for b < n0, b + my0 otherwise)."""
+    from .linsys import build_leaf_kkt_lower
+    ch = lp.children[i]
+    krow, jcol, val, diag_pos = build_leaf_kkt_lower(ch)
+    n0 = lp.root.n
+    A, Cm, F, G = ch.A.tocoo(), ch.C.tocoo(), ch.F.tocoo(), ch.G.tocoo()
+    brow = np.concatenate([ch.n + A.row, ch.n + ch.my + Cm.row, F.col, G.col]).astype(np.int32)
+    bcol = np.concatenate([A.col, Cm.col, n0 + F.row, n0 + lp.myl + G.row]).astype(np.int32)
+    bval = np.concatenate([A.data, Cm.data, F.data, G.data]).astype(np.float64)
+    nB = n0 + lp.myl + lp.mzl
+    return krow, jcol, val, diag_pos, nB, brow, bcol, bval
+
+
+class MfLeaf:
+    """numeric multifrontal LDL^T of one leaf on a given symbolic structure `sym` (dict of numpy arrays)."""
+
+    def __init__(self, sym, pivot_eps=1e-8):
+        self.sym = sym
+        self.S = _MfSym(sym["n"], sym["nB"], sym["ns"], *[_p(sym[k]) for k in (
+            "sn_col", "sn_rowptr", "rowidx", "relidx", "sn_na", "sn_nb", "sn_parent", "Loff", "Coff", "ptype", "sgn")])
+        n = sym["n"]
+        self.L = np.zeros(int(sym["Loff"][-1]) + 1)
+        self.Cb = np.zeros(int(sym["Coff"][-1]) + 1)
+        self.d_d, self.d_e, self.dinv_d, self.dinv_e = (np.zeros(n + 1) for _ in range(4))
+        self.pivot_eps = pivot_eps
+        self.inertia = np.zeros(3, dtype=np.int32)
+        self.npert = C.c_int(0)
+
+    def factorize(self, kval, bval, SCb=None, knorm=None):
+        sym = self.sym
+        kval = np.ascontiguousarray(kval, dtype=np.float64)
+        bval = np.ascontiguousarray(bval, dtype=np.float64)
+        if knorm is None:
+            knorm = max(1.0, float(np.abs(kval).max(initial=0.0)))
+        rc = lib().mf_factorize(C.byref(self.S), C.c_int64(len(kval)), _p(sym["kmap"]), _p(kval), C.c_int64(len(bval)),
+                                _p(sym["bmap"]), _p(bval), _p(self.L), _p(self.Cb), _p(self.d_d), _p(self.d_e),
+                                _p(self.dinv_d), _p(self.dinv_e), _p(SCb) if SCb is not None else None,
+                                C.c_double(self.pivot_eps * knorm), _p(self.inertia), C.byref(self.npert))
+        assert rc == 0
+        return tuple(int(v) for v in self.inertia), self.npert.value
+
+    def solve(self, x):
+        x = np.array(x, dtype=np.float64, copy=True)
+        rc = lib().mf_solve(C.byref(self.S), _p(self.sym["perm"]), _p(self.L), _p(self.dinv_d), _p(self.dinv_e), _p(x))
+        assert rc == 0
+        return x
