@@ -209,13 +209,20 @@ def partition_children(N, P):
     """mapChildrenToNSubTrees (Readers/Distributed/DistributedTree.C:437-475): contiguous ranges, floor(N/P) each,
     the N mod P leftovers spread by stride over the ranks. Returns list of (lo, hi) per rank."""
     assert 1 <= P <= max(N, 1)
-    base, left = divmod(N, P)
-    extra = np.zeros(P, dtype=int)
-    if left > 0:
-        step = P / left
-        for k in range(left):
-            extra[int(k * step)] += 1
-    sizes = base + extra
+    everyone_gets, n_leftovers = divmod(N, P)
+    sizes = np.full(P, everyone_gets, dtype=int)
+    if n_leftovers > 0:
+        free_in_row = P - n_leftovers
+        free_after, additional = divmod(free_in_row, n_leftovers)
+        assigned = 0
+        i = 0
+        while i < P:
+            sizes[i] += 1
+            i += 1
+            if additional != assigned:
+                i += 1
+                assigned += 1
+            i += free_after
     offs = np.concatenate([[0], np.cumsum(sizes)])
     return [(int(offs[r]), int(offs[r + 1])) for r in range(P)]
 

@@ -4,3 +4,4 @@ The directory name contains a hyphen, so import it through `__graft_entry__.load
 `pips_ipmpp_b200`)."""
 from . import problem  # noqa: F401
 from . import capi  # noqa: F401
+from . import linsys  # noqa: F401

@@ -106,3 +106,217 @@ class Symbolic:
                 lib().pipsgpu_symbolic_destroy(self.h)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device objects
+# ---------------------------------------------------------------------------------------------------------------
+class Context:
+    """pipsgpu_ctx: one per process / GPU."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().pipsgpu_ctx_create(C.c_int(device), C.byref(self.h)))
+        self.device = device
+        self._keep = []
+
+    def init_comm(self, uid: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(uid, 128)
+        _check(lib().pipsgpu_ctx_init_comm(self.h, buf, C.c_int(rank), C.c_int(nranks)))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().pipsgpu_nccl_unique_id(buf))
+        return buf.raw
+
+    def commit(self, threads=0):
+        _check(lib().pipsgpu_ctx_commit(self.h, C.c_int(threads)))
+
+    def synchronize(self):
+        _check(lib().pipsgpu_ctx_synchronize(self.h))
+
+    def factorize_leaves(self, sc=None):
+        _check(lib().pipsgpu_ctx_factorize_leaves(self.h, sc.h if sc is not None else None))
+
+    def launch_count(self):
+        return int(lib().pipsgpu_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            _check(lib().pipsgpu_ctx_destroy(self.h))
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Leaf:
+    """pipsgpu_leaf: one scenario block (DistributedLeafLinearSystem + its DoubleLinearSolver)."""
+
+    def __init__(self, ctx: Context, n, nx, ny, nz, krow, jcol, val):
+        self.ctx = ctx
+        self.n, self.nx, self.ny, self.nz = n, nx, ny, nz
+        self.h = C.c_void_p()
+        krow, jcol, val = _i32(krow), _i32(jcol), _f64(val)
+        _check(lib().pipsgpu_leaf_create(ctx.h, C.c_int(n), C.c_int(nx), C.c_int(ny), C.c_int(nz), _ip(krow), _ip(jcol),
+                                         _ip(val), C.byref(self.h)))
+
+    def set_border(self, n0, my0, myl, mzl, A, Cm, F, G):
+        args = []
+        for m in (A, Cm, F, G):
+            args.extend(_csr_args(m))
+        _check(lib().pipsgpu_leaf_set_border(self.h, C.c_int(n0), C.c_int(my0), C.c_int(myl), C.c_int(mzl),
+                                             *[_ip(a) for a in args]))
+
+    def analyze(self):
+        _check(lib().pipsgpu_leaf_analyze(self.h))
+
+    def set_diagonal(self, dd, nomegainv, regP=0.0, regDy=0.0, regDz=0.0):
+        dd, nomegainv = _f64(dd), _f64(nomegainv)
+        _check(lib().pipsgpu_leaf_set_diagonal(self.h, _ip(dd), _ip(nomegainv), C.c_double(regP), C.c_double(regDy),
+                                               C.c_double(regDz)))
+
+    def set_values(self, val):
+        val = _f64(val)
+        _check(lib().pipsgpu_leaf_set_values(self.h, _ip(val)))
+
+    def factorize(self):
+        inertia = np.zeros(3, dtype=np.int32)
+        _check(lib().pipsgpu_leaf_factorize(self.h, _ip(inertia)))
+        return tuple(int(v) for v in inertia)
+
+    def solve(self, rhs):
+        """rhs: (nrhs, n) or (n,) array; returns the solution (same shape)."""
+        x = np.array(rhs, dtype=np.float64, order="C", copy=True)
+        nrhs = 1 if x.ndim == 1 else x.shape[0]
+        _check(lib().pipsgpu_leaf_solve(self.h, C.c_int(nrhs), _ip(x)))
+        return x
+
+    def inertia(self):
+        inertia = np.zeros(3, dtype=np.int32)
+        npert = C.c_int(0)
+        _check(lib().pipsgpu_leaf_get_inertia(self.h, _ip(inertia), C.byref(npert)))
+        return tuple(int(v) for v in inertia), npert.value
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        fl = C.c_double(0)
+        _check(lib().pipsgpu_leaf_get_stats(self.h, _ip(out), C.byref(fl)))
+        keys = ("nnzL", "nnzL_border", "stored", "nfronts", "nlevels", "n_pairs", "max_m", "contrib")
+        d = {k: int(v) for k, v in zip(keys, out)}
+        d["flops"] = fl.value
+        return d
+
+    def add_schur(self, sc):
+        _check(lib().pipsgpu_leaf_add_schur(self.h, sc.h))
+
+
+class SchurComplement:
+    """pipsgpu_sc: dense root Schur complement + dense LDL^T solver."""
+
+    def __init__(self, ctx: Context, n0, my0, myl, mzl, handle=None):
+        self.ctx = ctx
+        self.owned = handle is None
+        self.h = C.c_void_p(handle) if handle is not None else C.c_void_p()
+        if handle is None:
+            _check(lib().pipsgpu_sc_create(ctx.h, C.c_int(n0), C.c_int(my0), C.c_int(myl), C.c_int(mzl), C.byref(self.h)))
+        self.n = int(lib().pipsgpu_sc_dim(self.h))
+
+    def zero(self):
+        _check(lib().pipsgpu_sc_zero(self.h))
+
+    def allreduce(self):
+        _check(lib().pipsgpu_sc_allreduce(self.h))
+
+    def add_sparse(self, row0, col0, M, alpha=1.0):
+        kr, jc, v = _csr_args(M)
+        if kr is None:
+            return
+        _check(lib().pipsgpu_sc_add_sparse(self.h, C.c_int(row0), C.c_int(col0), C.c_int(M.shape[0]), _ip(kr), _ip(jc),
+                                           _ip(v), C.c_double(alpha)))
+
+    def add_diag(self, offset, d, alpha=1.0):
+        d = _f64(d)
+        _check(lib().pipsgpu_sc_add_diag(self.h, C.c_int(offset), C.c_int(len(d)), _ip(d), C.c_double(alpha)))
+
+    def factorize(self):
+        inertia = np.zeros(3, dtype=np.int32)
+        _check(lib().pipsgpu_sc_factorize(self.h, _ip(inertia)))
+        return tuple(int(v) for v in inertia)
+
+    def solve(self, rhs):
+        x = np.array(rhs, dtype=np.float64, order="C", copy=True)
+        nrhs = 1 if x.ndim == 1 else x.shape[0]
+        _check(lib().pipsgpu_sc_solve(self.h, C.c_int(nrhs), _ip(x)))
+        return x
+
+    def download(self):
+        out = np.zeros((self.n, self.n))
+        _check(lib().pipsgpu_sc_download(self.h, _ip(out)))
+        return out
+
+    def upload(self, lower):
+        a = _f64(lower)
+        assert a.shape == (self.n, self.n)
+        _check(lib().pipsgpu_sc_upload(self.h, _ip(a)))
+
+    def close(self):
+        if self.owned and self.h:
+            _check(lib().pipsgpu_sc_destroy(self.h))
+            self.h = C.c_void_p()
+
+
+class KKT:
+    """pipsgpu_kkt: sLinsysRootAug for the two-level dense-Schur-complement case."""
+
+    def __init__(self, ctx: Context, n0, my0, mz0, myl, mzl, A0, C0, F0, G0):
+        self.ctx = ctx
+        self.dims = (n0, my0, mz0, myl, mzl)
+        self.h = C.c_void_p()
+        args = []
+        for m in (A0, C0, F0, G0):
+            args.extend(_csr_args(m))
+        _check(lib().pipsgpu_kkt_create(ctx.h, C.c_int(n0), C.c_int(my0), C.c_int(mz0), C.c_int(myl), C.c_int(mzl),
+                                        *[_ip(a) for a in args], C.byref(self.h)))
+        self.leaves = []
+
+    def add_leaf(self, leaf: Leaf):
+        _check(lib().pipsgpu_kkt_add_leaf(self.h, leaf.h))
+        self.leaves.append(leaf)
+
+    def setup(self, threads=0):
+        _check(lib().pipsgpu_kkt_setup(self.h, C.c_int(threads)))
+
+    def factorize(self, dd0, nomegainv0, nomegainv_link, dd_leaves, nomegainv_leaves, reg=None):
+        """all arguments host arrays (or raw integer addresses of pinned buffers); returns the root inertia"""
+        inertia = np.zeros(3, dtype=np.int32)
+        regp = _ip(_f64(reg)) if reg is not None else None
+        keep = [_f64(a) if not isinstance(a, int) else a for a in (dd0, nomegainv0, nomegainv_link, dd_leaves, nomegainv_leaves)]
+        ptrs = [C.c_void_p(a) if isinstance(a, int) else _ip(a) for a in keep]
+        _check(lib().pipsgpu_kkt_factorize(self.h, *ptrs, regp, _ip(inertia)))
+        return tuple(int(v) for v in inertia)
+
+    def solve_compressed(self, b0, b_leaves):
+        """in place on float64 C-contiguous arrays (or raw addresses)"""
+        p0 = C.c_void_p(b0) if isinstance(b0, int) else _ip(b0)
+        pl = C.c_void_p(b_leaves) if isinstance(b_leaves, int) else _ip(b_leaves)
+        _check(lib().pipsgpu_kkt_solve_compressed(self.h, p0, pl))
+
+    def sc(self):
+        n0, my0, mz0, myl, mzl = self.dims
+        return SchurComplement(self.ctx, n0, my0, myl, mzl, handle=lib().pipsgpu_kkt_sc(self.h))
+
+    def stage_times(self):
+        out = np.zeros(8)
+        _check(lib().pipsgpu_kkt_stage_times(self.h, _ip(out)))
+        keys = ("h2d_assembly", "leaf_ldlt_schur", "allreduce", "finalize", "root_ldlt", "lsolve", "dsolve", "ltsolve")
+        return dict(zip(keys, out.tolist()))
+
+    def close(self):
+        if self.h:
+            _check(lib().pipsgpu_kkt_destroy(self.h))
+            self.h = C.c_void_p()

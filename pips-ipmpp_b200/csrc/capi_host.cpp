@@ -3,6 +3,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../include/pipsgpu.h"
 #include "common.h"
@@ -35,18 +36,28 @@ int pipsgpu_partition(int N, int P, int* lo, int* hi) {
         pipsgpu::set_error("pipsgpu_partition: need 1 <= n_ranks <= n_children");
         return PIPSGPU_ERR_INVALID;
     }
-    const int base = N / P, left = N % P;
+    const int everyone_gets = N / P, n_leftovers = N % P;
+    std::vector<int> per(P, everyone_gets);
+    if (n_leftovers > 0) {
+        const int free_in_leftover_row = P - n_leftovers;
+        const int free_after_each_leftover = free_in_leftover_row / n_leftovers;
+        const int additional_frees = free_in_leftover_row % n_leftovers;
+        int assigned = 0;
+        for (int i = 0; i < P; i += free_after_each_leftover) {
+            ++per[i];
+            ++i;
+            if (additional_frees != assigned) { ++i; ++assigned; }
+        }
+    }
     int off = 0;
     for (int r = 0; r < P; ++r) {
-        int extra = 0;
-        if (left > 0) {
-            const double step = (double)P / left;
-            for (int k = 0; k < left; ++k)
-                if ((int)(k * step) == r) ++extra;
-        }
         lo[r] = off;
-        off += base + extra;
+        off += per[r];
         hi[r] = off;
+    }
+    if (off != N) {
+        pipsgpu::set_error("pipsgpu_partition: internal error");
+        return PIPSGPU_ERR_INVALID;
     }
     return PIPSGPU_OK;
 }

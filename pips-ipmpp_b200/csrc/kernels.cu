@@ -1,0 +1,758 @@
+// CUDA kernels of the KKT hot path, written for sm_100a (B200). FP64 throughout.
+//
+//  leaf path   : front_factor_kernel  - one CTA per front, one launch per tree level over ALL blocks of the GPU:
+//                                       extend-add of the children, static 1x1/2x2-pivot LDL^T of the pivot block
+//                                       (one warp, shared memory), register-blocked panel solve, contribution block
+//                                       and the front's share of  SC -= Bord^T K^-1 Bord  (red.global.add.f64).
+//                fwd/bwd_level_kernel - one warp per front, level-scheduled supernodal triangular solves, multi-RHS.
+//  root path   : dense right-looking LDL^T of the Schur complement: diagonal block (1 warp) / panel (thread per row)
+//                / trailing update on the FP64 tensor pipe (mma.sync m8n8k4 f64 = DMMA).
+// Reference anchors for what these kernels replace are in include/pipsgpu.h next to each entry point.
+#include "kernels.cuh"
+
+#include <atomic>
+
+namespace pipsgpu {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t kernel_launch_count() { return g_launches.load(); }
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// =====================================================================================================
+// value scatter / diagonal refresh
+// =====================================================================================================
+__global__ void scatter_values_kernel(const int64_t* __restrict__ map, const double* __restrict__ val, int64_t nnz,
+                                      double* __restrict__ L) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) atomicAdd(&L[map[i]], val[i]);
+}
+void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s) {
+    if (nnz <= 0) return;
+    scatter_values_kernel<<<cdiv(nnz, 256), 256, 0, s>>>(map, val, nnz, L);
+    COUNT_LAUNCH();
+}
+
+__global__ void set_diag_kernel(const int64_t* __restrict__ diagpos, const double* __restrict__ dvals, int64_t n,
+                                double* __restrict__ kval) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) kval[diagpos[i]] = dvals[i];
+}
+void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s) {
+    if (n <= 0) return;
+    set_diag_kernel<<<cdiv(n, 256), 256, 0, s>>>(diagpos, dvals, n, kval);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// multifrontal numeric factorisation: one CTA per front
+// =====================================================================================================
+constexpr int FT = 128;   // threads per front CTA
+
+// panel rows below the pivot block: W = A - L * Wp^T (left-looking by row, row kept in registers), L = W * D^-1
+template <int WP>
+__device__ __forceinline__ void panel_rows(const FrontDesc& fd, double* __restrict__ F, double* __restrict__ Wscr,
+                                           const double (*Pw)[MAXW + 1], const int8_t* s_pt, const double* s_did,
+                                           const double* s_die) {
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
+    for (int r = threadIdx.x; r < u; r += FT) {
+        double l[WP], wv[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) {
+            l[k] = (k < w) ? F[(size_t)k * m + w + r] : 0.0;
+            wv[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < WP; ++k) {
+            if (k < w) {
+                double acc = l[k];
+#pragma unroll
+                for (int j = 0; j < k; ++j) acc -= l[j] * Pw[k][j];
+                const int t = s_pt[k];
+                if (t == 0) {
+                    wv[k] = acc;
+                    l[k] = acc * s_did[k];
+                } else if (t == 1) {
+                    l[k] = acc;   // r1, finalised together with the second column (Pw[k+1][k] == 0)
+                } else if (k > 0) {
+                    const double r1 = l[k - 1], r2 = acc;
+                    wv[k - 1] = r1;
+                    wv[k] = r2;
+                    l[k - 1] = r1 * s_did[k - 1] + r2 * s_die[k - 1];
+                    l[k] = r1 * s_die[k - 1] + r2 * s_did[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < WP; ++k)
+            if (k < w) F[(size_t)k * m + w + r] = l[k];
+        double* wr = Wscr + (size_t)r * WP;
+#pragma unroll
+        for (int k = 0; k < WP; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(wv[k], wv[k + 1]);
+    }
+}
+
+// contribution block C(i,j) -= L_i . W_j  (j < na) and the border x border part straight into the Schur complement
+template <int WP>
+__device__ __forceinline__ void update_rows(const FrontDesc& fd, const double* __restrict__ F,
+                                            const double* __restrict__ Wscr, double* __restrict__ Cs,
+                                            const int* __restrict__ rowg, double* __restrict__ SC, int ldsc) {
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
+    for (int r = threadIdx.x; r < u; r += FT) {
+        double l[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + r] : 0.0;
+        const int jend = (SC != nullptr) ? r : min(r, na - 1);
+        const int64_t scrow = (r >= na) ? (int64_t)rowg[r] * ldsc : 0;
+        for (int j = 0; j <= jend; ++j) {
+            const double* wj = Wscr + (size_t)j * WP;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < WP; k += 2) {
+                const double2 wk = *reinterpret_cast<const double2*>(wj + k);
+                acc0 = fma(l[k], wk.x, acc0);
+                acc1 = fma(l[k + 1], wk.y, acc1);
+            }
+            const double acc = acc0 + acc1;
+            if (j < na) Cs[(size_t)j * u + r] -= acc;
+            else atomicAdd(&SC[scrow + rowg[j]], -acc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FT) front_factor_kernel(FactorArgs a, int level_begin) {
+    __shared__ double Pl[MAXW][MAXW + 1];   // pivot block: A on entry, strict lower L on exit
+    __shared__ double Pw[MAXW][MAXW + 1];   // pivot block: W = L*D (strictly below the pivot blocks)
+    __shared__ double s_did[MAXW], s_die[MAXW];
+    __shared__ int8_t s_pt[MAXW];
+
+    const int tid = threadIdx.x;
+    const int f = a.level_fronts[level_begin + blockIdx.x];
+    const FrontDesc fd = a.fronts[f];
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
+    double* F = a.L + fd.Loff;
+    double* Cs = a.C + fd.Coff;
+
+    // ---- 1. extend-add of the children's contribution blocks (children sequential, entries parallel) ----
+    for (int c = fd.child_begin; c < fd.child_end; ++c) {
+        const FrontDesc cd = a.fronts[a.child_list[c]];
+        const int uc = cd.na + cd.nb, nac = cd.na;
+        const double* Cc = a.C + cd.Coff;
+        const int* rel = a.relidx + cd.rows_off;
+        const int total = uc * nac;
+        for (int idx = tid; idx < total; idx += FT) {
+            const int j = idx / uc, i = idx - j * uc;
+            if (i < j) continue;
+            const double v = Cc[idx];
+            const int li = rel[i], lj = rel[j];
+            if (lj < w) F[(size_t)lj * m + li] += v;
+            else Cs[(size_t)(lj - w) * u + (li - w)] += v;
+        }
+        __syncthreads();
+    }
+
+    // ---- 2. pivot block into shared memory ----
+    for (int idx = tid; idx < MAXW * (MAXW + 1); idx += FT) {
+        (&Pl[0][0])[idx] = 0.0;
+        (&Pw[0][0])[idx] = 0.0;
+    }
+    if (tid < MAXW) {
+        s_pt[tid] = (tid < w) ? a.ptype[fd.col0 + tid] : (int8_t)0;
+        s_did[tid] = 0.0;
+        s_die[tid] = 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += FT) {
+        const int j = idx / w, i = idx - j * w;
+        if (i >= j) Pl[i][j] = F[(size_t)j * m + i];
+    }
+    __syncthreads();
+
+    // ---- 3. LDL^T of the pivot block by warp 0: lane i owns row i, lock-step over pivots ----
+    if (tid < 32) {
+        const int lane = tid;
+        const unsigned full = 0xffffffffu;
+        const double eps = a.leaves[fd.leaf].eps;
+        int npos = 0, nneg = 0, nzero = 0, npert = 0;
+        int k = 0;
+        while (k < w) {
+            const bool pair = (s_pt[k] == 1) && (k + 1 < w);
+            double r1 = 0.0, r2 = 0.0;
+            if (lane >= k && lane < w) {
+                r1 = Pl[lane][k];
+                for (int j = 0; j < k; ++j) r1 -= Pl[lane][j] * Pw[k][j];
+                if (pair && lane >= k + 1) {
+                    r2 = Pl[lane][k + 1];
+                    for (int j = 0; j < k; ++j) r2 -= Pl[lane][j] * Pw[k + 1][j];
+                }
+            }
+            const int g = fd.col0 + k;
+            if (!pair) {
+                double d = __shfl_sync(full, r1, k);
+                const double sg = (double)a.sgn[g];
+                if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
+                if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
+                const double inv = 1.0 / d;
+                if (lane > k && lane < w) { Pw[lane][k] = r1; Pl[lane][k] = r1 * inv; }
+                if (lane == k) {
+                    a.Dd[g] = d; a.De[g] = 0.0; a.Did[g] = inv; a.Die[g] = 0.0;
+                    s_did[k] = inv; s_die[k] = 0.0;
+                }
+                k += 1;
+            } else {
+                double da = __shfl_sync(full, r1, k);
+                const double db = __shfl_sync(full, r1, k + 1);
+                double dc = __shfl_sync(full, r2, k + 1);
+                double det = da * dc - db * db;
+                if (!(det <= -eps * eps)) {
+                    if (da < eps) da = eps;
+                    if (dc > -eps) dc = -eps;
+                    det = da * dc - db * db;
+                    ++npert;
+                }
+                if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
+                const double ia = dc / det, ib = -db / det, ic = da / det;
+                if (lane > k + 1 && lane < w) {
+                    Pw[lane][k] = r1; Pw[lane][k + 1] = r2;
+                    Pl[lane][k] = r1 * ia + r2 * ib;
+                    Pl[lane][k + 1] = r1 * ib + r2 * ic;
+                }
+                if (lane == k + 1) { Pl[k + 1][k] = 0.0; Pw[k + 1][k] = 0.0; }
+                if (lane == k) {
+                    a.Dd[g] = da; a.De[g] = db; a.Dd[g + 1] = dc; a.De[g + 1] = 0.0;
+                    a.Did[g] = ia; a.Die[g] = ib; a.Did[g + 1] = ic; a.Die[g + 1] = 0.0;
+                    s_did[k] = ia; s_die[k] = ib; s_did[k + 1] = ic; s_die[k + 1] = 0.0;
+                }
+                k += 2;
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && a.stats) {
+            int* st = a.stats + 4 * fd.leaf;
+            if (npos) atomicAdd(st + 0, npos);
+            if (nneg) atomicAdd(st + 1, nneg);
+            if (nzero) atomicAdd(st + 2, nzero);
+            if (npert) atomicAdd(st + 3, npert);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += FT) {
+        const int j = idx / w, i = idx - j * w;
+        if (i > j) F[(size_t)j * m + i] = Pl[i][j];
+        else if (i == j) F[(size_t)j * m + i] = 1.0;
+    }
+    if (u == 0) return;
+
+    // ---- 4. panel rows, 5. contribution block + Schur complement share ----
+    double* Wscr = a.W + fd.Woff;
+    const int* rowg = a.rowg + fd.rows_off;
+    if (w <= 8) {
+        panel_rows<8>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
+        __syncthreads();
+        update_rows<8>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
+    } else if (w <= 16) {
+        panel_rows<16>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
+        __syncthreads();
+        update_rows<16>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
+    } else {
+        panel_rows<32>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
+        __syncthreads();
+        update_rows<32>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
+    }
+    (void)na;
+}
+
+void launch_front_factor(const FactorArgs& a, int level_begin, int nfronts, cudaStream_t s) {
+    if (nfronts <= 0) return;
+    front_factor_kernel<<<nfronts, FT, 0, s>>>(a, level_begin);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// supernodal triangular solves (level scheduled, one warp per front, grid.y = right-hand side)
+// =====================================================================================================
+__global__ void perm_kernel(const int* __restrict__ gidx, const double* __restrict__ src, double* __restrict__ dst,
+                            int64_t n, int64_t stride, bool gather) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t o = (int64_t)blockIdx.y * stride;
+    if (gather) dst[o + i] = src[o + gidx[i]];
+    else dst[o + gidx[i]] = src[o + i];
+}
+void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s) {
+    if (n <= 0 || nrhs <= 0) return;
+    perm_kernel<<<dim3(cdiv(n, 256), nrhs), 256, 0, s>>>(gidx, src, dst, n, stride, true);
+    COUNT_LAUNCH();
+}
+void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s) {
+    if (n <= 0 || nrhs <= 0) return;
+    perm_kernel<<<dim3(cdiv(n, 256), nrhs), 256, 0, s>>>(gidx, src, dst, n, stride, false);
+    COUNT_LAUNCH();
+}
+
+constexpr int SW = 4;   // warps (= fronts) per solve CTA
+
+__global__ void __launch_bounds__(SW * 32) fwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SW + warp;
+    if (fi >= nfronts) return;
+    const unsigned full = 0xffffffffu;
+    const FrontDesc fd = a.fronts[a.level_fronts[level_begin + fi]];
+    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
+    double* upd = a.upd + (int64_t)blockIdx.y * a.upd_stride;
+    double* us = upd + fd.upd_off;
+    const double* F = a.L + fd.Loff;
+
+    for (int i = lane; i < na; i += 32) us[i] = 0.0;
+    __syncwarp();
+    for (int c = fd.child_begin; c < fd.child_end; ++c) {
+        const FrontDesc cd = a.fronts[a.child_list[c]];
+        const int* rel = a.relidx + cd.rows_off;
+        const double* uc = upd + cd.upd_off;
+        for (int i = lane; i < cd.na; i += 32) {
+            const int li = rel[i];
+            const double v = uc[i];
+            if (li < w) x[fd.col0 + li] += v;
+            else us[li - w] += v;
+        }
+        __syncwarp();
+    }
+    double y = (lane < w) ? x[fd.col0 + lane] : 0.0;
+    for (int k = 0; k < w; ++k) {
+        const double yk = __shfl_sync(full, y, k);
+        if (lane > k && lane < w) y -= F[(size_t)k * m + lane] * yk;
+    }
+    if (lane < w) x[fd.col0 + lane] = y;
+    for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        double acc = 0.0;
+        for (int k = 0; k < w; ++k) {
+            const double yk = __shfl_sync(full, y, k);
+            if (i < na) acc = fma(F[(size_t)k * m + w + i], yk, acc);
+        }
+        if (i < na) us[i] -= acc;
+    }
+}
+
+__global__ void __launch_bounds__(SW * 32) bwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SW + warp;
+    if (fi >= nfronts) return;
+    const unsigned full = 0xffffffffu;
+    const FrontDesc fd = a.fronts[a.level_fronts[level_begin + fi]];
+    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
+    const double* F = a.L + fd.Loff;
+    const int* rowg = a.rowg + fd.rows_off;
+
+    double t = (lane < w) ? x[fd.col0 + lane] : 0.0;
+    for (int k = 0; k < w; ++k) {
+        double s = 0.0;
+        for (int i = lane; i < na; i += 32) s = fma(F[(size_t)k * m + w + i], x[rowg[i]], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
+        if (lane == k) t -= s;
+    }
+    for (int k = w - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(full, t, k);
+        if (lane < k) t -= F[(size_t)lane * m + k] * xk;
+    }
+    if (lane < w) x[fd.col0 + lane] = t;
+}
+
+void launch_fwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
+    if (nfronts <= 0 || nrhs <= 0) return;
+    fwd_level_kernel<<<dim3(cdiv(nfronts, SW), nrhs), SW * 32, 0, s>>>(a, level_begin, nfronts);
+    COUNT_LAUNCH();
+}
+void launch_bwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
+    if (nfronts <= 0 || nrhs <= 0) return;
+    bwd_level_kernel<<<dim3(cdiv(nfronts, SW), nrhs), SW * 32, 0, s>>>(a, level_begin, nfronts);
+    COUNT_LAUNCH();
+}
+
+__global__ void diag_solve_kernel(SolveArgs a, int64_t npos) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npos) return;
+    double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
+    const int t = a.ptype[p];
+    if (t == 0) {
+        x[p] *= a.Did[p];
+    } else if (t == 1) {
+        const double y0 = x[p], y1 = x[p + 1];
+        x[p] = a.Did[p] * y0 + a.Die[p] * y1;
+        x[p + 1] = a.Die[p] * y0 + a.Did[p + 1] * y1;
+    }
+}
+void launch_diag_solve(const SolveArgs& a, int64_t npos, int nrhs, cudaStream_t s) {
+    if (npos <= 0 || nrhs <= 0) return;
+    diag_solve_kernel<<<dim3(cdiv(npos, 256), nrhs), 256, 0, s>>>(a, npos);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// border products of Lsolve / Ltsolve
+// =====================================================================================================
+__global__ void border_tmult_kernel(const int* __restrict__ brow, const int* __restrict__ bidx, const double* __restrict__ val,
+                                    int64_t nnz, const double* __restrict__ z, double* __restrict__ b0) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) atomicAdd(&b0[bidx[k]], -val[k] * z[brow[k]]);
+}
+__global__ void border_mult_kernel(const int* __restrict__ brow, const int* __restrict__ bidx, const double* __restrict__ val,
+                                   int64_t nnz, const double* __restrict__ u, double* __restrict__ t) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) atomicAdd(&t[brow[k]], val[k] * u[bidx[k]]);
+}
+void launch_border_tmult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* z, double* b0, cudaStream_t s) {
+    if (nnz <= 0) return;
+    border_tmult_kernel<<<cdiv(nnz, 256), 256, 0, s>>>(brow, bidx, val, nnz, z, b0);
+    COUNT_LAUNCH();
+}
+void launch_border_mult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* u, double* t, cudaStream_t s) {
+    if (nnz <= 0) return;
+    border_mult_kernel<<<cdiv(nnz, 256), 256, 0, s>>>(brow, bidx, val, nnz, u, t);
+    COUNT_LAUNCH();
+}
+
+__global__ void axpy_kernel(double alpha, const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += alpha * x[i];
+}
+void launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t s) {
+    if (n <= 0) return;
+    axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(alpha, x, y, n);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// dense Schur complement: assembly helpers
+// =====================================================================================================
+__global__ void sc_add_sparse_kernel(double* SC, int ld, int row0, int col0, int m, const int* __restrict__ krow,
+                                     const int* __restrict__ jcol, const double* __restrict__ val, double alpha) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    for (int p = krow[r]; p < krow[r + 1]; ++p) {
+        int i = row0 + r, j = col0 + jcol[p];
+        if (j > i) { const int t = i; i = j; j = t; }
+        atomicAdd(&SC[(int64_t)i * ld + j], alpha * val[p]);
+    }
+}
+void launch_sc_add_sparse(double* SC, int ld, int row0, int col0, int m, const int* krow, const int* jcol, const double* val,
+                          double alpha, cudaStream_t s) {
+    if (m <= 0) return;
+    sc_add_sparse_kernel<<<cdiv(m, 128), 128, 0, s>>>(SC, ld, row0, col0, m, krow, jcol, val, alpha);
+    COUNT_LAUNCH();
+}
+
+__global__ void sc_add_diag_kernel(double* SC, int ld, int off, int n, const double* __restrict__ d, double alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) SC[(int64_t)(off + i) * ld + off + i] += alpha * (d ? d[i] : 1.0);
+}
+void launch_sc_add_diag(double* SC, int ld, int off, int n, const double* d, double alpha, cudaStream_t s) {
+    if (n <= 0) return;
+    sc_add_diag_kernel<<<cdiv(n, 128), 128, 0, s>>>(SC, ld, off, n, d, alpha);
+    COUNT_LAUNCH();
+}
+
+__global__ void sc_add_ctdc_kernel(double* SC, int ld, int mz, const int* __restrict__ krow, const int* __restrict__ jcol,
+                                   const double* __restrict__ val, const double* __restrict__ zdiag) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= mz) return;
+    const double dinv = 1.0 / zdiag[r];
+    for (int p = krow[r]; p < krow[r + 1]; ++p)
+        for (int q = krow[r]; q < krow[r + 1]; ++q) {
+            const int i = jcol[p], j = jcol[q];
+            if (j <= i) atomicAdd(&SC[(int64_t)i * ld + j], -val[p] * val[q] * dinv);
+        }
+}
+void launch_sc_add_ctdc(double* SC, int ld, int mz, const int* krow, const int* jcol, const double* val, const double* zdiag,
+                        cudaStream_t s) {
+    if (mz <= 0) return;
+    sc_add_ctdc_kernel<<<cdiv(mz, 128), 128, 0, s>>>(SC, ld, mz, krow, jcol, val, zdiag);
+    COUNT_LAUNCH();
+}
+
+// packed layout of the three reduced pieces (LS/DistributedRootLinearSystem.C:860-881)
+int64_t sc_pack_size(int n0, int nl) {
+    return (int64_t)n0 * (n0 + 1) / 2 + (int64_t)nl * n0 + (int64_t)nl * (nl + 1) / 2;
+}
+__global__ void sc_pack_kernel(const double* __restrict__ SC, int ld, int n0, int my0, int nl, double* __restrict__ buf,
+                               bool unpack, double* __restrict__ SCout) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int n = n0 + my0 + nl;
+    if (i >= n || j > i) return;
+    int64_t off;
+    const int64_t base1 = (int64_t)n0 * (n0 + 1) / 2, base2 = base1 + (int64_t)nl * n0;
+    if (i < n0) off = (int64_t)i * (i + 1) / 2 + j;
+    else if (i >= n0 + my0) {
+        const int q = i - n0 - my0;
+        if (j < n0) off = base1 + (int64_t)q * n0 + j;
+        else if (j >= n0 + my0) off = base2 + (int64_t)q * (q + 1) / 2 + (j - n0 - my0);
+        else return;
+    } else return;
+    if (unpack) SCout[(int64_t)i * ld + j] = buf[off];
+    else buf[off] = SC[(int64_t)i * ld + j];
+}
+void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* buf, bool unpack, double* SCout, cudaStream_t s) {
+    const int n = n0 + my0 + nl;
+    if (n <= 0) return;
+    sc_pack_kernel<<<dim3(cdiv(n, 128), n), 128, 0, s>>>(SC, ld, n0, my0, nl, buf, unpack, SCout);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// dense right-looking LDL^T (no pivoting: the x0-block is eliminated first, expected pivot signs + / -)
+// =====================================================================================================
+__global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int kb, int bw, int n0, double eps, double* D,
+                                                        double* Dinv, double* diagW, int* stats) {
+    __shared__ double Pl[DENSE_NB][DENSE_NB + 1];
+    __shared__ double Pw[DENSE_NB][DENSE_NB + 1];
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    for (int j = 0; j < DENSE_NB; ++j) {
+        Pl[lane][j] = (lane < bw && j <= lane) ? A[(int64_t)(kb + lane) * ld + kb + j] : 0.0;
+        Pw[lane][j] = 0.0;
+    }
+    __syncwarp();
+    int npos = 0, nneg = 0, nzero = 0, npert = 0;
+    for (int k = 0; k < bw; ++k) {
+        double r1 = 0.0;
+        if (lane >= k && lane < bw) {
+            r1 = Pl[lane][k];
+            for (int j = 0; j < k; ++j) r1 -= Pl[lane][j] * Pw[k][j];
+        }
+        double d = __shfl_sync(full, r1, k);
+        const double sg = (kb + k < n0) ? 1.0 : -1.0;
+        if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
+        if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
+        const double inv = 1.0 / d;
+        if (lane > k && lane < bw) { Pw[lane][k] = r1; Pl[lane][k] = r1 * inv; }
+        if (lane == k) { D[kb + k] = d; Dinv[kb + k] = inv; }
+        __syncwarp();
+    }
+    for (int j = 0; j < DENSE_NB; ++j) {
+        if (lane < bw && j < lane) A[(int64_t)(kb + lane) * ld + kb + j] = Pl[lane][j];
+        diagW[lane * DENSE_NB + j] = (j < lane) ? Pw[lane][j] : 0.0;
+    }
+    if (lane == 0 && stats) {
+        atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
+    }
+}
+void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps, double* D, double* Dinv, double* diagW, int* stats,
+                       cudaStream_t s) {
+    dense_diag_kernel<<<1, 32, 0, s>>>(A, ld, kb, bw, n0, eps, D, Dinv, diagW, stats);
+    COUNT_LAUNCH();
+}
+
+// rows below the diagonal block: thread per row, row in registers
+__global__ void __launch_bounds__(128) dense_trsm_kernel(double* A, int ld, int n, int kb, int bw, const double* __restrict__ Dinv,
+                                                         const double* __restrict__ diagW, double* __restrict__ Wbuf) {
+    __shared__ double Pw[DENSE_NB][DENSE_NB + 1];
+    __shared__ double s_dinv[DENSE_NB];
+    for (int idx = threadIdx.x; idx < DENSE_NB * DENSE_NB; idx += blockDim.x) Pw[idx / DENSE_NB][idx % DENSE_NB] = diagW[idx];
+    if (threadIdx.x < DENSE_NB) s_dinv[threadIdx.x] = (threadIdx.x < bw) ? Dinv[kb + threadIdx.x] : 0.0;
+    __syncthreads();
+    const int r = kb + bw + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double* arow = A + (int64_t)r * ld + kb;
+    double l[DENSE_NB], wv[DENSE_NB];
+#pragma unroll
+    for (int k = 0; k < DENSE_NB; ++k) l[k] = (k < bw) ? arow[k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < DENSE_NB; ++k) {
+        double acc = l[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) acc -= l[j] * Pw[k][j];
+        wv[k] = acc;
+        l[k] = acc * s_dinv[k];
+    }
+#pragma unroll
+    for (int k = 0; k < DENSE_NB; ++k)
+        if (k < bw) arow[k] = l[k];
+    double* wr = Wbuf + (int64_t)r * DENSE_NB;
+#pragma unroll
+    for (int k = 0; k < DENSE_NB; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(wv[k], wv[k + 1]);
+}
+void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf,
+                       cudaStream_t s) {
+    const int rows = n - kb - bw;
+    if (rows <= 0) return;
+    dense_trsm_kernel<<<cdiv(rows, 128), 128, 0, s>>>(A, ld, n, kb, bw, Dinv, diagW, Wbuf);
+    COUNT_LAUNCH();
+}
+
+// trailing update  A(i,j) -= sum_k L(i,kb+k) * W(j,k)  for i >= j >= kb+bw  on the FP64 tensor pipe.
+// CTA tile 64x64, 4 warps x (32x32), K = 32 (one block column); operands staged in shared memory (stride 36
+// doubles => the m8n8k4 fragment loads are bank-conflict free).
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+constexpr int SY_T = 64, SY_LD = 36;
+__global__ void __launch_bounds__(128) dense_syrk_kernel(double* A, int ld, int n, int kb, int bw, const double* __restrict__ Wbuf) {
+    const int t0 = kb + bw;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int i0 = t0 + bi * SY_T, j0 = t0 + bj * SY_T;
+    __shared__ double As[SY_T * SY_LD];
+    __shared__ double Bs[SY_T * SY_LD];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < SY_T * DENSE_NB; idx += 128) {
+        const int r = idx / DENSE_NB, k = idx - r * DENSE_NB;
+        const int gi = i0 + r, gj = j0 + r;
+        As[r * SY_LD + k] = (gi < n && k < bw) ? A[(int64_t)gi * ld + kb + k] : 0.0;
+        Bs[r * SY_LD + k] = (gj < n && k < bw) ? Wbuf[(int64_t)gj * DENSE_NB + k] : 0.0;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < DENSE_NB; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) af[a] = As[(wr + a * 8 + lr) * SY_LD + k0 + lk];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = Bs[(wc + b * 8 + lr) * SY_LD + k0 + lk];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int gi = i0 + wr + a * 8 + lr;
+            const int gj = j0 + wc + b * 8 + lk * 2;
+            if (gi < n) {
+                if (gj <= gi) A[(int64_t)gi * ld + gj] -= acc[a][b][0];
+                if (gj + 1 <= gi) A[(int64_t)gi * ld + gj + 1] -= acc[a][b][1];
+            }
+        }
+}
+void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s) {
+    const int rows = n - kb - bw;
+    if (rows <= 0) return;
+    const int nt = cdiv(rows, SY_T);
+    dense_syrk_kernel<<<dim3(nt, nt), 128, 0, s>>>(A, ld, n, kb, bw, Wbuf);
+    COUNT_LAUNCH();
+}
+
+// forward / diagonal / backward solve with the dense factors, one CTA per right-hand side
+constexpr int DS_T = 1024;
+__global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restrict__ A, int ld, int n,
+                                                           const double* __restrict__ Dinv, double* xall, int64_t xstride) {
+    __shared__ double xs[DENSE_NB];
+    __shared__ double red[DS_T / 32][DENSE_NB + 1];
+    double* x = xall + (int64_t)blockIdx.x * xstride;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned full = 0xffffffffu;
+    const int nwarps = DS_T / 32;
+    // ---- forward: L y = b ----
+    for (int kb = 0; kb < n; kb += DENSE_NB) {
+        const int bw = min(DENSE_NB, n - kb);
+        if (warp == 0) {
+            double t = (lane < bw) ? x[kb + lane] : 0.0;
+            for (int k = 0; k < bw; ++k) {
+                const double xk = __shfl_sync(full, t, k);
+                if (lane > k && lane < bw) t -= A[(int64_t)(kb + lane) * ld + kb + k] * xk;
+            }
+            if (lane < bw) x[kb + lane] = t;
+            xs[lane] = (lane < bw) ? t : 0.0;
+        }
+        __syncthreads();
+        for (int r = kb + bw + warp; r < n; r += nwarps) {
+            double v = (lane < bw) ? A[(int64_t)r * ld + kb + lane] * xs[lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            if (lane == 0) x[r] -= v;
+        }
+        __syncthreads();
+    }
+    // ---- diagonal ----
+    for (int i = tid; i < n; i += DS_T) x[i] *= Dinv[i];
+    __syncthreads();
+    // ---- backward: L^T x = y ----
+    const int nblk = (n + DENSE_NB - 1) / DENSE_NB;
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int kb = b * DENSE_NB;
+        const int bw = min(DENSE_NB, n - kb);
+        double acc = 0.0;
+        for (int r = kb + bw + warp; r < n; r += nwarps)
+            if (lane < bw) acc = fma(A[(int64_t)r * ld + kb + lane], x[r], acc);
+        red[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double s = 0.0;
+            for (int q = 0; q < nwarps; ++q) s += red[q][lane];
+            double t = (lane < bw) ? x[kb + lane] - s : 0.0;
+            for (int k = bw - 1; k >= 0; --k) {
+                const double xk = __shfl_sync(full, t, k);
+                if (lane < k) t -= A[(int64_t)(kb + k) * ld + kb + lane] * xk;
+            }
+            if (lane < bw) x[kb + lane] = t;
+        }
+        __syncthreads();
+    }
+}
+void launch_dense_solve(const double* A, int ld, int n, const double* Dinv, double* x, int nrhs, int64_t xstride, cudaStream_t s) {
+    if (n <= 0 || nrhs <= 0) return;
+    dense_solve_kernel<<<nrhs, DS_T, 0, s>>>(A, ld, n, Dinv, x, xstride);
+    COUNT_LAUNCH();
+}
+
+// =====================================================================================================
+// small helpers
+// =====================================================================================================
+__global__ void csr_mult_kernel(int m, const int* __restrict__ krow, const int* __restrict__ jcol, const double* __restrict__ val,
+                                double alpha, const double* __restrict__ x, double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double acc = 0.0;
+    for (int p = krow[r]; p < krow[r + 1]; ++p) acc = fma(val[p], x[jcol[p]], acc);
+    y[r] += alpha * acc;
+}
+__global__ void csr_tmult_kernel(int m, const int* __restrict__ krow, const int* __restrict__ jcol, const double* __restrict__ val,
+                                 double alpha, const double* __restrict__ x, double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const double xr = alpha * x[r];
+    for (int p = krow[r]; p < krow[r + 1]; ++p) atomicAdd(&y[jcol[p]], val[p] * xr);
+}
+void launch_csr_mult(int m, const int* krow, const int* jcol, const double* val, double alpha, const double* x, double* y, cudaStream_t s) {
+    if (m <= 0) return;
+    csr_mult_kernel<<<cdiv(m, 128), 128, 0, s>>>(m, krow, jcol, val, alpha, x, y);
+    COUNT_LAUNCH();
+}
+void launch_csr_tmult(int m, const int* krow, const int* jcol, const double* val, double alpha, const double* x, double* y, cudaStream_t s) {
+    if (m <= 0) return;
+    csr_tmult_kernel<<<cdiv(m, 128), 128, 0, s>>>(m, krow, jcol, val, alpha, x, y);
+    COUNT_LAUNCH();
+}
+__global__ void vec_div_kernel(double* x, const double* __restrict__ d, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] /= d[i];
+}
+void launch_vec_div(double* x, const double* d, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    vec_div_kernel<<<cdiv(n, 128), 128, 0, s>>>(x, d, n);
+    COUNT_LAUNCH();
+}
+void launch_vec_copy(double* dst, const double* src, int n, cudaStream_t s) {
+    if (n > 0) cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, s);
+}
+void launch_vec_zero(double* dst, int64_t n, cudaStream_t s) {
+    if (n > 0) cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)n, s);
+}
+
+}  // namespace pipsgpu

@@ -1,0 +1,103 @@
+// Device data layout and kernel launchers of the KKT hot path (sm_100a). See DESIGN.md for the layout rationale.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pipsgpu {
+
+constexpr int MAXW = 32;         // maximum front width (pivot columns); symbolic analysis splits wider supernodes
+constexpr int DENSE_NB = 32;     // block size of the dense root LDL^T
+
+// One front (supernode) of one scenario block. All offsets index context-wide pools.
+struct FrontDesc {
+    int64_t Loff;      // panel: m x w column-major (ld = m), rows = [pivot cols | ancestor rows | border rows]
+    int64_t Coff;      // contribution block: (na+nb) x na column-major (ld = na+nb), lower trapezoid
+    int64_t rows_off;  // into rowg / relidx (na+nb entries)
+    int64_t Woff;      // per-level scratch: W21 = L21*D, (na+nb) rows, row-major with stride wp(w)
+    int64_t upd_off;   // solve-phase update vector (na entries)
+    int w, na, nb;
+    int col0;          // global position of the first pivot column
+    int child_begin, child_end;   // into child_list (global front ids)
+    int leaf;
+    int parent;
+};
+
+struct LeafDev {
+    double eps;       // absolute pivot perturbation threshold (1e-8 * ||K||)
+    int pos_off;      // first global position of this leaf
+    int n;
+};
+
+__host__ __device__ inline int padded_width(int w) { return w <= 8 ? 8 : (w <= 16 ? 16 : 32); }
+
+struct FactorArgs {
+    const FrontDesc* fronts;
+    const int* level_fronts;     // front ids grouped by level, deepest level first
+    const int* child_list;
+    const int* rowg;             // per front row: global position (non-border) or Schur-complement index (border)
+    const int* relidx;           // per front row: local row index in the parent front
+    const int8_t* ptype;
+    const int8_t* sgn;
+    const LeafDev* leaves;
+    double* L;
+    double* C;
+    double* W;                   // per-level scratch
+    double* Dd; double* De;      // D      (diagonal / coupling to the next position for 2x2 pivots)
+    double* Did; double* Die;    // D^-1
+    double* SC;                  // dense Schur complement, lower, row-major (may be null)
+    int ldsc;
+    int* stats;                  // per leaf: {positive, negative, zero, perturbed}
+};
+
+struct SolveArgs {
+    const FrontDesc* fronts;
+    const int* level_fronts;
+    const int* child_list;
+    const int* rowg;
+    const int* relidx;
+    const int8_t* ptype;
+    const double* L;
+    const double* Did; const double* Die;
+    double* x;        // permuted right-hand sides, nrhs x x_stride
+    double* upd;      // update vectors, nrhs x upd_stride
+    int64_t x_stride, upd_stride;
+};
+
+// ---- leaf path ----
+void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
+void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
+void launch_front_factor(const FactorArgs& a, int level_begin, int nfronts, cudaStream_t s);
+void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
+void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
+void launch_fwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s);
+void launch_bwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s);
+void launch_diag_solve(const SolveArgs& a, int64_t npos, int nrhs, cudaStream_t s);
+// b0[bidx[k]] -= val[k] * z[brow[k]]   /   t[brow[k]] += val[k] * u[bidx[k]]
+void launch_border_tmult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* z, double* b0, cudaStream_t s);
+void launch_border_mult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* u, double* t, cudaStream_t s);
+void launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t s);
+
+// ---- dense root path (lower triangle, row-major, ld = n) ----
+void launch_sc_add_sparse(double* SC, int ld, int row0, int col0, int m, const int* krow, const int* jcol, const double* val, double alpha, cudaStream_t s);
+void launch_sc_add_diag(double* SC, int ld, int off, int n, const double* d, double alpha, cudaStream_t s);
+// SC[0:n0,0:n0] (lower) -= C^T diag(1/zdiag) C   for CSR C (mz x n0)
+void launch_sc_add_ctdc(double* SC, int ld, int mz, const int* krow, const int* jcol, const double* val, const double* zdiag, cudaStream_t s);
+void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* buf, bool unpack, double* SCout, cudaStream_t s);
+int64_t sc_pack_size(int n0, int nl);
+// one block column of the right-looking LDL^T; n0 = number of leading (positive) indices
+void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps, double* D, double* Dinv, double* diagW, int* stats, cudaStream_t s);
+void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf, cudaStream_t s);
+void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s);
+void launch_dense_solve(const double* A, int ld, int n, const double* Dinv, double* x, int nrhs, int64_t xstride, cudaStream_t s);
+
+// ---- small vector / CSR helpers for the root-level solve ----
+void launch_csr_mult(int m, const int* krow, const int* jcol, const double* val, double alpha, const double* x, double* y, cudaStream_t s);    // y += alpha*A x
+void launch_csr_tmult(int m, const int* krow, const int* jcol, const double* val, double alpha, const double* x, double* y, cudaStream_t s);   // y += alpha*A^T x
+void launch_vec_div(double* x, const double* d, int n, cudaStream_t s);   // x /= d
+void launch_vec_copy(double* dst, const double* src, int n, cudaStream_t s);
+void launch_vec_zero(double* dst, int64_t n, cudaStream_t s);
+
+int64_t kernel_launch_count();
+
+}  // namespace pipsgpu

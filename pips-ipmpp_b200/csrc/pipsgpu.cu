@@ -1,0 +1,1097 @@
+// C-ABI implementation (include/pipsgpu.h): context / leaf / Schur-complement / kkt objects on top of kernels.cu.
+// Host orchestration mirrors the reference's call stack: factor2 -> leaf LDL^T + Schur terms ->
+// reduceKKT -> finalizeKKT -> factorizeKKT, and solveCompressed = Lsolve; Dsolve; Ltsolve - but batched over all
+// scenario blocks of the GPU and stream-ordered, with the operands resident in HBM.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/pipsgpu.h"
+#include "common.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+#include "symbolic.h"
+
+using namespace pipsgpu;
+
+#define CUDA_CHECK(expr)                                                                                          \
+    do {                                                                                                          \
+        cudaError_t _e = (expr);                                                                                  \
+        if (_e != cudaSuccess)                                                                                    \
+            throw pipsgpu::Error(PIPSGPU_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e));    \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count > 0) CUDA_CHECK(cudaMalloc(&p, sizeof(T) * count));
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+    void upload(const std::vector<T>& v, cudaStream_t s) {
+        alloc(v.size());
+        if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+    }
+};
+
+struct CsrDev {
+    int m = 0, n = 0;
+    int64_t nnz = 0;
+    DevBuf<int> krow, jcol;
+    DevBuf<double> val;
+    void upload(int m_, int n_, const int* kr, const int* jc, const double* v, cudaStream_t s) {
+        m = m_; n = n_;
+        std::vector<int> k(m + 1, 0);
+        if (kr && m > 0) std::copy(kr, kr + m + 1, k.begin());
+        nnz = k[m];
+        krow.upload(k, s);
+        std::vector<int> j(jc ? jc : nullptr, jc ? jc + nnz : nullptr);
+        std::vector<double> vv(v ? v : nullptr, v ? v + nnz : nullptr);
+        if ((int64_t)j.size() != nnz || (int64_t)vv.size() != nnz) { j.assign(nnz, 0); vv.assign(nnz, 0.0); }
+        jcol.upload(j, s);
+        val.upload(vv, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init() {
+        if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    }
+    ~Timer() {
+        if (a) { cudaEventDestroy(a); cudaEventDestroy(b); }
+    }
+};
+
+}  // namespace
+
+// ============================================================================================================
+// objects
+// ============================================================================================================
+struct pipsgpu_leaf {
+    pipsgpu_ctx* ctx = nullptr;
+    int index = -1;
+    int n = 0, nx = 0, ny = 0, nz = 0;
+    std::vector<int> krow, jcol;
+    std::vector<double> val;
+    std::vector<int> diag_entry;     // per row: index of the diagonal entry in val
+    // border
+    int n0 = 0, my0 = 0, myl = 0, mzl = 0, nB = 0;
+    std::vector<int> brow, bcol;
+    std::vector<double> bval;
+    bool border_set = false;
+    // symbolic
+    LeafSymbolic S;
+    bool analyzed = false;
+    double knorm = 1.0;
+    // placement in the context pools (valid after commit)
+    int pos_off = 0;
+    int64_t Lbase = 0, Lsize = 0, Cbase = 0, Csize = 0, kval_off = 0, bval_off = 0, upd_base = 0, upd_size = 0;
+    int front_base = 0;
+    std::vector<int> level_begin, level_count;   // per global level: sub-range of level_fronts owned by this leaf
+    int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double flops = 0;
+    int inertia[3] = {0, 0, 0};
+    int n_perturbed = 0;
+    bool factorized = false;
+};
+
+struct pipsgpu_sc {
+    pipsgpu_ctx* ctx = nullptr;
+    int n0 = 0, my0 = 0, myl = 0, mzl = 0, n = 0;
+    DevBuf<double> A;        // assembled matrix, n x n row-major, lower triangle used (owned by the linear system)
+    DevBuf<double> Fm;       // the solver's own copy, overwritten by the factors (DeSymIndefSolver.C:65 copies too)
+    DevBuf<double> D, Dinv, diagW, Wbuf, pack, rhs;
+    DevBuf<int> stats;
+    bool factorized = false;
+    int inertia[3] = {0, 0, 0};
+    int n_perturbed = 0;
+};
+
+struct pipsgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<pipsgpu_leaf*> leaves;
+    bool committed = false;
+    NcclComm comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // pools
+    int64_t npos = 0, nfronts = 0, Ltot = 0, Ctot = 0, Wtot = 0, updtot = 0, nnzK = 0, nnzB = 0;
+    int nlevels = 0;
+    std::vector<int> level_ptr;     // nlevels+1 into level_fronts, deepest level first: order[0] = deepest
+    DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
+    DevBuf<int> rowg, relidx, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
+    DevBuf<int8_t> ptype, sgn;
+    DevBuf<FrontDesc> fronts;
+    DevBuf<LeafDev> leafdev;
+    DevBuf<int64_t> kmap, bmap, diagpos;
+    std::vector<double> h_dvals;
+
+    FactorArgs factor_args(pipsgpu_sc* sc) {
+        FactorArgs a;
+        a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p;
+        a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p; a.W = W.p;
+        a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
+        a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p;
+        return a;
+    }
+    SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
+        SolveArgs a;
+        a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p;
+        a.relidx = relidx.p; a.ptype = ptype.p; a.L = L.p; a.Did = Did.p; a.Die = Die.p;
+        a.x = xbuf; a.upd = updbuf; a.x_stride = xstride; a.upd_stride = updstride;
+        return a;
+    }
+};
+
+struct pipsgpu_kkt {
+    pipsgpu_ctx* ctx = nullptr;
+    int n0 = 0, my0 = 0, mz0 = 0, myl = 0, mzl = 0;
+    CsrDev A0, C0, F0, G0;
+    std::vector<pipsgpu_leaf*> leaves;
+    std::unique_ptr<pipsgpu_sc> sc;
+    bool ready = false;
+    DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl;
+    int64_t sum_nx = 0, sum_nz = 0, sum_n = 0;
+    double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[12] = {};
+    bool ev_init = false;
+};
+
+namespace {
+
+void require_device(pipsgpu_ctx* ctx) {
+    if (!ctx) throw Error(PIPSGPU_ERR_INVALID, "null context");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+}
+
+void analyze_one(pipsgpu_leaf* lf) {
+    if (lf->analyzed) return;
+    SymbolicOptions opt;
+    opt.max_width = MAXW;
+    analyze_leaf(lf->n, lf->nx, lf->ny, lf->nz, lf->krow.data(), lf->jcol.data(), lf->val.data(), lf->nB,
+                 (int64_t)lf->brow.size(), lf->brow.data(), lf->bcol.data(), opt, lf->S);
+    double kn = 0.0;
+    for (int i = 0; i < lf->n; ++i)
+        for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p)
+            if (lf->jcol[p] != i) kn = std::max(kn, std::fabs(lf->val[p]));
+    lf->knorm = std::max(kn, 1.0);
+    lf->analyzed = true;
+}
+
+// ---- batched leaf solve on the context buffers: x (permuted order) <- K^-1 x for the leaves in [range of levels] ----
+void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_leaf* only, int64_t npos_range_begin,
+                    int64_t npos_range_count) {
+    cudaStream_t s = ctx->stream;
+    for (int lv = 0; lv < ctx->nlevels; ++lv) {   // order index 0 = deepest level
+        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
+        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
+        launch_fwd_level(sa, begin, count, nrhs, s);
+    }
+    {
+        SolveArgs d = sa;
+        // diag kernel indexes positions from 0: shift the base pointers to the requested range
+        d.x = sa.x + npos_range_begin;
+        d.ptype = sa.ptype + npos_range_begin;
+        d.Did = sa.Did + npos_range_begin;
+        d.Die = sa.Die + npos_range_begin;
+        launch_diag_solve(d, npos_range_count, nrhs, s);
+    }
+    for (int lv = ctx->nlevels - 1; lv >= 0; --lv) {
+        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
+        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
+        launch_bwd_level(sa, begin, count, nrhs, s);
+    }
+}
+
+void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
+    cudaStream_t s = ctx->stream;
+    FactorArgs fa = ctx->factor_args(sc);
+    for (int lv = 0; lv < ctx->nlevels; ++lv) {
+        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
+        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
+        launch_front_factor(fa, begin, count, s);
+    }
+}
+
+void fetch_leaf_stats(pipsgpu_ctx* ctx) {
+    std::vector<int> h(4 * ctx->leaves.size());
+    if (h.empty()) return;
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), ctx->stats.p, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->leaves.size(); ++i) {
+        pipsgpu_leaf* lf = ctx->leaves[i];
+        lf->inertia[0] = h[4 * i]; lf->inertia[1] = h[4 * i + 1]; lf->inertia[2] = h[4 * i + 2];
+        lf->n_perturbed = h[4 * i + 3];
+    }
+}
+
+void sc_factorize_impl(pipsgpu_sc* sc) {
+    pipsgpu_ctx* ctx = sc->ctx;
+    cudaStream_t s = ctx->stream;
+    const int n = sc->n;
+    CUDA_CHECK(cudaMemsetAsync(sc->stats.p, 0, sizeof(int) * 4, s));
+    // perturbation threshold relative to the largest diagonal magnitude is not known on the host; use 1e-8 (entries
+    // of the scaled KKT system are O(1), Utilities/pipsdef.h pips_eps = 1e-13 is far below)
+    const double eps = 1e-10;
+    const int npos_expected = sc->n0;
+    CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+    for (int kb = 0; kb < n; kb += DENSE_NB) {
+        const int bw = std::min(DENSE_NB, n - kb);
+        launch_dense_diag(sc->Fm.p, n, kb, bw, npos_expected, eps, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
+        launch_dense_trsm(sc->Fm.p, n, n, kb, bw, sc->Dinv.p, sc->diagW.p, sc->Wbuf.p, s);
+        launch_dense_syrk(sc->Fm.p, n, n, kb, bw, sc->Wbuf.p, s);
+    }
+    sc->factorized = true;
+}
+
+void sc_fetch_stats(pipsgpu_sc* sc) {
+    int h[4];
+    CUDA_CHECK(cudaMemcpyAsync(h, sc->stats.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, sc->ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    sc->inertia[0] = h[0]; sc->inertia[1] = h[1]; sc->inertia[2] = h[2]; sc->n_perturbed = h[3];
+}
+
+void sc_allreduce_impl(pipsgpu_sc* sc) {
+    pipsgpu_ctx* ctx = sc->ctx;
+    if (!ctx->comm || ctx->nranks <= 1) return;
+    const int nl = sc->myl + sc->mzl;
+    const int64_t cnt = sc_pack_size(sc->n0, nl);
+    sc->pack.ensure((size_t)cnt);
+    launch_sc_pack(sc->A.p, sc->n, sc->n0, sc->my0, nl, sc->pack.p, false, nullptr, ctx->stream);
+    NcclApi& api = NcclApi::get();
+    const int rc = api.AllReduce(sc->pack.p, sc->pack.p, (size_t)cnt, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+    if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce: ") + api.GetErrorString(rc));
+    launch_sc_pack(nullptr, sc->n, sc->n0, sc->my0, nl, sc->pack.p, true, sc->A.p, ctx->stream);
+}
+
+}  // namespace
+
+// ============================================================================================================
+// C ABI
+// ============================================================================================================
+extern "C" {
+
+int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
+    PIPSGPU_TRY
+    if (!out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_ctx_create: null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        throw Error(PIPSGPU_ERR_NO_DEVICE, "pipsgpu_ctx_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_ctx_create: invalid device index");
+    CUDA_CHECK(cudaSetDevice(device));
+    auto ctx = std::make_unique<pipsgpu_ctx>();
+    ctx->device = device;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx.release();
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx) {
+    PIPSGPU_TRY
+    if (!ctx) return PIPSGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) NcclApi::get().CommDestroy(ctx->comm);
+    for (auto* lf : ctx->leaves) delete lf;
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_synchronize(pipsgpu_ctx* ctx) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    PIPSGPU_CATCH
+}
+
+int64_t pipsgpu_ctx_launch_count(pipsgpu_ctx*) { return kernel_launch_count(); }
+
+int pipsgpu_nccl_unique_id(char id[128]) {
+    PIPSGPU_TRY
+    NcclApi& api = NcclApi::get();
+    if (!api.ok) throw Error(PIPSGPU_ERR_NCCL, api.err);
+    NcclUniqueId uid;
+    const int rc = api.GetUniqueId(&uid);
+    if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
+    std::memcpy(id, uid.internal, 128);
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_init_comm(pipsgpu_ctx* ctx, const char id[128], int rank, int nranks) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    NcclApi& api = NcclApi::get();
+    if (!api.ok) throw Error(PIPSGPU_ERR_NCCL, api.err);
+    NcclUniqueId uid;
+    std::memcpy(uid.internal, id, 128);
+    const int rc = api.CommInitRank(&ctx->comm, nranks, uid, rank);
+    if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    PIPSGPU_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// leaf
+// ------------------------------------------------------------------------------------------------------------
+int pipsgpu_leaf_create(pipsgpu_ctx* ctx, int n, int nx, int ny, int nz, const int* krow, const int* jcol, const double* val,
+                        pipsgpu_leaf** out) {
+    PIPSGPU_TRY
+    if (!ctx || !krow || !jcol || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_create: null argument");
+    if (ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_create: context already committed");
+    if (n < 0 || nx + ny + nz != n) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_create: nx+ny+nz != n");
+    auto lf = std::make_unique<pipsgpu_leaf>();
+    lf->ctx = ctx; lf->n = n; lf->nx = nx; lf->ny = ny; lf->nz = nz;
+    lf->krow.assign(krow, krow + n + 1);
+    const int64_t nnz = krow[n];
+    lf->jcol.assign(jcol, jcol + nnz);
+    if (val) lf->val.assign(val, val + nnz); else lf->val.assign(nnz, 0.0);
+    lf->diag_entry.assign(n, -1);
+    for (int i = 0; i < n; ++i)
+        for (int p = krow[i]; p < krow[i + 1]; ++p) {
+            if (jcol[p] > i) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_create: matrix must be lower triangular CSR");
+            if (jcol[p] == i) lf->diag_entry[i] = p;
+        }
+    for (int i = 0; i < n; ++i)
+        if (lf->diag_entry[i] < 0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_create: every diagonal entry must be stored");
+    lf->index = (int)ctx->leaves.size();
+    ctx->leaves.push_back(lf.get());
+    *out = lf.release();
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_set_border(pipsgpu_leaf* lf, int n0, int my0, int myl, int mzl, const int* A_krow, const int* A_jcol,
+                            const double* A_val, const int* C_krow, const int* C_jcol, const double* C_val, const int* F_krow,
+                            const int* F_jcol, const double* F_val, const int* G_krow, const int* G_jcol, const double* G_val) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_set_border: null leaf");
+    if (lf->analyzed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_set_border: leaf already analyzed");
+    lf->n0 = n0; lf->my0 = my0; lf->myl = myl; lf->mzl = mzl;
+    lf->nB = n0 + myl + mzl;
+    lf->brow.clear(); lf->bcol.clear(); lf->bval.clear();
+    auto add = [&](int r, int b, double v) { lf->brow.push_back(r); lf->bcol.push_back(b); lf->bval.push_back(v); };
+    if (A_krow)   // rows of A live in the y-part of K, columns are linking variables
+        for (int r = 0; r < lf->ny; ++r)
+            for (int p = A_krow[r]; p < A_krow[r + 1]; ++p) {
+                if (A_jcol[p] < 0 || A_jcol[p] >= n0) throw Error(PIPSGPU_ERR_INVALID, "border A: column out of range");
+                add(lf->nx + r, A_jcol[p], A_val[p]);
+            }
+    if (C_krow)
+        for (int r = 0; r < lf->nz; ++r)
+            for (int p = C_krow[r]; p < C_krow[r + 1]; ++p) {
+                if (C_jcol[p] < 0 || C_jcol[p] >= n0) throw Error(PIPSGPU_ERR_INVALID, "border C: column out of range");
+                add(lf->nx + lf->ny + r, C_jcol[p], C_val[p]);
+            }
+    if (F_krow)   // F^T: border column n0+j has the entries of row j of F, living in the x-part of K
+        for (int j = 0; j < myl; ++j)
+            for (int p = F_krow[j]; p < F_krow[j + 1]; ++p) {
+                if (F_jcol[p] < 0 || F_jcol[p] >= lf->nx) throw Error(PIPSGPU_ERR_INVALID, "border F: column out of range");
+                add(F_jcol[p], n0 + j, F_val[p]);
+            }
+    if (G_krow)
+        for (int j = 0; j < mzl; ++j)
+            for (int p = G_krow[j]; p < G_krow[j + 1]; ++p) {
+                if (G_jcol[p] < 0 || G_jcol[p] >= lf->nx) throw Error(PIPSGPU_ERR_INVALID, "border G: column out of range");
+                add(G_jcol[p], n0 + myl + j, G_val[p]);
+            }
+    lf->border_set = true;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_analyze(pipsgpu_leaf* lf) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_analyze: null leaf");
+    analyze_one(lf);
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_ctx_commit: already committed");
+    const int nl = (int)ctx->leaves.size();
+    // ---- symbolic analysis of all leaves on host threads ----
+    {
+        int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, nl));
+        std::atomic<int> next{0};
+        std::mutex emu;
+        std::string err;
+        auto work = [&]() {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= nl) break;
+                try {
+                    analyze_one(ctx->leaves[i]);
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> g(emu);
+                    err = e.what();
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (!err.empty()) throw Error(PIPSGPU_ERR_INVALID, "symbolic analysis failed: " + err);
+    }
+    // ---- placement ----
+    int64_t npos = 0, nfr = 0, Ltot = 0, Ctot = 0, updtot = 0, nnzK = 0, nnzB = 0, nrows = 0, nchild = 0;
+    int nlev = 0;
+    for (auto* lf : ctx->leaves) {
+        const LeafSymbolic& S = lf->S;
+        lf->pos_off = (int)npos; lf->front_base = (int)nfr;
+        lf->Lbase = Ltot; lf->Lsize = S.Loff.empty() ? 0 : S.Loff.back();
+        lf->Cbase = Ctot; lf->Csize = S.Coff.empty() ? 0 : S.Coff.back();
+        lf->kval_off = nnzK; lf->bval_off = nnzB; lf->upd_base = updtot;
+        int64_t us = 0;
+        for (int s = 0; s < S.ns; ++s) us += S.sn_na[s];
+        lf->upd_size = us;
+        npos += lf->n; nfr += S.ns; Ltot += lf->Lsize; Ctot += lf->Csize; updtot += us;
+        nnzK += (int64_t)lf->val.size(); nnzB += (int64_t)lf->bval.size();
+        nrows += (int64_t)S.rowidx.size(); nchild += (int64_t)S.child_idx.size();
+        nlev = std::max(nlev, S.nlevels);
+        if (npos > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "too many KKT rows for one context (int32 positions)");
+    }
+    ctx->npos = npos; ctx->nfronts = nfr; ctx->Ltot = Ltot; ctx->Ctot = Ctot; ctx->updtot = updtot;
+    ctx->nnzK = nnzK; ctx->nnzB = nnzB; ctx->nlevels = nlev;
+
+    std::vector<FrontDesc> fronts((size_t)nfr);
+    std::vector<int> rowg((size_t)nrows), relidx((size_t)nrows), child_list((size_t)nchild), gidx((size_t)npos);
+    std::vector<int8_t> ptype((size_t)npos), sgn((size_t)npos);
+    std::vector<int64_t> kmap((size_t)nnzK), bmap((size_t)nnzB), diagpos((size_t)npos);
+    std::vector<double> kval((size_t)nnzK), bval((size_t)nnzB);
+    std::vector<int> bg_row((size_t)nnzB), bg_sc((size_t)nnzB), bg_b0((size_t)nnzB);
+    std::vector<LeafDev> leafdev((size_t)nl);
+    // level lists: order index 0 = deepest level; within a level fronts are grouped by leaf
+    std::vector<int> level_count(nlev, 0);
+    for (auto* lf : ctx->leaves)
+        for (int s = 0; s < lf->S.ns; ++s) ++level_count[nlev - 1 - lf->S.sn_level[s]];
+    ctx->level_ptr.assign(nlev + 1, 0);
+    for (int l = 0; l < nlev; ++l) ctx->level_ptr[l + 1] = ctx->level_ptr[l] + level_count[l];
+    std::vector<int> level_fronts((size_t)nfr), lfill(ctx->level_ptr.begin(), ctx->level_ptr.end() - 1);
+    std::vector<int64_t> wfill(nlev, 0);
+
+    int64_t rows_off = 0, child_off = 0;
+    for (auto* lf : ctx->leaves) {
+        const LeafSymbolic& S = lf->S;
+        lf->level_begin.assign(nlev, 0); lf->level_count.assign(nlev, 0);
+        for (int l = 0; l < nlev; ++l) lf->level_begin[l] = lfill[l];
+        auto b2sc = [&](int b) { return b < lf->n0 ? b : b + lf->my0; };
+        int64_t upd = lf->upd_base;
+        for (int s = 0; s < S.ns; ++s) {
+            FrontDesc& fd = fronts[(size_t)lf->front_base + s];
+            fd.w = S.sn_col[s + 1] - S.sn_col[s]; fd.na = S.sn_na[s]; fd.nb = S.sn_nb[s];
+            fd.Loff = lf->Lbase + S.Loff[s]; fd.Coff = lf->Cbase + S.Coff[s];
+            fd.rows_off = rows_off + S.sn_rowptr[s];
+            fd.col0 = lf->pos_off + S.sn_col[s];
+            fd.child_begin = (int)(child_off + S.child_ptr[s]); fd.child_end = (int)(child_off + S.child_ptr[s + 1]);
+            fd.leaf = lf->index;
+            fd.parent = S.sn_parent[s] < 0 ? -1 : lf->front_base + S.sn_parent[s];
+            fd.upd_off = upd; upd += fd.na;
+            const int ol = nlev - 1 - S.sn_level[s];
+            level_fronts[(size_t)lfill[ol]++] = lf->front_base + s;
+            ++lf->level_count[ol];
+            fd.Woff = wfill[ol];
+            int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
+            wfill[ol] += (wsz + 1) & ~int64_t(1);
+        }
+        for (size_t t = 0; t < S.rowidx.size(); ++t) {
+            const int r = S.rowidx[t];
+            rowg[(size_t)rows_off + t] = (r < lf->n) ? lf->pos_off + r : b2sc(r - lf->n);
+            relidx[(size_t)rows_off + t] = S.relidx[t];
+        }
+        for (size_t t = 0; t < S.child_idx.size(); ++t) child_list[(size_t)child_off + t] = lf->front_base + S.child_idx[t];
+        for (int p = 0; p < lf->n; ++p) {
+            gidx[(size_t)lf->pos_off + p] = lf->pos_off + S.perm[p];
+            ptype[(size_t)lf->pos_off + p] = S.ptype[p];
+            sgn[(size_t)lf->pos_off + p] = S.sgn[p];
+            diagpos[(size_t)lf->pos_off + p] = lf->kval_off + lf->diag_entry[p];
+        }
+        for (size_t e = 0; e < lf->val.size(); ++e) {
+            kmap[(size_t)lf->kval_off + e] = lf->Lbase + S.kmap[e];
+            kval[(size_t)lf->kval_off + e] = lf->val[e];
+        }
+        const int b0tail = lf->n0 + lf->my0;   // b0 layout [x0;y0;z0;yl;zl]: filled in by the kkt (needs mz0)
+        (void)b0tail;
+        for (size_t e = 0; e < lf->bval.size(); ++e) {
+            bmap[(size_t)lf->bval_off + e] = lf->Lbase + S.bmap[e];
+            bval[(size_t)lf->bval_off + e] = lf->bval[e];
+            bg_row[(size_t)lf->bval_off + e] = lf->pos_off + lf->brow[e];
+            bg_sc[(size_t)lf->bval_off + e] = b2sc(lf->bcol[e]);
+            bg_b0[(size_t)lf->bval_off + e] = lf->bcol[e];   // border index; the kkt remaps to the b0 layout
+        }
+        leafdev[(size_t)lf->index].eps = 1e-8 * lf->knorm;
+        leafdev[(size_t)lf->index].pos_off = lf->pos_off;
+        leafdev[(size_t)lf->index].n = lf->n;
+        // statistics kept on the host
+        int64_t stored = lf->Lsize;
+        lf->stats8[0] = S.nnzL; lf->stats8[1] = S.nnzL_border; lf->stats8[2] = stored; lf->stats8[3] = S.ns;
+        lf->stats8[4] = S.nlevels; lf->stats8[5] = S.n_pairs; lf->stats8[6] = S.max_m; lf->stats8[7] = lf->Csize;
+        lf->flops = S.flops_factor;
+        rows_off += (int64_t)S.rowidx.size();
+        child_off += (int64_t)S.child_idx.size();
+        // the symbolic arrays are now on their way to the device; drop the big host copies
+        LeafSymbolic& Sm = lf->S;
+        std::vector<int>().swap(Sm.rowidx); std::vector<int>().swap(Sm.relidx);
+        std::vector<int64_t>().swap(Sm.kmap); std::vector<int64_t>().swap(Sm.bmap);
+    }
+    ctx->Wtot = 0;
+    for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
+
+    cudaStream_t s = ctx->stream;
+    ctx->fronts.upload(fronts, s); ctx->rowg.upload(rowg, s); ctx->relidx.upload(relidx, s);
+    ctx->child_list.upload(child_list, s); ctx->level_fronts.upload(level_fronts, s); ctx->gidx.upload(gidx, s);
+    ctx->ptype.upload(ptype, s); ctx->sgn.upload(sgn, s); ctx->kmap.upload(kmap, s); ctx->bmap.upload(bmap, s);
+    ctx->diagpos.upload(diagpos, s); ctx->Kval.upload(kval, s); ctx->Bval.upload(bval, s);
+    ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
+    ctx->leafdev.upload(leafdev, s);
+    ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2);
+    ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
+    ctx->Die.alloc((size_t)npos + 1);
+    ctx->x.alloc((size_t)npos + 1); ctx->upd.alloc((size_t)updtot + 1); ctx->dvals.alloc((size_t)npos + 1);
+    ctx->work.alloc((size_t)npos + 1);
+    ctx->stats.alloc((size_t)4 * std::max(nl, 1));
+    CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));
+    CUDA_CHECK(cudaMemsetAsync(ctx->De.p, 0, sizeof(double) * ((size_t)npos + 1), s));
+    ctx->h_dvals.assign((size_t)npos, 0.0);
+    for (auto* lf : ctx->leaves)
+        for (int i = 0; i < lf->n; ++i) ctx->h_dvals[(size_t)lf->pos_off + i] = lf->val[lf->diag_entry[i]];
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    ctx->committed = true;
+    PIPSGPU_CATCH
+}
+
+static void leaf_fill_dvals(pipsgpu_leaf* lf, const double* dd, const double* nomegainv, double regP, double regDy, double regDz) {
+    double* d = lf->ctx->h_dvals.data() + lf->pos_off;
+    for (int i = 0; i < lf->nx; ++i) d[i] = (dd ? dd[i] : 0.0) + regP;
+    for (int i = 0; i < lf->ny; ++i) d[lf->nx + i] = -regDy;
+    for (int i = 0; i < lf->nz; ++i) d[lf->nx + lf->ny + i] = (nomegainv ? nomegainv[i] : 0.0) - regDz;
+}
+
+static void leaf_push_dvals(pipsgpu_ctx* ctx, int64_t pos_begin, int64_t count) {
+    if (count <= 0) return;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->dvals.p + pos_begin, ctx->h_dvals.data() + pos_begin, sizeof(double) * (size_t)count,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    launch_set_diag(ctx->diagpos.p + pos_begin, ctx->dvals.p + pos_begin, count, ctx->Kval.p, ctx->stream);
+}
+
+int pipsgpu_leaf_set_diagonal(pipsgpu_leaf* lf, const double* dd, const double* nomegainv, double regP, double regDy, double regDz) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_set_diagonal: null leaf");
+    pipsgpu_ctx* ctx = lf->ctx;
+    if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_set_diagonal: context not committed");
+    require_device(ctx);
+    leaf_fill_dvals(lf, dd, nomegainv, regP, regDy, regDz);
+    leaf_push_dvals(ctx, lf->pos_off, lf->n);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    lf->factorized = false;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_set_values(pipsgpu_leaf* lf, const double* val) {
+    PIPSGPU_TRY
+    if (!lf || !val) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_set_values: null argument");
+    pipsgpu_ctx* ctx = lf->ctx;
+    if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_set_values: context not committed");
+    require_device(ctx);
+    std::copy(val, val + lf->val.size(), lf->val.begin());
+    for (int i = 0; i < lf->n; ++i) ctx->h_dvals[(size_t)lf->pos_off + i] = lf->val[lf->diag_entry[i]];
+    CUDA_CHECK(cudaMemcpyAsync(ctx->Kval.p + lf->kval_off, lf->val.data(), sizeof(double) * lf->val.size(), cudaMemcpyHostToDevice,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    lf->factorized = false;
+    PIPSGPU_CATCH
+}
+
+static void factor_prepare(pipsgpu_ctx* ctx, pipsgpu_leaf* only) {
+    cudaStream_t s = ctx->stream;
+    if (only) {
+        launch_vec_zero(ctx->L.p + only->Lbase, only->Lsize, s);
+        launch_vec_zero(ctx->C.p + only->Cbase, only->Csize, s);
+        launch_scatter_values(ctx->kmap.p + only->kval_off, ctx->Kval.p + only->kval_off, (int64_t)only->val.size(), ctx->L.p, s);
+        launch_scatter_values(ctx->bmap.p + only->bval_off, ctx->Bval.p + only->bval_off, (int64_t)only->bval.size(), ctx->L.p, s);
+        CUDA_CHECK(cudaMemsetAsync(ctx->stats.p + 4 * only->index, 0, sizeof(int) * 4, s));
+    } else {
+        launch_vec_zero(ctx->L.p, ctx->Ltot, s);
+        launch_vec_zero(ctx->C.p, ctx->Ctot, s);
+        launch_scatter_values(ctx->kmap.p, ctx->Kval.p, ctx->nnzK, ctx->L.p, s);
+        launch_scatter_values(ctx->bmap.p, ctx->Bval.p, ctx->nnzB, ctx->L.p, s);
+        CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(int) * 4 * ctx->leaves.size(), s));
+    }
+}
+
+int pipsgpu_leaf_factorize(pipsgpu_leaf* lf, int inertia[3]) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_factorize: null leaf");
+    pipsgpu_ctx* ctx = lf->ctx;
+    if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_factorize: context not committed");
+    require_device(ctx);
+    factor_prepare(ctx, lf);
+    run_factor_levels(ctx, nullptr, lf);
+    fetch_leaf_stats(ctx);
+    lf->factorized = true;
+    if (inertia) { inertia[0] = lf->inertia[0]; inertia[1] = lf->inertia[1]; inertia[2] = lf->inertia[2]; }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_factorize_leaves(pipsgpu_ctx* ctx, pipsgpu_sc* sc) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_ctx_factorize_leaves: context not committed");
+    factor_prepare(ctx, nullptr);
+    run_factor_levels(ctx, sc, nullptr);
+    fetch_leaf_stats(ctx);
+    for (auto* lf : ctx->leaves) lf->factorized = true;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_add_schur(pipsgpu_leaf* lf, pipsgpu_sc* sc) {
+    PIPSGPU_TRY
+    if (!lf || !sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_add_schur: null argument");
+    pipsgpu_ctx* ctx = lf->ctx;
+    require_device(ctx);
+    // the Schur term is a by-product of the elimination: redo this leaf's numeric phase with the SC attached
+    factor_prepare(ctx, lf);
+    run_factor_levels(ctx, sc, lf);
+    fetch_leaf_stats(ctx);
+    lf->factorized = true;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_solve(pipsgpu_leaf* lf, int nrhs, double* rhs) {
+    PIPSGPU_TRY
+    if (!lf || !rhs) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_solve: null argument");
+    pipsgpu_ctx* ctx = lf->ctx;
+    require_device(ctx);
+    if (!lf->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_solve: leaf not factorized");
+    cudaStream_t s = ctx->stream;
+    const int64_t n = lf->n;
+    const int chunk = 64;
+    DevBuf<double> b, xp, up;
+    b.alloc((size_t)n * chunk); xp.alloc((size_t)n * chunk); up.alloc((size_t)std::max<int64_t>(lf->upd_size, 1) * chunk);
+    DevBuf<int> lg;   // leaf-local permutation indices
+    {
+        std::vector<int> h((size_t)n);
+        for (int64_t p = 0; p < n; ++p) h[(size_t)p] = lf->S.perm[(size_t)p];
+        lg.upload(h, s);
+    }
+    for (int r0 = 0; r0 < nrhs; r0 += chunk) {
+        const int nr = std::min(chunk, nrhs - r0);
+        CUDA_CHECK(cudaMemcpyAsync(b.p, rhs + (size_t)r0 * n, sizeof(double) * (size_t)n * nr, cudaMemcpyHostToDevice, s));
+        launch_gather_perm(lg.p, b.p, xp.p, n, nr, n, s);
+        // kernels index x by global position and upd by global offset: shift the bases so that this leaf's range
+        // lands at the start of the private buffers
+        SolveArgs sa = ctx->solve_args(xp.p - lf->pos_off, n, up.p - lf->upd_base, std::max<int64_t>(lf->upd_size, 1));
+        run_leaf_solve(ctx, sa, nr, lf, lf->pos_off, n);
+        launch_scatter_perm(lg.p, xp.p, b.p, n, nr, n, s);
+        CUDA_CHECK(cudaMemcpyAsync(rhs + (size_t)r0 * n, b.p, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_get_inertia(pipsgpu_leaf* lf, int inertia[3], int* n_perturbed) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_get_inertia: null leaf");
+    if (inertia) { inertia[0] = lf->inertia[0]; inertia[1] = lf->inertia[1]; inertia[2] = lf->inertia[2]; }
+    if (n_perturbed) *n_perturbed = lf->n_perturbed;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_get_stats(pipsgpu_leaf* lf, int64_t out[8], double* flops) {
+    PIPSGPU_TRY
+    if (!lf || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_get_stats: null argument");
+    if (!lf->analyzed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_get_stats: leaf not analyzed");
+    if (lf->ctx->committed) {
+        for (int i = 0; i < 8; ++i) out[i] = lf->stats8[i];
+        if (flops) *flops = lf->flops;
+    } else {
+        const LeafSymbolic& S = lf->S;
+        out[0] = S.nnzL; out[1] = S.nnzL_border; out[2] = S.Loff.empty() ? 0 : S.Loff.back(); out[3] = S.ns;
+        out[4] = S.nlevels; out[5] = S.n_pairs; out[6] = S.max_m; out[7] = S.Coff.empty() ? 0 : S.Coff.back();
+        if (flops) *flops = S.flops_factor;
+    }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_destroy(pipsgpu_leaf*) {
+    // leaves are owned by their context (device pools are shared); destroyed with pipsgpu_ctx_destroy
+    return PIPSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dense Schur complement
+// ------------------------------------------------------------------------------------------------------------
+int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsgpu_sc** out) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (!out || n0 < 0 || my0 < 0 || myl < 0 || mzl < 0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_create: invalid argument");
+    auto sc = std::make_unique<pipsgpu_sc>();
+    sc->ctx = ctx; sc->n0 = n0; sc->my0 = my0; sc->myl = myl; sc->mzl = mzl;
+    sc->n = n0 + my0 + myl + mzl;
+    const size_t n = (size_t)sc->n;
+    sc->A.alloc(n * n + 1); sc->Fm.alloc(n * n + 1); sc->D.alloc(n + 1); sc->Dinv.alloc(n + 1); sc->diagW.alloc(DENSE_NB * DENSE_NB);
+    sc->Wbuf.alloc(n * DENSE_NB + 2); sc->stats.alloc(4); sc->rhs.alloc(n + 1);
+    CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (n * n + 1), ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *out = sc.release();
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_destroy(pipsgpu_sc* sc) {
+    PIPSGPU_TRY
+    if (sc) { cudaSetDevice(sc->ctx->device); cudaStreamSynchronize(sc->ctx->stream); delete sc; }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_dim(pipsgpu_sc* sc) { return sc ? sc->n : -1; }
+
+int pipsgpu_sc_zero(pipsgpu_sc* sc) {
+    PIPSGPU_TRY
+    if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_zero: null");
+    require_device(sc->ctx);
+    CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (size_t)sc->n * sc->n, sc->ctx->stream));
+    sc->factorized = false;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_allreduce(pipsgpu_sc* sc) {
+    PIPSGPU_TRY
+    if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_allreduce: null");
+    require_device(sc->ctx);
+    sc_allreduce_impl(sc);
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_add_sparse(pipsgpu_sc* sc, int row0, int col0, int m, const int* krow, const int* jcol, const double* val, double alpha) {
+    PIPSGPU_TRY
+    if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_add_sparse: null");
+    require_device(sc->ctx);
+    if (m <= 0 || !krow) return PIPSGPU_OK;
+    CsrDev M;
+    int maxc = 0;
+    for (int p = 0; p < krow[m]; ++p) maxc = std::max(maxc, jcol[p] + 1);
+    if (row0 < 0 || col0 < 0 || row0 + m > sc->n || col0 + maxc > sc->n) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_add_sparse: block out of range");
+    M.upload(m, maxc, krow, jcol, val, sc->ctx->stream);
+    launch_sc_add_sparse(sc->A.p, sc->n, row0, col0, m, M.krow.p, M.jcol.p, M.val.p, alpha, sc->ctx->stream);
+    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_add_diag(pipsgpu_sc* sc, int offset, int n, const double* d, double alpha) {
+    PIPSGPU_TRY
+    if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_add_diag: null");
+    require_device(sc->ctx);
+    if (n <= 0) return PIPSGPU_OK;
+    if (offset < 0 || offset + n > sc->n) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_add_diag: out of range");
+    DevBuf<double> dv;
+    if (d) {
+        dv.alloc((size_t)n);
+        CUDA_CHECK(cudaMemcpyAsync(dv.p, d, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, sc->ctx->stream));
+    }
+    launch_sc_add_diag(sc->A.p, sc->n, offset, n, dv.p, alpha, sc->ctx->stream);
+    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_factorize(pipsgpu_sc* sc, int inertia[3]) {
+    PIPSGPU_TRY
+    if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_factorize: null");
+    require_device(sc->ctx);
+    sc_factorize_impl(sc);
+    sc_fetch_stats(sc);
+    if (inertia) { inertia[0] = sc->inertia[0]; inertia[1] = sc->inertia[1]; inertia[2] = sc->inertia[2]; }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_solve(pipsgpu_sc* sc, int nrhs, double* rhs) {
+    PIPSGPU_TRY
+    if (!sc || !rhs) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_solve: null");
+    require_device(sc->ctx);
+    if (!sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_sc_solve: not factorized");
+    cudaStream_t s = sc->ctx->stream;
+    const size_t n = (size_t)sc->n;
+    DevBuf<double> x;
+    x.alloc(n * (size_t)std::max(nrhs, 1));
+    CUDA_CHECK(cudaMemcpyAsync(x.p, rhs, sizeof(double) * n * nrhs, cudaMemcpyHostToDevice, s));
+    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->Dinv.p, x.p, nrhs, (int64_t)n, s);
+    CUDA_CHECK(cudaMemcpyAsync(rhs, x.p, sizeof(double) * n * nrhs, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_download(pipsgpu_sc* sc, double* out) {
+    PIPSGPU_TRY
+    if (!sc || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_download: null");
+    require_device(sc->ctx);
+    const size_t n = (size_t)sc->n;
+    CUDA_CHECK(cudaMemcpyAsync(out, sc->A.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost, sc->ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = i + 1; j < n; ++j) out[i * n + j] = 0.0;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_upload(pipsgpu_sc* sc, const double* in) {
+    PIPSGPU_TRY
+    if (!sc || !in) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_upload: null");
+    require_device(sc->ctx);
+    const size_t n = (size_t)sc->n;
+    CUDA_CHECK(cudaMemcpyAsync(sc->A.p, in, sizeof(double) * n * n, cudaMemcpyHostToDevice, sc->ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    sc->factorized = false;
+    PIPSGPU_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kkt (sLinsysRootAug)
+// ------------------------------------------------------------------------------------------------------------
+int pipsgpu_kkt_create(pipsgpu_ctx* ctx, int n0, int my0, int mz0, int myl, int mzl, const int* A0_krow, const int* A0_jcol,
+                       const double* A0_val, const int* C0_krow, const int* C0_jcol, const double* C0_val, const int* F0_krow,
+                       const int* F0_jcol, const double* F0_val, const int* G0_krow, const int* G0_jcol, const double* G0_val,
+                       pipsgpu_kkt** out) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (!out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_create: null output");
+    auto k = std::make_unique<pipsgpu_kkt>();
+    k->ctx = ctx; k->n0 = n0; k->my0 = my0; k->mz0 = mz0; k->myl = myl; k->mzl = mzl;
+    cudaStream_t s = ctx->stream;
+    k->A0.upload(my0, n0, A0_krow, A0_jcol, A0_val, s);
+    k->C0.upload(mz0, n0, C0_krow, C0_jcol, C0_val, s);
+    k->F0.upload(myl, n0, F0_krow, F0_jcol, F0_val, s);
+    k->G0.upload(mzl, n0, G0_krow, G0_jcol, G0_val, s);
+    pipsgpu_sc* sc = nullptr;
+    const int rc = pipsgpu_sc_create(ctx, n0, my0, myl, mzl, &sc);
+    if (rc != 0) return rc;
+    k->sc.reset(sc);
+    const size_t nb0 = (size_t)n0 + my0 + mz0 + myl + mzl;
+    k->dd0.alloc((size_t)n0 + 1); k->zdiag0.alloc((size_t)mz0 + 1); k->zdiagl.alloc((size_t)mzl + 1);
+    k->b0.alloc(nb0 + 1); k->r.alloc((size_t)sc->n + 1); k->t3.alloc((size_t)mz0 + 1);
+    *out = k.release();
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_destroy(pipsgpu_kkt* k) {
+    PIPSGPU_TRY
+    if (k) {
+        cudaSetDevice(k->ctx->device);
+        cudaStreamSynchronize(k->ctx->stream);
+        if (k->ev_init) for (auto& e : k->ev) cudaEventDestroy(e);
+        delete k;
+    }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_add_leaf(pipsgpu_kkt* k, pipsgpu_leaf* lf) {
+    PIPSGPU_TRY
+    if (!k || !lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_add_leaf: null");
+    if (lf->ctx != k->ctx) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_add_leaf: leaf belongs to another context");
+    if (k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_add_leaf: kkt already set up");
+    if (lf->border_set && (lf->n0 != k->n0 || lf->my0 != k->my0 || lf->myl != k->myl || lf->mzl != k->mzl))
+        throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_add_leaf: border dimensions do not match the root");
+    if ((int)k->leaves.size() != lf->index) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_add_leaf: leaves must be added in creation order");
+    k->leaves.push_back(lf);
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_setup(pipsgpu_kkt* k, int threads) {
+    PIPSGPU_TRY
+    if (!k) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_setup: null");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    if (k->leaves.size() != ctx->leaves.size()) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_setup: every leaf of the context must be added");
+    if (!ctx->committed) {
+        const int rc = pipsgpu_ctx_commit(ctx, threads);
+        if (rc != 0) return rc;
+    }
+    k->sum_nx = k->sum_nz = k->sum_n = 0;
+    for (auto* lf : k->leaves) { k->sum_nx += lf->nx; k->sum_nz += lf->nz; k->sum_n += lf->n; }
+    // remap the border indices to the b0 layout [x0; y0; z0; yl; zl]
+    if (ctx->nnzB > 0) {
+        std::vector<int> h((size_t)ctx->nnzB);
+        CUDA_CHECK(cudaMemcpy(h.data(), ctx->bg_b0.p, sizeof(int) * h.size(), cudaMemcpyDeviceToHost));
+        for (auto& b : h) b = (b < k->n0) ? b : b + k->my0 + k->mz0;
+        CUDA_CHECK(cudaMemcpy(ctx->bg_b0.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+    }
+    k->bl.alloc((size_t)k->sum_n + 1);
+    k->tl.alloc((size_t)k->sum_n + 1);
+    if (!k->ev_init) {
+        for (auto& e : k->ev) CUDA_CHECK(cudaEventCreate(&e));
+        k->ev_init = true;
+    }
+    k->ready = true;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,
+                          const double* dd_leaves, const double* nomegainv_leaves, const double reg[3], int inertia_root[3]) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_factorize: kkt not set up");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    cudaStream_t s = ctx->stream;
+    pipsgpu_sc* sc = k->sc.get();
+    const double regP = reg ? reg[0] : 0.0, regDy = reg ? reg[1] : 0.0, regDz = reg ? reg[2] : 0.0;
+    CUDA_CHECK(cudaEventRecord(k->ev[0], s));
+    // ---- diagonals down (the only per-iteration H2D payload of the factorisation) ----
+    {
+        const double* dd = dd_leaves;
+        const double* nz = nomegainv_leaves;
+        for (auto* lf : k->leaves) {
+            leaf_fill_dvals(lf, dd, nz, regP, regDy, regDz);
+            if (dd) dd += lf->nx;
+            if (nz) nz += lf->nz;
+        }
+        leaf_push_dvals(ctx, 0, ctx->npos);
+        std::vector<double> h0((size_t)k->n0), hz((size_t)k->mz0), hl((size_t)k->mzl);
+        for (int i = 0; i < k->n0; ++i) h0[i] = (dd0 ? dd0[i] : 0.0) + regP;
+        for (int i = 0; i < k->mz0; ++i) hz[i] = (nomegainv0 ? nomegainv0[i] : 0.0) - regDz;
+        for (int i = 0; i < k->mzl; ++i) hl[i] = (nomegainv_link ? nomegainv_link[i] : 0.0) - regDz;
+        if (k->n0) CUDA_CHECK(cudaMemcpyAsync(k->dd0.p, h0.data(), sizeof(double) * h0.size(), cudaMemcpyHostToDevice, s));
+        if (k->mz0) CUDA_CHECK(cudaMemcpyAsync(k->zdiag0.p, hz.data(), sizeof(double) * hz.size(), cudaMemcpyHostToDevice, s));
+        if (k->mzl) CUDA_CHECK(cudaMemcpyAsync(k->zdiagl.p, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));   // h0/hz/hl are stack-lifetime staging buffers
+    }
+    // ---- initializeKKT + leaf LDL^T + Schur terms ----
+    CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (size_t)sc->n * sc->n, s));
+    factor_prepare(ctx, nullptr);
+    CUDA_CHECK(cudaEventRecord(k->ev[1], s));
+    run_factor_levels(ctx, sc, nullptr);
+    CUDA_CHECK(cudaEventRecord(k->ev[2], s));
+    // ---- reduceKKT ----
+    sc_allreduce_impl(sc);
+    CUDA_CHECK(cudaEventRecord(k->ev[3], s));
+    // ---- finalizeKKTdense ----
+    const int n0 = k->n0, my0 = k->my0, myl = k->myl, mzl = k->mzl;
+    launch_sc_add_diag(sc->A.p, sc->n, 0, n0, k->dd0.p, 1.0, s);
+    launch_sc_add_ctdc(sc->A.p, sc->n, k->mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, k->zdiag0.p, s);
+    launch_sc_add_sparse(sc->A.p, sc->n, n0, 0, my0, k->A0.krow.p, k->A0.jcol.p, k->A0.val.p, 1.0, s);
+    if (regDy != 0.0) launch_sc_add_diag(sc->A.p, sc->n, n0, my0 + myl, nullptr, -regDy, s);
+    launch_sc_add_sparse(sc->A.p, sc->n, n0 + my0, 0, myl, k->F0.krow.p, k->F0.jcol.p, k->F0.val.p, 1.0, s);
+    launch_sc_add_sparse(sc->A.p, sc->n, n0 + my0 + myl, 0, mzl, k->G0.krow.p, k->G0.jcol.p, k->G0.val.p, 1.0, s);
+    launch_sc_add_diag(sc->A.p, sc->n, n0 + my0 + myl, mzl, k->zdiagl.p, 1.0, s);
+    CUDA_CHECK(cudaEventRecord(k->ev[4], s));
+    sc_factorize_impl(sc);
+    CUDA_CHECK(cudaEventRecord(k->ev[5], s));
+    fetch_leaf_stats(ctx);
+    sc_fetch_stats(sc);
+    for (auto* lf : ctx->leaves) lf->factorized = true;
+    if (inertia_root) { inertia_root[0] = sc->inertia[0]; inertia_root[1] = sc->inertia[1]; inertia_root[2] = sc->inertia[2]; }
+    float ms;
+    for (int i = 0; i < 5; ++i) {
+        CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]));
+        k->times[i] = ms;
+    }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: kkt not set up");
+    if (!b0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b0");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    pipsgpu_sc* sc = k->sc.get();
+    if (!sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: not factorized");
+    cudaStream_t s = ctx->stream;
+    const int n0 = k->n0, my0 = k->my0, mz0 = k->mz0, myl = k->myl, mzl = k->mzl;
+    const int nb0 = n0 + my0 + mz0 + myl + mzl;
+    const int64_t N = ctx->npos;
+    CUDA_CHECK(cudaEventRecord(k->ev[6], s));
+    if (N > 0) {
+        if (!b_leaves) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b_leaves");
+        CUDA_CHECK(cudaMemcpyAsync(k->bl.p, b_leaves, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+    }
+    if (ctx->rank > 0) launch_vec_zero(k->b0.p, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
+    else CUDA_CHECK(cudaMemcpyAsync(k->b0.p, b0, sizeof(double) * (size_t)nb0, cudaMemcpyHostToDevice, s));
+    SolveArgs sa = ctx->solve_args(ctx->x.p, N, ctx->upd.p, ctx->updtot);
+    // ---- Lsolve: z_i = K_i^-1 b_i ; b0 -= Bord_i^T z_i ; allreduce ----
+    launch_gather_perm(ctx->gidx.p, k->bl.p, ctx->x.p, N, 1, N, s);
+    run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
+    launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->bl.p, N, 1, N, s);
+    launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, k->bl.p, k->b0.p, s);
+    if (ctx->comm && ctx->nranks > 1) {
+        NcclApi& api = NcclApi::get();
+        const int rc = api.AllReduce(k->b0.p, k->b0.p, (size_t)nb0, kNcclFloat64, kNcclSum, ctx->comm, s);
+        if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce(b0): ") + api.GetErrorString(rc));
+    }
+    CUDA_CHECK(cudaEventRecord(k->ev[7], s));
+    // ---- Dsolve: solveReducedLinkCons ----
+    double* b = k->b0.p;
+    double* r = k->r.p;
+    launch_vec_copy(r, b, n0 + my0, s);
+    launch_vec_copy(r + n0 + my0, b + n0 + my0 + mz0, myl + mzl, s);
+    if (mz0 > 0) {
+        launch_vec_copy(k->t3.p, b + n0 + my0, mz0, s);
+        launch_vec_div(k->t3.p, k->zdiag0.p, mz0, s);
+        launch_csr_tmult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, k->t3.p, r, s);
+    }
+    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->Dinv.p, r, 1, sc->n, s);
+    launch_vec_copy(b, r, n0 + my0, s);
+    if (mz0 > 0) {
+        launch_csr_mult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, r, b + n0 + my0, s);
+        launch_vec_div(b + n0 + my0, k->zdiag0.p, mz0, s);
+    }
+    launch_vec_copy(b + n0 + my0 + mz0, r + n0 + my0, myl + mzl, s);
+    CUDA_CHECK(cudaEventRecord(k->ev[8], s));
+    // ---- Ltsolve: b_i -= K_i^-1 (Bord_i u) ----
+    if (N > 0) {
+        launch_vec_zero(k->tl.p, N, s);
+        launch_border_mult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, b, k->tl.p, s);
+        launch_gather_perm(ctx->gidx.p, k->tl.p, ctx->x.p, N, 1, N, s);
+        run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
+        launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->tl.p, N, 1, N, s);
+        launch_axpy(-1.0, k->tl.p, k->bl.p, N, s);
+        CUDA_CHECK(cudaMemcpyAsync(b_leaves, k->bl.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(b0, b, sizeof(double) * (size_t)nb0, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaEventRecord(k->ev[9], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    float ms;
+    for (int i = 0; i < 3; ++i) {
+        CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[6 + i], k->ev[7 + i]));
+        k->times[5 + i] = ms;
+    }
+    PIPSGPU_CATCH
+}
+
+pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* k) { return k ? k->sc.get() : nullptr; }
+
+int pipsgpu_kkt_stage_times(pipsgpu_kkt* k, double out[8]) {
+    PIPSGPU_TRY
+    if (!k || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_stage_times: null");
+    for (int i = 0; i < 8; ++i) out[i] = k->times[i];
+    PIPSGPU_CATCH
+}
+
+}  // extern "C"

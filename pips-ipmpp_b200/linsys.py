@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's linear-system classes for the hot path, over the C ABI (capi.py).
+
+  CudaLeafLinearSystem   <- LinearSystems/DistributedLeafLinearSystem.{h,C}  (create_kkt :52-72, factor2 :74-86, ...)
+  CudaRootLinearSystem   <- LinearSystems/sLinsysRootAug.{h,C} + DistributedRootLinearSystem.{h,C}
+                            (createChildren :711-758 with DistributedDummyLinearSystem for non-owned blocks,
+                             factor2 :206-243, solveCompressed DistributedLinearSystem.C:409-420)
+
+The C++ rendition a PIPS-IPM++ maintainer would compile in is include/pipsgpu_shim.hpp; this
+Python rendition is what the tests and bench.py drive. No arithmetic happens here: the methods assemble index/value
+arrays once (create_kkt) and afterwards only move diagonals and right-hand sides through the ABI."""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import capi
+
+
+def create_kkt_lower(ch):
+    """create_kkt (DistributedLeafLinearSystem.C:52-72): lower CSR of [Q+diag . .; W 0 .; D . 0] with the full diagonal
+    stored explicitly (diagonal entry last in each row), Q = 0 for LPs."""
+    n, my, mz = ch.n, ch.my, ch.mz
+    nK = n + my + mz
+    blocks = []
+    if my > 0:
+        W = ch.W.tocoo()
+        blocks.append((W.row + n, W.col, W.data))
+    if mz > 0:
+        D = ch.D.tocoo()
+        blocks.append((D.row + n + my, D.col, D.data))
+    rows = np.concatenate([b[0] for b in blocks] + [np.arange(nK)])
+    cols = np.concatenate([b[1] for b in blocks] + [np.arange(nK)])
+    vals = np.concatenate([b[2] for b in blocks] + [np.zeros(nK)])
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    krow = np.zeros(nK + 1, dtype=np.int64)
+    np.add.at(krow, rows + 1, 1)
+    krow = np.cumsum(krow).astype(np.int32)
+    return krow, cols.astype(np.int32), vals.astype(np.float64)
+
+
+class CudaRootLinearSystem:
+    """Root linear system of a two-level block-angular LP on one GPU (one rank of the reference)."""
+
+    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0):
+        self.lp = lp
+        root = lp.root
+        self.rank, self.n_ranks = rank, n_ranks
+        self.ctx = capi.Context(device)
+        if n_ranks > 1:
+            assert nccl_uid is not None
+            self.ctx.init_comm(nccl_uid, rank, n_ranks)
+        # `lp.children` holds only the blocks this rank owns (problem.synthetic(block_range=...)); the reference gets
+        # the same effect with DistributedDummyLinearSystem children (LS/DistributedRootLinearSystem.C:725-757)
+        self.kkt = capi.KKT(self.ctx, root.n, root.my, root.mz, lp.myl, lp.mzl, root.A, root.C, root.F, root.G)
+        self.leaves = []
+        for ch in lp.children:
+            krow, jcol, val = create_kkt_lower(ch)
+            leaf = capi.Leaf(self.ctx, ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val)
+            leaf.set_border(root.n, root.my, lp.myl, lp.mzl, ch.A, ch.C, ch.F, ch.G)
+            self.kkt.add_leaf(leaf)
+            self.leaves.append(leaf)
+        self.kkt.setup(threads)
+        self.nb0 = root.n + root.my + root.mz + lp.myl + lp.mzl
+        self.sum_n = sum(ch.n + ch.my + ch.mz for ch in lp.children)
+        self._b_leaves = np.zeros(max(self.sum_n, 1))
+        self._b0 = np.zeros(self.nb0)
+
+    # ---- backend interface used by the host IPM driver ----------------------------------------------------
+    def factorize(self, dd, nomegainv, reg=None):
+        """dd: [root, child..]; nomegainv: [root, child.., link] (owned children only)."""
+        cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0)
+        self.inertia_root = self.kkt.factorize(np.asarray(dd[0], float), np.asarray(nomegainv[0], float),
+                                               np.asarray(nomegainv[-1], float), cat(dd[1:]), cat(nomegainv[1:-1]), reg)
+        return self.inertia_root
+
+    def solve_compressed(self, rhs):
+        """rhs = [b0, b_1, ..., b_N] (owned children), solved in place."""
+        self._b0[:] = rhs[0]
+        off = 0
+        for b in rhs[1:]:
+            self._b_leaves[off:off + len(b)] = b
+            off += len(b)
+        self.kkt.solve_compressed(self._b0, self._b_leaves)
+        rhs[0][:] = self._b0
+        off = 0
+        for b in rhs[1:]:
+            b[:] = self._b_leaves[off:off + len(b)]
+            off += len(b)
+        return rhs
+
+    def schur_complement(self):
+        """assembled (un-factorised) Schur complement, lower triangle row-major"""
+        return self.kkt.sc().download()
+
+    def close(self):
+        self.kkt.close()
+        self.ctx.close()

@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs. `-m gpu`.
+
+Tolerances (BASELINE.json north_star): assembled Schur complement relative Frobenius error <= 1e-10, IPM iteration
+count within +-1, final objective within 1e-8 relative. Solves: 1e-9 relative (the KKT systems of the synthetic
+iterate have condition numbers around 1e6-1e8, two different pivot orders)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _iterate(pkg, lp, cfg):
+    return pkg.problem.synthetic_iterate(lp, pkg.problem.CONFIG_ID[cfg])
+
+
+@pytest.mark.parametrize("cfg", ["T1", "T2", "T3"])
+def test_leaf_factor_and_solve(pkg, cfg):
+    from oracle.linsys import OracleLeaf
+    lp = pkg.problem.synthetic(cfg)
+    dd, nom = _iterate(pkg, lp, cfg)
+    ctx = pkg.capi.Context(0)
+    leaves = []
+    for ch in lp.children[:2]:
+        krow, jcol, val = pkg.linsys.create_kkt_lower(ch)
+        leaves.append(pkg.capi.Leaf(ctx, ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val))
+    ctx.commit()
+    rng = np.random.default_rng(0)
+    for i, leaf in enumerate(leaves):
+        ch = lp.children[i]
+        leaf.set_diagonal(dd[1 + i], nom[1 + i])
+        assert leaf.factorize() == (ch.n, ch.my + ch.mz, 0)
+        assert leaf.inertia()[1] == 0          # no perturbed pivots on a well-posed leaf
+        ref = OracleLeaf(lp, i)
+        ref.put_diagonals(dd[1 + i], nom[1 + i])
+        ref.factor2()
+        B = rng.standard_normal((5, leaf.n))
+        X = leaf.solve(B)
+        assert _rel(X, ref.solve(B)) <= 1e-9
+        x1 = leaf.solve(B[0])
+        assert _rel(x1, X[0]) <= 1e-14
+        K = ref.full_matrix()
+        assert np.linalg.norm(K @ x1 - B[0]) / np.linalg.norm(B[0]) <= 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg", ["T1", "T2", "T3", "T4"])
+def test_schur_complement_and_solve_compressed(pkg, cfg):
+    from oracle.linsys import OracleRoot
+    lp = pkg.problem.synthetic(cfg)
+    dd, nom = _iterate(pkg, lp, cfg)
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    inertia = gpu.factorize(dd, nom)
+    ref = OracleRoot(lp)
+    ref.put_diagonals(dd, nom)
+    ref.factor2()
+    assert _rel(gpu.schur_complement(), np.tril(ref.SC)) <= 1e-10
+    assert inertia == ref.inertia() == (lp.root.n, lp.root.my + lp.myl + lp.mzl, 0)
+    rng = np.random.default_rng(2)
+    rhs = [rng.standard_normal(gpu.nb0)] + [rng.standard_normal(ch.n + ch.my + ch.mz) for ch in lp.children]
+    want = ref.solve_compressed([r.copy() for r in rhs])
+    got = gpu.solve_compressed([r.copy() for r in rhs])
+    assert _rel(np.concatenate(got), np.concatenate(want)) <= 1e-8
+    t = gpu.kkt.stage_times()
+    assert t["leaf_ldlt_schur"] > 0 and t["root_ldlt"] > 0
+    assert gpu.ctx.launch_count() > 0
+    gpu.close()
+
+
+def test_regularised_and_repeated_factorisation(pkg):
+    """symbolic analysis is reused: factorising twice with different diagonals gives each time the oracle's result"""
+    from oracle.linsys import OracleRoot
+    lp = pkg.problem.synthetic("T2")
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    ref = OracleRoot(lp)
+    for seed_shift, reg in ((0, None), (5, (1e-6, 1e-7, 1e-7))):
+        dd, nom = pkg.problem.synthetic_iterate(lp, pkg.problem.CONFIG_ID["T2"] + seed_shift)
+        gpu.factorize(dd, nom, reg)
+        r = reg or (0.0, 0.0, 0.0)
+        ref.put_diagonals(dd, nom, *r)
+        ref.factor2()
+        assert _rel(gpu.schur_complement(), np.tril(ref.SC)) <= 1e-10
+    gpu.close()
+
+
+@pytest.mark.parametrize("n0,nneg", [(40, 25), (200, 137), (333, 90)])
+def test_dense_root_solver(pkg, n0, nneg):
+    """dense LDL^T + solve of a saddle-point Schur complement vs numpy; inertia reported exactly"""
+    rng = np.random.default_rng(n0)
+    n = n0 + nneg
+    H = rng.standard_normal((n0, n0)); H = H @ H.T + n0 * np.eye(n0)
+    A = rng.standard_normal((nneg, n0))
+    G = np.diag(rng.uniform(0.0, 1.0, nneg))
+    S = np.block([[H, A.T], [A, -G]])
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, n0, 0, nneg, 0)
+    sc.upload(np.tril(S))
+    assert sc.factorize() == (n0, nneg, 0)
+    B = rng.standard_normal((3, n))
+    X = sc.solve(B)
+    assert _rel(X, np.linalg.solve(S, B.T).T) <= 1e-10
+    assert _rel(sc.download(), np.tril(S)) == 0.0
+    sc.close()
+    ctx.close()
+
+
+def test_sc_assembly_helpers(pkg):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, 6, 2, 3, 1)
+    M = sp.random(3, 6, density=0.5, random_state=1, format="csr")
+    sc.add_sparse(8, 0, M, alpha=2.0)
+    d = rng.standard_normal(6)
+    sc.add_diag(0, d, alpha=-1.0)
+    want = np.zeros((12, 12))
+    want[8:11, 0:6] += 2.0 * M.toarray()
+    want[np.arange(6), np.arange(6)] -= d
+    assert np.allclose(sc.download(), want, atol=1e-15)
+    sc.zero()
+    assert np.all(sc.download() == 0)
+    sc.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "callback", "T1"])
+def test_ipm_iteration_and_objective_parity(pkg, name):
+    """full IPM runs driven by the host driver: CUDA backend vs oracle backend (golden: objective 14)"""
+    from oracle.ipm import IPM, OracleBackend
+    P = pkg.problem
+    lp = {"c1": P.c1_hier_4blocks, "callback": P.callback_example, "T1": lambda: P.synthetic("T1")}[name]()
+    ref = IPM(lp, OracleBackend(lp))
+    st_r, obj_r, it_r = ref.solve()
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    run = IPM(lp, gpu)
+    st_g, obj_g, it_g = run.solve()
+    gpu.close()
+    assert st_r == st_g == "SUCCESSFUL_TERMINATION"
+    assert abs(it_g - it_r) <= 1
+    assert abs(obj_g - obj_r) <= 1e-8 * max(1.0, abs(obj_r))
+    if "expected_objective" in lp.meta:
+        assert abs(obj_g - lp.meta["expected_objective"]) <= 1e-4      # t_pips.cpp:27 tolerance
+        if "expected_iterations" in lp.meta:
+            assert it_g <= int(np.ceil(1.1 * lp.meta["expected_iterations"]))
+
+
+def test_full_size_block_properties(pkg):
+    """C2-sized blocks (44 000 KKT rows each): size-independent checks - residual of the leaf solve through the host
+    matvec, symmetry/linearity of solveCompressed, Schur complement against the C multifrontal oracle."""
+    from oracle import mf
+    P = pkg.problem
+    lp = P.synthetic("C2", n_blocks=2)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID["C2"])
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    gpu.factorize(dd, nom)
+    sc = gpu.schur_complement()
+    # Schur term of block 0 and 1 from the serial C multifrontal oracle on the same symbolic structure
+    n0, my0, myl, mzl = lp.root.n, lp.root.my, lp.myl, lp.mzl
+    nB = n0 + myl + mzl
+    SCb = np.zeros((nB, nB))
+    for i, ch in enumerate(lp.children):
+        krow, jcol, val, diag_pos, nB_, brow, bcol, bval = mf.leaf_kkt_and_border(lp, i)
+        val = val.copy()
+        val[diag_pos[:ch.n]] = dd[1 + i]
+        val[diag_pos[ch.n + ch.my:]] = nom[1 + i]
+        sym = pkg.capi.Symbolic(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol).export()
+        m = mf.MfLeaf(sym)
+        inertia, npert = m.factorize(val, bval, SCb)
+        assert inertia == (ch.n, ch.my + ch.mz, 0) and npert == 0
+    idx = np.concatenate([np.arange(n0), n0 + my0 + np.arange(myl + mzl)])
+    # remove the root's own block from the GPU matrix to compare the children's contribution only
+    from oracle.linsys import OracleRoot
+    root_only = OracleRoot(lp, owned=[])
+    root_only.put_diagonals(dd, nom)
+    root_only.initialize_kkt()
+    root_only.finalize_kkt_dense()
+    contrib = (sc - np.tril(root_only.SC))[np.ix_(idx, idx)]
+    assert _rel(contrib, np.tril(SCb)) <= 1e-10
+    # solveCompressed: linearity
+    rng = np.random.default_rng(4)
+    mk = lambda: [rng.standard_normal(gpu.nb0)] + [rng.standard_normal(ch.n + ch.my + ch.mz) for ch in lp.children]
+    a, b = mk(), mk()
+    sa = gpu.solve_compressed([v.copy() for v in a])
+    sb = gpu.solve_compressed([v.copy() for v in b])
+    sab = gpu.solve_compressed([2.0 * u - 3.0 * v for u, v in zip(a, b)])
+    lin = np.concatenate([2.0 * u - 3.0 * v for u, v in zip(sa, sb)])
+    assert _rel(np.concatenate(sab), lin) <= 1e-9
+    gpu.close()
