@@ -648,16 +648,22 @@ void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* W
     COUNT_LAUNCH();
 }
 
-// forward / diagonal / backward solve with the dense factors, one CTA per right-hand side
+// forward / block-diagonal / backward solve with the dense factors  P A P^T = L D L^T, one CTA per right-hand side.
+// perm[i] = original index at pivot position i; ptype marks 2x2 pivots (Bunch-Kaufman path), Dinv_e their coupling.
 constexpr int DS_T = 1024;
 __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restrict__ A, int ld, int n,
-                                                           const double* __restrict__ Dinv, double* xall, int64_t xstride) {
+                                                           const int* __restrict__ perm, const int8_t* __restrict__ ptype,
+                                                           const double* __restrict__ Dinv, const double* __restrict__ Dinv_e,
+                                                           double* xall, int64_t xstride, double* wall) {
     __shared__ double xs[DENSE_NB];
     __shared__ double red[DS_T / 32][DENSE_NB + 1];
-    double* x = xall + (int64_t)blockIdx.x * xstride;
+    double* xo = xall + (int64_t)blockIdx.x * xstride;
+    double* x = wall + (int64_t)blockIdx.x * n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     const int nwarps = DS_T / 32;
+    for (int i = tid; i < n; i += DS_T) x[i] = xo[perm[i]];
+    __syncthreads();
     // ---- forward: L y = b ----
     for (int kb = 0; kb < n; kb += DENSE_NB) {
         const int bw = min(DENSE_NB, n - kb);
@@ -679,8 +685,16 @@ __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restr
         }
         __syncthreads();
     }
-    // ---- diagonal ----
-    for (int i = tid; i < n; i += DS_T) x[i] *= Dinv[i];
+    // ---- block diagonal ----
+    for (int i = tid; i < n; i += DS_T) {
+        const int t = ptype[i];
+        if (t == 0) x[i] *= Dinv[i];
+        else if (t == 1) {
+            const double y0 = x[i], y1 = x[i + 1];
+            x[i] = Dinv[i] * y0 + Dinv_e[i] * y1;
+            x[i + 1] = Dinv_e[i] * y0 + Dinv[i + 1] * y1;
+        }
+    }
     __syncthreads();
     // ---- backward: L^T x = y ----
     const int nblk = (n + DENSE_NB - 1) / DENSE_NB;
@@ -704,10 +718,196 @@ __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restr
         }
         __syncthreads();
     }
+    for (int i = tid; i < n; i += DS_T) xo[perm[i]] = x[i];
 }
-void launch_dense_solve(const double* A, int ld, int n, const double* Dinv, double* x, int nrhs, int64_t xstride, cudaStream_t s) {
+void launch_dense_solve(const double* A, int ld, int n, const int* perm, const int8_t* ptype, const double* Dinv,
+                        const double* Dinv_e, double* x, int nrhs, int64_t xstride, double* work, cudaStream_t s) {
     if (n <= 0 || nrhs <= 0) return;
-    dense_solve_kernel<<<nrhs, DS_T, 0, s>>>(A, ld, n, Dinv, x, xstride);
+    dense_solve_kernel<<<nrhs, DS_T, 0, s>>>(A, ld, n, perm, ptype, Dinv, Dinv_e, x, xstride, work);
+    COUNT_LAUNCH();
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Bunch-Kaufman LDL^T (the algorithm of LAPACK dsytf2 that the reference calls through dsytrf,
+// DeSymIndefSolver.C:76-90), used when the static-order factorisation meets a wrong-signed / tiny pivot (free
+// variables at the root). Right-looking, one pivot step = bk_pivot_kernel (1 CTA: pivot search, symmetric
+// interchange of whole rows so that P A P^T = L D L^T, pivot-column scaling) + bk_update_kernel (whole GPU: rank-1/2
+// update of the trailing lower triangle). The step counter lives on the device (2x2 pivots advance it by two).
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_max(double& v, int& idx, double* sv, int* si) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(full, v, o);
+        const int oi = __shfl_xor_sync(full, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { sv[warp] = v; si[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        v = (lane < nw) ? sv[lane] : -1.0;
+        idx = (lane < nw) ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(full, v, o);
+            const int oi = __shfl_xor_sync(full, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { sv[0] = v; si[0] = idx; }
+    }
+    __syncthreads();
+    v = sv[0];
+    idx = si[0];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) bk_pivot_kernel(double* A, int ld, int n, int* perm, int8_t* ptype, double* Dd,
+                                                        double* De, double* Did, double* Die, double* Wc, BkState* st,
+                                                        double eps) {
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    const int k = st->k;
+    if (k >= n) {
+        if (threadIdx.x == 0) st->s = 0;
+        return;
+    }
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double alpha = 0.6403882032022076;   // (1+sqrt(17))/8
+    // ---- pivot search (dsytf2, lower) ----
+    double cm = -1.0; int im = 0x7fffffff;
+    for (int i = k + 1 + tid; i < n; i += nt) {
+        const double v = fabs(A[(int64_t)i * ld + k]);
+        if (v > cm) { cm = v; im = i; }
+    }
+    block_max(cm, im, sv, si);
+    const double colmax = (k + 1 < n) ? cm : 0.0;
+    const int imax = im;
+    const double absakk = fabs(A[(int64_t)k * ld + k]);
+    int kp = k, kstep = 1;
+    if (fmax(absakk, colmax) > 0.0 && absakk < alpha * colmax) {
+        double rm = -1.0; int ri = 0x7fffffff;
+        for (int j = k + tid; j < imax; j += nt) {
+            const double v = fabs(A[(int64_t)imax * ld + j]);
+            if (v > rm) { rm = v; ri = j; }
+        }
+        for (int i = imax + 1 + tid; i < n; i += nt) {
+            const double v = fabs(A[(int64_t)i * ld + imax]);
+            if (v > rm) { rm = v; ri = i; }
+        }
+        block_max(rm, ri, sv, si);
+        const double rowmax = rm;
+        if (absakk >= alpha * colmax * (colmax / rowmax)) { kp = k; kstep = 1; }
+        else if (fabs(A[(int64_t)imax * ld + imax]) >= alpha * rowmax) { kp = imax; kstep = 1; }
+        else { kp = imax; kstep = 2; }
+    }
+    const int kk = k + kstep - 1;
+    // ---- symmetric interchange kk <-> kp (kp > kk), whole rows so that the L part follows ----
+    if (kp != kk) {
+        for (int j = tid; j < kk; j += nt) {
+            const double t = A[(int64_t)kk * ld + j];
+            A[(int64_t)kk * ld + j] = A[(int64_t)kp * ld + j];
+            A[(int64_t)kp * ld + j] = t;
+        }
+        for (int j = kk + 1 + tid; j < kp; j += nt) {
+            const double t = A[(int64_t)j * ld + kk];
+            A[(int64_t)j * ld + kk] = A[(int64_t)kp * ld + j];
+            A[(int64_t)kp * ld + j] = t;
+        }
+        for (int i = kp + 1 + tid; i < n; i += nt) {
+            const double t = A[(int64_t)i * ld + kk];
+            A[(int64_t)i * ld + kk] = A[(int64_t)i * ld + kp];
+            A[(int64_t)i * ld + kp] = t;
+        }
+        if (tid == 0) {
+            const double t = A[(int64_t)kk * ld + kk];
+            A[(int64_t)kk * ld + kk] = A[(int64_t)kp * ld + kp];
+            A[(int64_t)kp * ld + kp] = t;
+            const int p = perm[kk]; perm[kk] = perm[kp]; perm[kp] = p;
+        }
+    }
+    __syncthreads();
+    // ---- pivot block, scaled pivot columns; unscaled copies go to Wc for the trailing update ----
+    if (kstep == 1) {
+        double d = A[(int64_t)k * ld + k];
+        bool pert = false;
+        if (!(fabs(d) >= eps)) { d = (d < 0.0) ? -eps : eps; pert = true; }
+        const double inv = 1.0 / d;
+        for (int i = k + 1 + tid; i < n; i += nt) {
+            const double w = A[(int64_t)i * ld + k];
+            Wc[2 * i] = w;
+            A[(int64_t)i * ld + k] = w * inv;
+        }
+        if (tid == 0) {
+            Dd[k] = d; De[k] = 0.0; Did[k] = inv; Die[k] = 0.0; ptype[k] = 0;
+            if (d > 0) ++st->npos; else ++st->nneg;
+            if (pert) ++st->npert;
+        }
+    } else {
+        const double a = A[(int64_t)k * ld + k], b = A[(int64_t)(k + 1) * ld + k], c = A[(int64_t)(k + 1) * ld + k + 1];
+        const double det = a * c - b * b;
+        const double ia = c / det, ib = -b / det, ic = a / det;
+        for (int i = k + 2 + tid; i < n; i += nt) {
+            const double w1 = A[(int64_t)i * ld + k], w2 = A[(int64_t)i * ld + k + 1];
+            Wc[2 * i] = w1; Wc[2 * i + 1] = w2;
+            A[(int64_t)i * ld + k] = w1 * ia + w2 * ib;
+            A[(int64_t)i * ld + k + 1] = w1 * ib + w2 * ic;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            A[(int64_t)(k + 1) * ld + k] = 0.0;
+            Dd[k] = a; De[k] = b; Dd[k + 1] = c; De[k + 1] = 0.0;
+            Did[k] = ia; Die[k] = ib; Did[k + 1] = ic; Die[k + 1] = 0.0;
+            ptype[k] = 1; ptype[k + 1] = 2;
+            if (det < 0) { ++st->npos; ++st->nneg; } else if (a > 0) st->npos += 2; else st->nneg += 2;
+        }
+    }
+    if (tid == 0) { st->kcur = k; st->s = kstep; st->k = k + kstep; }
+}
+
+__global__ void __launch_bounds__(256) bk_update_kernel(double* A, int ld, int n, const double* __restrict__ Wc,
+                                                        const BkState* __restrict__ st, int lower) {
+    const int s = st->s;
+    if (s == 0) return;
+    const int k = st->kcur, t0 = k + s;
+    const int j = lower + blockIdx.x * 32 + threadIdx.x;
+    const int ib = lower + blockIdx.y * 32;
+    if (j >= n || j < t0 || ib + 31 < j) return;
+    const double w1 = Wc[2 * j];
+    const double w2 = (s == 2) ? Wc[2 * j + 1] : 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = ib + threadIdx.y + 8 * r;
+        if (i < n && i >= j) {
+            double v = A[(int64_t)i * ld + j] - A[(int64_t)i * ld + k] * w1;
+            if (s == 2) v -= A[(int64_t)i * ld + k + 1] * w2;
+            A[(int64_t)i * ld + j] = v;
+        }
+    }
+}
+
+void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype, double* Dd, double* De, double* Did,
+                    double* Die, double* Wc, BkState* st, double eps, cudaStream_t s) {
+    bk_pivot_kernel<<<1, 1024, 0, s>>>(A, ld, n, perm, ptype, Dd, De, Did, Die, Wc, st, eps);
+    COUNT_LAUNCH();
+    const int lower = step + 1;
+    const int rows = n - lower;
+    if (rows > 0) {
+        const int nt = cdiv(rows, 32);
+        bk_update_kernel<<<dim3(nt, nt), dim3(32, 8), 0, s>>>(A, ld, n, Wc, st, lower);
+        COUNT_LAUNCH();
+    }
+}
+
+__global__ void iota_kernel(int* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+void launch_iota(int* p, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    iota_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, n);
     COUNT_LAUNCH();
 }
 

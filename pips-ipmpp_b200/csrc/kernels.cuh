@@ -89,7 +89,13 @@ int64_t sc_pack_size(int n0, int nl);
 void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps, double* D, double* Dinv, double* diagW, int* stats, cudaStream_t s);
 void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf, cudaStream_t s);
 void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s);
-void launch_dense_solve(const double* A, int ld, int n, const double* Dinv, double* x, int nrhs, int64_t xstride, cudaStream_t s);
+void launch_dense_solve(const double* A, int ld, int n, const int* perm, const int8_t* ptype, const double* Dinv,
+                        const double* Dinv_e, double* x, int nrhs, int64_t xstride, double* work, cudaStream_t s);
+// Bunch-Kaufman fallback (dsytf2 restated): device-side step counter
+struct BkState { int k, kcur, s, npos, nneg, npert; };
+void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype, double* Dd, double* De, double* Did,
+                    double* Die, double* Wc, BkState* st, double eps, cudaStream_t s);
+void launch_iota(int* p, int n, cudaStream_t s);
 
 // ---- small vector / CSR helpers for the root-level solve ----
 void launch_csr_mult(int m, const int* krow, const int* jcol, const double* val, double alpha, const double* x, double* y, cudaStream_t s);    // y += alpha*A x

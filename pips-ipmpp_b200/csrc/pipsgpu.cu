@@ -127,9 +127,12 @@ struct pipsgpu_sc {
     int n0 = 0, my0 = 0, myl = 0, mzl = 0, n = 0;
     DevBuf<double> A;        // assembled matrix, n x n row-major, lower triangle used (owned by the linear system)
     DevBuf<double> Fm;       // the solver's own copy, overwritten by the factors (DeSymIndefSolver.C:65 copies too)
-    DevBuf<double> D, Dinv, diagW, Wbuf, pack, rhs;
-    DevBuf<int> stats;
+    DevBuf<double> D, De, Dinv, Dinv_e, diagW, Wbuf, Wc, pack, rhs, swork;
+    DevBuf<int> stats, perm;
+    DevBuf<int8_t> ptype;
+    DevBuf<BkState> bk;
     bool factorized = false;
+    bool used_bk = false;      // last factorisation needed the Bunch-Kaufman path
     int inertia[3] = {0, 0, 0};
     int n_perturbed = 0;
 };
@@ -253,30 +256,59 @@ void fetch_leaf_stats(pipsgpu_ctx* ctx) {
     }
 }
 
-void sc_factorize_impl(pipsgpu_sc* sc) {
+// static-order LDL^T on the tensor pipe (x0 block first; exact for quasi-definite Schur complements)
+void sc_factorize_static(pipsgpu_sc* sc) {
     pipsgpu_ctx* ctx = sc->ctx;
     cudaStream_t s = ctx->stream;
     const int n = sc->n;
     CUDA_CHECK(cudaMemsetAsync(sc->stats.p, 0, sizeof(int) * 4, s));
-    // perturbation threshold relative to the largest diagonal magnitude is not known on the host; use 1e-8 (entries
-    // of the scaled KKT system are O(1), Utilities/pipsdef.h pips_eps = 1e-13 is far below)
+    CUDA_CHECK(cudaMemsetAsync(sc->ptype.p, 0, sizeof(int8_t) * (size_t)(n + 1), s));
+    CUDA_CHECK(cudaMemsetAsync(sc->Dinv_e.p, 0, sizeof(double) * (size_t)(n + 1), s));
+    launch_iota(sc->perm.p, n, s);
     const double eps = 1e-10;
-    const int npos_expected = sc->n0;
     CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
     for (int kb = 0; kb < n; kb += DENSE_NB) {
         const int bw = std::min(DENSE_NB, n - kb);
-        launch_dense_diag(sc->Fm.p, n, kb, bw, npos_expected, eps, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
+        launch_dense_diag(sc->Fm.p, n, kb, bw, sc->n0, eps, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
         launch_dense_trsm(sc->Fm.p, n, n, kb, bw, sc->Dinv.p, sc->diagW.p, sc->Wbuf.p, s);
         launch_dense_syrk(sc->Fm.p, n, n, kb, bw, sc->Wbuf.p, s);
     }
-    sc->factorized = true;
 }
 
-void sc_fetch_stats(pipsgpu_sc* sc) {
+// Bunch-Kaufman LDL^T (dsytf2 restated, what the reference's dsytrf does): any symmetric indefinite matrix
+void sc_factorize_bk(pipsgpu_sc* sc) {
+    pipsgpu_ctx* ctx = sc->ctx;
+    cudaStream_t s = ctx->stream;
+    const int n = sc->n;
+    CUDA_CHECK(cudaMemsetAsync(sc->bk.p, 0, sizeof(BkState), s));
+    CUDA_CHECK(cudaMemsetAsync(sc->ptype.p, 0, sizeof(int8_t) * (size_t)(n + 1), s));
+    CUDA_CHECK(cudaMemsetAsync(sc->Dinv_e.p, 0, sizeof(double) * (size_t)(n + 1), s));
+    launch_iota(sc->perm.p, n, s);
+    CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+    for (int step = 0; step < n; ++step)
+        launch_bk_step(sc->Fm.p, n, n, step, sc->perm.p, sc->ptype.p, sc->D.p, sc->De.p, sc->Dinv.p, sc->Dinv_e.p, sc->Wc.p,
+                       sc->bk.p, 1e-13, s);
+}
+
+// factorize: fast static path first; if a pivot had to be perturbed or the inertia is not (n0, n-n0, 0) the matrix is
+// not quasi-definite in this order -> redo with Bunch-Kaufman. Leaves sc->inertia / n_perturbed up to date.
+void sc_factorize_impl(pipsgpu_sc* sc) {
+    pipsgpu_ctx* ctx = sc->ctx;
+    sc_factorize_static(sc);
     int h[4];
-    CUDA_CHECK(cudaMemcpyAsync(h, sc->stats.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, sc->ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(sc->ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h, sc->stats.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     sc->inertia[0] = h[0]; sc->inertia[1] = h[1]; sc->inertia[2] = h[2]; sc->n_perturbed = h[3];
+    sc->used_bk = false;
+    if (h[3] != 0 || h[0] != sc->n0 || h[2] != 0) {
+        sc_factorize_bk(sc);
+        BkState st;
+        CUDA_CHECK(cudaMemcpyAsync(&st, sc->bk.p, sizeof(BkState), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        sc->inertia[0] = st.npos; sc->inertia[1] = st.nneg; sc->inertia[2] = 0; sc->n_perturbed = st.npert;
+        sc->used_bk = true;
+    }
+    sc->factorized = true;
 }
 
 void sc_allreduce_impl(pipsgpu_sc* sc) {
@@ -761,6 +793,8 @@ int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsg
     sc->n = n0 + my0 + myl + mzl;
     const size_t n = (size_t)sc->n;
     sc->A.alloc(n * n + 1); sc->Fm.alloc(n * n + 1); sc->D.alloc(n + 1); sc->Dinv.alloc(n + 1); sc->diagW.alloc(DENSE_NB * DENSE_NB);
+    sc->De.alloc(n + 1); sc->Dinv_e.alloc(n + 1); sc->Wc.alloc(2 * n + 2); sc->perm.alloc(n + 1); sc->ptype.alloc(n + 1);
+    sc->bk.alloc(1); sc->swork.alloc(n + 1);
     sc->Wbuf.alloc(n * DENSE_NB + 2); sc->stats.alloc(4); sc->rhs.alloc(n + 1);
     CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (n * n + 1), ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -829,7 +863,6 @@ int pipsgpu_sc_factorize(pipsgpu_sc* sc, int inertia[3]) {
     if (!sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_factorize: null");
     require_device(sc->ctx);
     sc_factorize_impl(sc);
-    sc_fetch_stats(sc);
     if (inertia) { inertia[0] = sc->inertia[0]; inertia[1] = sc->inertia[1]; inertia[2] = sc->inertia[2]; }
     PIPSGPU_CATCH
 }
@@ -844,7 +877,9 @@ int pipsgpu_sc_solve(pipsgpu_sc* sc, int nrhs, double* rhs) {
     DevBuf<double> x;
     x.alloc(n * (size_t)std::max(nrhs, 1));
     CUDA_CHECK(cudaMemcpyAsync(x.p, rhs, sizeof(double) * n * nrhs, cudaMemcpyHostToDevice, s));
-    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->Dinv.p, x.p, nrhs, (int64_t)n, s);
+    sc->swork.ensure(n * (size_t)std::max(nrhs, 1));
+    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, x.p, nrhs, (int64_t)n,
+                       sc->swork.p, s);
     CUDA_CHECK(cudaMemcpyAsync(rhs, x.p, sizeof(double) * n * nrhs, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     PIPSGPU_CATCH
@@ -1004,7 +1039,6 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomeg
     sc_factorize_impl(sc);
     CUDA_CHECK(cudaEventRecord(k->ev[5], s));
     fetch_leaf_stats(ctx);
-    sc_fetch_stats(sc);
     for (auto* lf : ctx->leaves) lf->factorized = true;
     if (inertia_root) { inertia_root[0] = sc->inertia[0]; inertia_root[1] = sc->inertia[1]; inertia_root[2] = sc->inertia[2]; }
     float ms;
@@ -1056,7 +1090,7 @@ int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
         launch_vec_div(k->t3.p, k->zdiag0.p, mz0, s);
         launch_csr_tmult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, k->t3.p, r, s);
     }
-    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->Dinv.p, r, 1, sc->n, s);
+    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, r, 1, sc->n, sc->swork.p, s);
     launch_vec_copy(b, r, n0 + my0, s);
     if (mz0 > 0) {
         launch_csr_mult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, r, b + n0 + my0, s);

@@ -189,3 +189,34 @@ def test_full_size_block_properties(pkg):
     lin = np.concatenate([2.0 * u - 3.0 * v for u, v in zip(sa, sb)])
     assert _rel(np.concatenate(sab), lin) <= 1e-9
     gpu.close()
+
+
+@pytest.mark.parametrize("kind", ["saddle_free", "random_indefinite", "c1_like_singular"])
+def test_dense_root_solver_bunch_kaufman(pkg, kind):
+    """matrices the static (x0-first) order cannot factor: the solver must fall back to Bunch-Kaufman pivoting (what
+    the reference's dsytrf does, DeSymIndefSolver.C:76-90) and still match numpy / the oracle's LAPACK dsytrf inertia"""
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(7)
+    if kind == "saddle_free":
+        n0 = m = 24
+        A = rng.standard_normal((m, n0)) + 3 * np.eye(m)
+        S = np.block([[np.zeros((n0, n0)), A.T], [A, np.zeros((m, m))]])
+    elif kind == "random_indefinite":
+        n0, m = 70, 80
+        S = rng.standard_normal((n0 + m, n0 + m)); S = S + S.T
+    else:
+        n0, m = 6, 12
+        A = rng.standard_normal((m, n0))
+        S = np.block([[np.zeros((n0, n0)), A.T], [A, -np.diag(rng.uniform(0.5, 1.5, m))]])
+    n = n0 + m
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, n0, 0, m, 0)
+    sc.upload(np.tril(S))
+    inertia = sc.factorize()
+    ev = np.linalg.eigvalsh(S)
+    assert inertia == (int((ev > 0).sum()), int((ev < 0).sum()), 0)
+    B = rng.standard_normal((2, n))
+    X = sc.solve(B)
+    assert _rel(X, np.linalg.solve(S, B.T).T) <= 1e-9
+    sc.close()
+    ctx.close()
