@@ -47,6 +47,9 @@ int pipsgpu_version(void);
 int pipsgpu_ctx_create(int device, pipsgpu_ctx** ctx);
 int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx);
 int pipsgpu_ctx_synchronize(pipsgpu_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the host application's or torch's current
+ * stream, so that the caller's own events bracket the work. The context does not destroy a borrowed stream. */
+int pipsgpu_ctx_set_stream(pipsgpu_ctx* ctx, void* cuda_stream);
 /* NCCL bootstrap without MPI: rank 0 creates the id, the host program ships the 128 bytes to the other ranks
  * (torch.distributed / MPI_Bcast / a file), every rank calls init_comm. Replaces the MPI communicator the reference
  * passes around (LS/DistributedRootLinearSystem.C:47-57, mpiComm). */
@@ -169,6 +172,11 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* kkt, const double* dd0, const double* nom
  * Lsolve (LS/sLinsysRootAug.C:340-341) runs over NCCL when a communicator is attached; on ranks > 0 the incoming b0
  * is ignored exactly as in the reference (:332-333). */
 int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* kkt, double* b0, double* b_leaves);
+/* device-resident variants for measuring the kernels without PCIe traffic: reuse the diagonals / the right-hand side
+ * of the last pipsgpu_kkt_factorize / pipsgpu_kkt_solve_compressed call, which stay in HBM. solve_compressed_resident
+ * is asynchronous (no D2H, no host synchronisation); factorize_resident synchronises once to read the inertia. */
+int pipsgpu_kkt_factorize_resident(pipsgpu_kkt* kkt, int inertia_root[3]);
+int pipsgpu_kkt_solve_compressed_resident(pipsgpu_kkt* kkt);
 /* the root Schur complement object (for download / parity checks) */
 pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* kkt);
 /* device time in ms of the stages of the last factorize: out[0]=H2D+assembly, [1]=leaf LDL^T + Schur terms,

@@ -239,6 +239,8 @@ class OracleRoot:
         self.nS = lp.n_S
         self.SC = np.zeros((self.nS, self.nS))
         self.regDy = 0.0
+        self.pivot_eps = 1e-12
+        self.n_perturbed = 0
 
     # -- LinearSystem::factorize part that moves data: diagonals for every node
     def put_diagonals(self, dd, nomegainv, regP=0.0, regDy=0.0, regDz=0.0):
@@ -316,6 +318,36 @@ class OracleRoot:
         S = self.sc_symmetric()
         self.ldu, self.ipiv, info = lapack.dsytrf(S, lower=1)
         assert info >= 0
+        # A singular Schur complement (redundant equality rows, e.g. hier_approach_4blocks_2by2 has 15 equalities for
+        # 14 variables) leaves dsytrf with a pivot of rounding-noise size. The reference's default root solver perturbs
+        # such pivots to 1e-8*||SC|| (PARDISO iparm[9]=8, PardisoProjectIndefSolver.C:34-61); do the same to the 1x1
+        # pivots of the LAPACK factor so that the outcome does not depend on rounding luck.
+        # The threshold is relative to the largest entry of the pivot's own (original) row, so badly scaled but
+        # well-posed systems are left untouched.
+        perm = np.arange(self.nS)
+        k = 0
+        while k < self.nS:
+            if self.ipiv[k] > 0:
+                j = self.ipiv[k] - 1
+                perm[[k, j]] = perm[[j, k]]
+                k += 1
+            else:
+                j = -self.ipiv[k] - 1
+                perm[[k + 1, j]] = perm[[j, k + 1]]
+                k += 2
+        rowmax = np.abs(S).max(axis=1, initial=0.0)
+        self.n_perturbed = 0
+        k = 0
+        while k < self.nS:
+            if self.ipiv[k] > 0:
+                d = self.ldu[k, k]
+                eps = self.pivot_eps * max(rowmax[perm[k]], 1e-300)
+                if abs(d) < eps:
+                    self.ldu[k, k] = -eps if d < 0 else eps
+                    self.n_perturbed += 1
+                k += 1
+            else:
+                k += 2
         return info
 
     def inertia(self):

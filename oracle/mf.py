@@ -91,3 +91,92 @@ class MfLeaf:
         rc = lib().mf_solve(C.byref(self.S), _p(self.sym["perm"]), _p(self.L), _p(self.dinv_d), _p(self.dinv_e), _p(x))
         assert rc == 0
         return x
+
+
+class MfBackend:
+    """CPU KKT backend (same interface as oracle.ipm.OracleBackend) built from the C multifrontal restatement for the
+    leaves (threads over blocks; ctypes releases the GIL) and the oracle's LAPACK dsytrf/dsytrs root. This is the
+    CPU path timed as `cpu_baseline` / `--impl reference` in bench.py: it does the same fused factor + Schur work as
+    the reference's default PARDISO-Schur configuration (sLinsysLeafSchurSlv.C:20-35)."""
+
+    def __init__(self, lp, symbolic_factory, threads=1, max_width=0):
+        from concurrent.futures import ThreadPoolExecutor
+        from .linsys import OracleRoot
+        self.lp = lp
+        self.threads = max(1, threads)
+        self.pool = ThreadPoolExecutor(self.threads)
+        self.root = OracleRoot(lp, owned=[])
+        self.leaf_data = []
+
+        def prep(i):
+            ch = lp.children[i]
+            krow, jcol, val, diag_pos, nB, brow, bcol, bval = leaf_kkt_and_border(lp, i)
+            sym = symbolic_factory(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol, max_width)
+            arrs = sym.export()
+            knorm = max(1.0, float(np.abs(val).max(initial=0.0)))     # off-diagonal norm (diagonal is still zero here)
+            return dict(m=MfLeaf(arrs), val=val.copy(), diag_pos=diag_pos, bval=bval, brow=brow, bcol=bcol, nB=nB,
+                        knorm=knorm, stats=dict(sym.sizes, flops=sym.flops))
+
+        self.leaf_data = list(self.pool.map(prep, range(len(lp.children))))
+        n0, my0, myl, mzl = lp.root.n, lp.root.my, lp.myl, lp.mzl
+        self.nB = n0 + myl + mzl
+        self.scidx = np.concatenate([np.arange(n0), n0 + my0 + np.arange(myl + mzl)])
+
+    def factorize(self, dd, nomegainv, blocks=None):
+        lp = self.lp
+        blocks = range(len(lp.children)) if blocks is None else blocks
+        nth = self.threads
+        acc = [np.zeros((self.nB, self.nB)) for _ in range(nth)]
+        chunks = [list(blocks)[t::nth] for t in range(nth)]
+
+        def work(t):
+            for i in chunks[t]:
+                d = self.leaf_data[i]
+                ch = lp.children[i]
+                v = d["val"]
+                v[d["diag_pos"][:ch.n]] = dd[1 + i]
+                v[d["diag_pos"][ch.n:ch.n + ch.my]] = 0.0
+                v[d["diag_pos"][ch.n + ch.my:]] = nomegainv[1 + i]
+                d["inertia"], d["npert"] = d["m"].factorize(v, d["bval"], acc[t], knorm=d["knorm"])
+
+        list(self.pool.map(work, range(nth)))
+        SCb = np.sum(acc, axis=0)
+        r = self.root
+        r.put_diagonals(dd, nomegainv)
+        r.initialize_kkt()
+        r.SC[np.ix_(self.scidx, self.scidx)] += np.tril(SCb)
+        r.finalize_kkt_dense()
+        r.factorize_kkt()
+
+    def solve_compressed(self, b, blocks=None):
+        lp = self.lp
+        r = self.root
+        blocks = list(range(len(lp.children)) if blocks is None else blocks)
+        n0 = lp.root.n
+        L0 = len(b[0])
+        tail = L0 - lp.myl - lp.mzl
+
+        def b0idx(bc):
+            return np.where(bc < n0, bc, bc - n0 + tail)
+
+        def fwd(i):
+            d = self.leaf_data[i]
+            z = d["m"].solve(b[1 + i])
+            b[1 + i][:] = z
+            contrib = np.zeros(L0)
+            np.add.at(contrib, b0idx(d["bcol"]), d["bval"] * z[d["brow"]])
+            return contrib
+
+        for c in self.pool.map(fwd, blocks):
+            b[0] -= c
+        r.solve_reduced_link_cons(b[0])
+
+        def bwd(i):
+            d = self.leaf_data[i]
+            ch = lp.children[i]
+            t = np.zeros(ch.n + ch.my + ch.mz)
+            np.add.at(t, d["brow"], d["bval"] * b[0][b0idx(d["bcol"])])
+            b[1 + i] -= d["m"].solve(t)
+
+        list(self.pool.map(bwd, blocks))
+        return b

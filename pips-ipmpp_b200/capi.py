@@ -130,6 +130,10 @@ class Context:
         _check(lib().pipsgpu_nccl_unique_id(buf))
         return buf.raw
 
+    def set_stream(self, cuda_stream: int):
+        """borrow a CUDA stream (raw cudaStream_t as int, e.g. torch.cuda.Stream().cuda_stream)"""
+        _check(lib().pipsgpu_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
     def commit(self, threads=0):
         _check(lib().pipsgpu_ctx_commit(self.h, C.c_int(threads)))
 
@@ -305,6 +309,14 @@ class KKT:
         p0 = C.c_void_p(b0) if isinstance(b0, int) else _ip(b0)
         pl = C.c_void_p(b_leaves) if isinstance(b_leaves, int) else _ip(b_leaves)
         _check(lib().pipsgpu_kkt_solve_compressed(self.h, p0, pl))
+
+    def factorize_resident(self):
+        inertia = np.zeros(3, dtype=np.int32)
+        _check(lib().pipsgpu_kkt_factorize_resident(self.h, _ip(inertia)))
+        return tuple(int(v) for v in inertia)
+
+    def solve_compressed_resident(self):
+        _check(lib().pipsgpu_kkt_solve_compressed_resident(self.h))
 
     def sc(self):
         n0, my0, mz0, myl, mzl = self.dims

@@ -10,6 +10,7 @@
 // Reference anchors for what these kernels replace are in include/pipsgpu.h next to each entry point.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 namespace pipsgpu {
@@ -506,8 +507,9 @@ void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* b
 // =====================================================================================================
 // dense right-looking LDL^T (no pivoting: the x0-block is eliminated first, expected pivot signs + / -)
 // =====================================================================================================
-__global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int kb, int bw, int n0, double eps, double* D,
-                                                        double* Dinv, double* diagW, int* stats) {
+__global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int kb, int bw, int n0, double eps_rel,
+                                                        const double* __restrict__ scale, double* D, double* Dinv,
+                                                        double* diagW, int* stats) {
     __shared__ double Pl[DENSE_NB][DENSE_NB + 1];
     __shared__ double Pw[DENSE_NB][DENSE_NB + 1];
     const int lane = threadIdx.x;
@@ -526,6 +528,7 @@ __global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int k
         }
         double d = __shfl_sync(full, r1, k);
         const double sg = (kb + k < n0) ? 1.0 : -1.0;
+        const double eps = eps_rel * fmax(scale[kb + k], 1e-300);   // relative to the pivot row's original max entry
         if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
         if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
         const double inv = 1.0 / d;
@@ -541,9 +544,9 @@ __global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int k
         atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
     }
 }
-void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps, double* D, double* Dinv, double* diagW, int* stats,
-                       cudaStream_t s) {
-    dense_diag_kernel<<<1, 32, 0, s>>>(A, ld, kb, bw, n0, eps, D, Dinv, diagW, stats);
+void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
+                       double* diagW, int* stats, cudaStream_t s) {
+    dense_diag_kernel<<<1, 32, 0, s>>>(A, ld, kb, bw, n0, eps_rel, scale, D, Dinv, diagW, stats);
     COUNT_LAUNCH();
 }
 
@@ -766,7 +769,7 @@ __device__ __forceinline__ void block_max(double& v, int& idx, double* sv, int* 
 
 __global__ void __launch_bounds__(1024) bk_pivot_kernel(double* A, int ld, int n, int* perm, int8_t* ptype, double* Dd,
                                                         double* De, double* Did, double* Die, double* Wc, BkState* st,
-                                                        double eps) {
+                                                        double eps_rel, const double* __restrict__ scale) {
     __shared__ double sv[32];
     __shared__ int si[32];
     const int k = st->k;
@@ -833,6 +836,7 @@ __global__ void __launch_bounds__(1024) bk_pivot_kernel(double* A, int ld, int n
     if (kstep == 1) {
         double d = A[(int64_t)k * ld + k];
         bool pert = false;
+        const double eps = eps_rel * fmax(scale[perm[k]], 1e-300);   // perm[k] = original row of this pivot
         if (!(fabs(d) >= eps)) { d = (d < 0.0) ? -eps : eps; pert = true; }
         const double inv = 1.0 / d;
         for (int i = k + 1 + tid; i < n; i += nt) {
@@ -889,8 +893,8 @@ __global__ void __launch_bounds__(256) bk_update_kernel(double* A, int ld, int n
 }
 
 void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype, double* Dd, double* De, double* Did,
-                    double* Die, double* Wc, BkState* st, double eps, cudaStream_t s) {
-    bk_pivot_kernel<<<1, 1024, 0, s>>>(A, ld, n, perm, ptype, Dd, De, Did, Die, Wc, st, eps);
+                    double* Die, double* Wc, BkState* st, double eps_rel, const double* scale, cudaStream_t s) {
+    bk_pivot_kernel<<<1, 1024, 0, s>>>(A, ld, n, perm, ptype, Dd, De, Did, Die, Wc, st, eps_rel, scale);
     COUNT_LAUNCH();
     const int lower = step + 1;
     const int rows = n - lower;
@@ -899,6 +903,26 @@ void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype
         bk_update_kernel<<<dim3(nt, nt), dim3(32, 8), 0, s>>>(A, ld, n, Wc, st, lower);
         COUNT_LAUNCH();
     }
+}
+
+// out[i] = max_j |A_sym(i,j)| of the symmetric matrix stored in the lower triangle (non-negative doubles order like
+// their bit patterns, so an integer atomicMax does the reduction)
+__global__ void row_absmax_kernel(const double* __restrict__ A, int ld, int n, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j > i || i >= n) return;
+    const double v = fabs(A[(int64_t)i * ld + j]);
+    if (v > 0.0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        atomicMax(reinterpret_cast<unsigned long long*>(out + i), b);
+        atomicMax(reinterpret_cast<unsigned long long*>(out + j), b);
+    }
+}
+void launch_row_absmax(const double* A, int ld, int n, double* out, cudaStream_t s) {
+    if (n <= 0) return;
+    cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n, s);
+    row_absmax_kernel<<<dim3(cdiv(n, 128), n), 128, 0, s>>>(A, ld, n, out);
+    COUNT_LAUNCH();
 }
 
 __global__ void iota_kernel(int* p, int n) {

@@ -86,7 +86,9 @@ void launch_sc_add_ctdc(double* SC, int ld, int mz, const int* krow, const int* 
 void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* buf, bool unpack, double* SCout, cudaStream_t s);
 int64_t sc_pack_size(int n0, int nl);
 // one block column of the right-looking LDL^T; n0 = number of leading (positive) indices
-void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps, double* D, double* Dinv, double* diagW, int* stats, cudaStream_t s);
+void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
+                       double* diagW, int* stats, cudaStream_t s);
+void launch_row_absmax(const double* A, int ld, int n, double* out, cudaStream_t s);
 void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf, cudaStream_t s);
 void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s);
 void launch_dense_solve(const double* A, int ld, int n, const int* perm, const int8_t* ptype, const double* Dinv,
@@ -94,7 +96,7 @@ void launch_dense_solve(const double* A, int ld, int n, const int* perm, const i
 // Bunch-Kaufman fallback (dsytf2 restated): device-side step counter
 struct BkState { int k, kcur, s, npos, nneg, npert; };
 void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype, double* Dd, double* De, double* Did,
-                    double* Die, double* Wc, BkState* st, double eps, cudaStream_t s);
+                    double* Die, double* Wc, BkState* st, double eps_rel, const double* scale, cudaStream_t s);
 void launch_iota(int* p, int n, cudaStream_t s);
 
 // ---- small vector / CSR helpers for the root-level solve ----

@@ -127,7 +127,7 @@ struct pipsgpu_sc {
     int n0 = 0, my0 = 0, myl = 0, mzl = 0, n = 0;
     DevBuf<double> A;        // assembled matrix, n x n row-major, lower triangle used (owned by the linear system)
     DevBuf<double> Fm;       // the solver's own copy, overwritten by the factors (DeSymIndefSolver.C:65 copies too)
-    DevBuf<double> D, De, Dinv, Dinv_e, diagW, Wbuf, Wc, pack, rhs, swork;
+    DevBuf<double> D, De, Dinv, Dinv_e, diagW, Wbuf, Wc, pack, rhs, swork, scale;
     DevBuf<int> stats, perm;
     DevBuf<int8_t> ptype;
     DevBuf<BkState> bk;
@@ -155,7 +155,8 @@ struct pipsgpu_ctx {
     DevBuf<FrontDesc> fronts;
     DevBuf<LeafDev> leafdev;
     DevBuf<int64_t> kmap, bmap, diagpos;
-    std::vector<double> h_dvals;
+    double* h_dvals = nullptr;      // pinned staging of all leaf diagonals (npos)
+    bool own_stream = true;
 
     FactorArgs factor_args(pipsgpu_sc* sc) {
         FactorArgs a;
@@ -181,7 +182,9 @@ struct pipsgpu_kkt {
     std::vector<pipsgpu_leaf*> leaves;
     std::unique_ptr<pipsgpu_sc> sc;
     bool ready = false;
-    DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl;
+    DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl, b0_in, bl_in;
+    bool have_diag = false, have_rhs = false;
+    double last_regDy = 0.0;
     int64_t sum_nx = 0, sum_nz = 0, sum_n = 0;
     double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[12] = {};
@@ -265,11 +268,14 @@ void sc_factorize_static(pipsgpu_sc* sc) {
     CUDA_CHECK(cudaMemsetAsync(sc->ptype.p, 0, sizeof(int8_t) * (size_t)(n + 1), s));
     CUDA_CHECK(cudaMemsetAsync(sc->Dinv_e.p, 0, sizeof(double) * (size_t)(n + 1), s));
     launch_iota(sc->perm.p, n, s);
-    const double eps = 1e-10;
+    // pivots below 1e-12 * (largest entry of their own original row) are perturbed, in the spirit of PARDISO's pivot
+    // perturbation (iparm[9], PardisoProjectIndefSolver.C:34-61) but scale-aware; the oracle applies the same rule
+    const double eps_rel = 1e-12;
+    launch_row_absmax(sc->A.p, n, n, sc->scale.p, s);
     CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
     for (int kb = 0; kb < n; kb += DENSE_NB) {
         const int bw = std::min(DENSE_NB, n - kb);
-        launch_dense_diag(sc->Fm.p, n, kb, bw, sc->n0, eps, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
+        launch_dense_diag(sc->Fm.p, n, kb, bw, sc->n0, eps_rel, sc->scale.p, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
         launch_dense_trsm(sc->Fm.p, n, n, kb, bw, sc->Dinv.p, sc->diagW.p, sc->Wbuf.p, s);
         launch_dense_syrk(sc->Fm.p, n, n, kb, bw, sc->Wbuf.p, s);
     }
@@ -287,7 +293,7 @@ void sc_factorize_bk(pipsgpu_sc* sc) {
     CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
     for (int step = 0; step < n; ++step)
         launch_bk_step(sc->Fm.p, n, n, step, sc->perm.p, sc->ptype.p, sc->D.p, sc->De.p, sc->Dinv.p, sc->Dinv_e.p, sc->Wc.p,
-                       sc->bk.p, 1e-13, s);
+                       sc->bk.p, 1e-12, sc->scale.p, s);
 }
 
 // factorize: fast static path first; if a pivot had to be perturbed or the inertia is not (n0, n-n0, 0) the matrix is
@@ -353,8 +359,19 @@ int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) NcclApi::get().CommDestroy(ctx->comm);
     for (auto* lf : ctx->leaves) delete lf;
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->h_dvals) cudaFreeHost(ctx->h_dvals);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_set_stream(pipsgpu_ctx* ctx, void* stream) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
     PIPSGPU_CATCH
 }
 
@@ -615,7 +632,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->stats.alloc((size_t)4 * std::max(nl, 1));
     CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMemsetAsync(ctx->De.p, 0, sizeof(double) * ((size_t)npos + 1), s));
-    ctx->h_dvals.assign((size_t)npos, 0.0);
+    CUDA_CHECK(cudaMallocHost(&ctx->h_dvals, sizeof(double) * ((size_t)npos + 1)));
     for (auto* lf : ctx->leaves)
         for (int i = 0; i < lf->n; ++i) ctx->h_dvals[(size_t)lf->pos_off + i] = lf->val[lf->diag_entry[i]];
     CUDA_CHECK(cudaStreamSynchronize(s));
@@ -624,7 +641,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
 }
 
 static void leaf_fill_dvals(pipsgpu_leaf* lf, const double* dd, const double* nomegainv, double regP, double regDy, double regDz) {
-    double* d = lf->ctx->h_dvals.data() + lf->pos_off;
+    double* d = lf->ctx->h_dvals + lf->pos_off;
     for (int i = 0; i < lf->nx; ++i) d[i] = (dd ? dd[i] : 0.0) + regP;
     for (int i = 0; i < lf->ny; ++i) d[lf->nx + i] = -regDy;
     for (int i = 0; i < lf->nz; ++i) d[lf->nx + lf->ny + i] = (nomegainv ? nomegainv[i] : 0.0) - regDz;
@@ -632,7 +649,7 @@ static void leaf_fill_dvals(pipsgpu_leaf* lf, const double* dd, const double* no
 
 static void leaf_push_dvals(pipsgpu_ctx* ctx, int64_t pos_begin, int64_t count) {
     if (count <= 0) return;
-    CUDA_CHECK(cudaMemcpyAsync(ctx->dvals.p + pos_begin, ctx->h_dvals.data() + pos_begin, sizeof(double) * (size_t)count,
+    CUDA_CHECK(cudaMemcpyAsync(ctx->dvals.p + pos_begin, ctx->h_dvals + pos_begin, sizeof(double) * (size_t)count,
                                cudaMemcpyHostToDevice, ctx->stream));
     launch_set_diag(ctx->diagpos.p + pos_begin, ctx->dvals.p + pos_begin, count, ctx->Kval.p, ctx->stream);
 }
@@ -794,7 +811,7 @@ int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsg
     const size_t n = (size_t)sc->n;
     sc->A.alloc(n * n + 1); sc->Fm.alloc(n * n + 1); sc->D.alloc(n + 1); sc->Dinv.alloc(n + 1); sc->diagW.alloc(DENSE_NB * DENSE_NB);
     sc->De.alloc(n + 1); sc->Dinv_e.alloc(n + 1); sc->Wc.alloc(2 * n + 2); sc->perm.alloc(n + 1); sc->ptype.alloc(n + 1);
-    sc->bk.alloc(1); sc->swork.alloc(n + 1);
+    sc->bk.alloc(1); sc->swork.alloc(n + 1); sc->scale.alloc(n + 1);
     sc->Wbuf.alloc(n * DENSE_NB + 2); sc->stats.alloc(4); sc->rhs.alloc(n + 1);
     CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (n * n + 1), ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -980,6 +997,8 @@ int pipsgpu_kkt_setup(pipsgpu_kkt* k, int threads) {
     }
     k->bl.alloc((size_t)k->sum_n + 1);
     k->tl.alloc((size_t)k->sum_n + 1);
+    k->bl_in.alloc((size_t)k->sum_n + 1);
+    k->b0_in.alloc((size_t)k->n0 + k->my0 + k->mz0 + k->myl + k->mzl + 1);
     if (!k->ev_init) {
         for (auto& e : k->ev) CUDA_CHECK(cudaEventCreate(&e));
         k->ev_init = true;
@@ -988,37 +1007,13 @@ int pipsgpu_kkt_setup(pipsgpu_kkt* k, int threads) {
     PIPSGPU_CATCH
 }
 
-int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,
-                          const double* dd_leaves, const double* nomegainv_leaves, const double reg[3], int inertia_root[3]) {
-    PIPSGPU_TRY
-    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_factorize: kkt not set up");
+static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[3]) {
     pipsgpu_ctx* ctx = k->ctx;
-    require_device(ctx);
     cudaStream_t s = ctx->stream;
     pipsgpu_sc* sc = k->sc.get();
-    const double regP = reg ? reg[0] : 0.0, regDy = reg ? reg[1] : 0.0, regDz = reg ? reg[2] : 0.0;
-    CUDA_CHECK(cudaEventRecord(k->ev[0], s));
-    // ---- diagonals down (the only per-iteration H2D payload of the factorisation) ----
-    {
-        const double* dd = dd_leaves;
-        const double* nz = nomegainv_leaves;
-        for (auto* lf : k->leaves) {
-            leaf_fill_dvals(lf, dd, nz, regP, regDy, regDz);
-            if (dd) dd += lf->nx;
-            if (nz) nz += lf->nz;
-        }
-        leaf_push_dvals(ctx, 0, ctx->npos);
-        std::vector<double> h0((size_t)k->n0), hz((size_t)k->mz0), hl((size_t)k->mzl);
-        for (int i = 0; i < k->n0; ++i) h0[i] = (dd0 ? dd0[i] : 0.0) + regP;
-        for (int i = 0; i < k->mz0; ++i) hz[i] = (nomegainv0 ? nomegainv0[i] : 0.0) - regDz;
-        for (int i = 0; i < k->mzl; ++i) hl[i] = (nomegainv_link ? nomegainv_link[i] : 0.0) - regDz;
-        if (k->n0) CUDA_CHECK(cudaMemcpyAsync(k->dd0.p, h0.data(), sizeof(double) * h0.size(), cudaMemcpyHostToDevice, s));
-        if (k->mz0) CUDA_CHECK(cudaMemcpyAsync(k->zdiag0.p, hz.data(), sizeof(double) * hz.size(), cudaMemcpyHostToDevice, s));
-        if (k->mzl) CUDA_CHECK(cudaMemcpyAsync(k->zdiagl.p, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));   // h0/hz/hl are stack-lifetime staging buffers
-    }
     // ---- initializeKKT + leaf LDL^T + Schur terms ----
     CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (size_t)sc->n * sc->n, s));
+    launch_set_diag(ctx->diagpos.p, ctx->dvals.p, ctx->npos, ctx->Kval.p, s);
     factor_prepare(ctx, nullptr);
     CUDA_CHECK(cudaEventRecord(k->ev[1], s));
     run_factor_levels(ctx, sc, nullptr);
@@ -1046,31 +1041,66 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomeg
         CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]));
         k->times[i] = ms;
     }
+}
+
+int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,
+                          const double* dd_leaves, const double* nomegainv_leaves, const double reg[3], int inertia_root[3]) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_factorize: kkt not set up");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    cudaStream_t s = ctx->stream;
+    const double regP = reg ? reg[0] : 0.0, regDy = reg ? reg[1] : 0.0, regDz = reg ? reg[2] : 0.0;
+    CUDA_CHECK(cudaEventRecord(k->ev[0], s));
+    // ---- diagonals down (the only per-iteration H2D payload of the factorisation) ----
+    {
+        const double* dd = dd_leaves;
+        const double* nz = nomegainv_leaves;
+        for (auto* lf : k->leaves) {
+            leaf_fill_dvals(lf, dd, nz, regP, regDy, regDz);
+            if (dd) dd += lf->nx;
+            if (nz) nz += lf->nz;
+        }
+        if (ctx->npos > 0)
+            CUDA_CHECK(cudaMemcpyAsync(ctx->dvals.p, ctx->h_dvals, sizeof(double) * (size_t)ctx->npos, cudaMemcpyHostToDevice, s));
+        std::vector<double> h0((size_t)k->n0), hz((size_t)k->mz0), hl((size_t)k->mzl);
+        for (int i = 0; i < k->n0; ++i) h0[i] = (dd0 ? dd0[i] : 0.0) + regP;
+        for (int i = 0; i < k->mz0; ++i) hz[i] = (nomegainv0 ? nomegainv0[i] : 0.0) - regDz;
+        for (int i = 0; i < k->mzl; ++i) hl[i] = (nomegainv_link ? nomegainv_link[i] : 0.0) - regDz;
+        if (k->n0) CUDA_CHECK(cudaMemcpyAsync(k->dd0.p, h0.data(), sizeof(double) * h0.size(), cudaMemcpyHostToDevice, s));
+        if (k->mz0) CUDA_CHECK(cudaMemcpyAsync(k->zdiag0.p, hz.data(), sizeof(double) * hz.size(), cudaMemcpyHostToDevice, s));
+        if (k->mzl) CUDA_CHECK(cudaMemcpyAsync(k->zdiagl.p, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));   // h0/hz/hl are stack-lifetime staging buffers
+    }
+    k->have_diag = true;
+    k->last_regDy = regDy;
+    kkt_factorize_device(k, regDy, inertia_root);
     PIPSGPU_CATCH
 }
 
-int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
+int pipsgpu_kkt_factorize_resident(pipsgpu_kkt* k, int inertia_root[3]) {
     PIPSGPU_TRY
-    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: kkt not set up");
-    if (!b0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b0");
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_factorize_resident: kkt not set up");
+    if (!k->have_diag) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_factorize_resident: no diagonals on the device yet");
+    require_device(k->ctx);
+    CUDA_CHECK(cudaEventRecord(k->ev[0], k->ctx->stream));
+    kkt_factorize_device(k, k->last_regDy, inertia_root);
+    PIPSGPU_CATCH
+}
+
+// solveCompressed on the device-resident right-hand side (k->b0_in / k->bl_in); result in k->b0 / k->bl
+static void kkt_solve_device(pipsgpu_kkt* k) {
     pipsgpu_ctx* ctx = k->ctx;
-    require_device(ctx);
     pipsgpu_sc* sc = k->sc.get();
-    if (!sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: not factorized");
     cudaStream_t s = ctx->stream;
     const int n0 = k->n0, my0 = k->my0, mz0 = k->mz0, myl = k->myl, mzl = k->mzl;
     const int nb0 = n0 + my0 + mz0 + myl + mzl;
     const int64_t N = ctx->npos;
-    CUDA_CHECK(cudaEventRecord(k->ev[6], s));
-    if (N > 0) {
-        if (!b_leaves) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b_leaves");
-        CUDA_CHECK(cudaMemcpyAsync(k->bl.p, b_leaves, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
-    }
     if (ctx->rank > 0) launch_vec_zero(k->b0.p, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
-    else CUDA_CHECK(cudaMemcpyAsync(k->b0.p, b0, sizeof(double) * (size_t)nb0, cudaMemcpyHostToDevice, s));
+    else launch_vec_copy(k->b0.p, k->b0_in.p, nb0, s);
     SolveArgs sa = ctx->solve_args(ctx->x.p, N, ctx->upd.p, ctx->updtot);
     // ---- Lsolve: z_i = K_i^-1 b_i ; b0 -= Bord_i^T z_i ; allreduce ----
-    launch_gather_perm(ctx->gidx.p, k->bl.p, ctx->x.p, N, 1, N, s);
+    launch_gather_perm(ctx->gidx.p, k->bl_in.p, ctx->x.p, N, 1, N, s);
     run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
     launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->bl.p, N, 1, N, s);
     launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, k->bl.p, k->b0.p, s);
@@ -1106,16 +1136,52 @@ int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
         run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
         launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->tl.p, N, 1, N, s);
         launch_axpy(-1.0, k->tl.p, k->bl.p, N, s);
-        CUDA_CHECK(cudaMemcpyAsync(b_leaves, k->bl.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s));
     }
-    CUDA_CHECK(cudaMemcpyAsync(b0, b, sizeof(double) * (size_t)nb0, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaEventRecord(k->ev[9], s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+static void kkt_solve_times(pipsgpu_kkt* k) {
     float ms;
     for (int i = 0; i < 3; ++i) {
         CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[6 + i], k->ev[7 + i]));
         k->times[5 + i] = ms;
     }
+}
+
+int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: kkt not set up");
+    if (!b0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b0");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    if (!k->sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed: not factorized");
+    cudaStream_t s = ctx->stream;
+    const int nb0 = k->n0 + k->my0 + k->mz0 + k->myl + k->mzl;
+    const int64_t N = ctx->npos;
+    CUDA_CHECK(cudaEventRecord(k->ev[6], s));
+    if (N > 0) {
+        if (!b_leaves) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve_compressed: null b_leaves");
+        CUDA_CHECK(cudaMemcpyAsync(k->bl_in.p, b_leaves, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(k->b0_in.p, b0, sizeof(double) * (size_t)nb0, cudaMemcpyHostToDevice, s));
+    k->have_rhs = true;
+    kkt_solve_device(k);
+    if (N > 0) CUDA_CHECK(cudaMemcpyAsync(b_leaves, k->bl.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(b0, k->b0.p, sizeof(double) * (size_t)nb0, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaEventRecord(k->ev[9], s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    kkt_solve_times(k);
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_solve_compressed_resident(pipsgpu_kkt* k) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed_resident: kkt not set up");
+    if (!k->have_rhs) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed_resident: no right-hand side on the device yet");
+    require_device(k->ctx);
+    if (!k->sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed_resident: not factorized");
+    CUDA_CHECK(cudaEventRecord(k->ev[6], k->ctx->stream));
+    kkt_solve_device(k);
+    CUDA_CHECK(cudaEventRecord(k->ev[9], k->ctx->stream));
     PIPSGPU_CATCH
 }
 
@@ -1124,6 +1190,11 @@ pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* k) { return k ? k->sc.get() : nullptr; }
 int pipsgpu_kkt_stage_times(pipsgpu_kkt* k, double out[8]) {
     PIPSGPU_TRY
     if (!k || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_stage_times: null");
+    if (k->have_rhs) {
+        require_device(k->ctx);
+        CUDA_CHECK(cudaStreamSynchronize(k->ctx->stream));
+        kkt_solve_times(k);
+    }
     for (int i = 0; i < 8; ++i) out[i] = k->times[i];
     PIPSGPU_CATCH
 }

@@ -42,11 +42,13 @@ def create_kkt_lower(ch):
 class CudaRootLinearSystem:
     """Root linear system of a two-level block-angular LP on one GPU (one rank of the reference)."""
 
-    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0):
+    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0, stream=None):
         self.lp = lp
         root = lp.root
         self.rank, self.n_ranks = rank, n_ranks
         self.ctx = capi.Context(device)
+        if stream is not None:
+            self.ctx.set_stream(stream)      # borrow the caller's CUDA stream (raw cudaStream_t)
         if n_ranks > 1:
             assert nccl_uid is not None
             self.ctx.init_comm(nccl_uid, rank, n_ranks)
