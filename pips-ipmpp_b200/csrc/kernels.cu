@@ -122,9 +122,10 @@ __device__ __forceinline__ void update_rows(const FrontDesc& fd, const double* _
     }
 }
 
-__global__ void __launch_bounds__(FT) front_factor_kernel(FactorArgs a, int level_begin) {
-    __shared__ double Pl[MAXW][MAXW + 1];   // pivot block: A on entry, strict lower L on exit
-    __shared__ double Pw[MAXW][MAXW + 1];   // pivot block: W = L*D (strictly below the pivot blocks)
+template <int WP>
+__global__ void __launch_bounds__(FT, (WP == 8 ? 5 : (WP == 16 ? 3 : 2))) front_factor_kernel(FactorArgs a, int level_begin) {
+    __shared__ double Pl[WP][MAXW + 1];   // pivot block: A on entry, strict lower L on exit
+    __shared__ double Pw[WP][MAXW + 1];   // pivot block: W = L*D (strictly below the pivot blocks)
     __shared__ double s_did[MAXW], s_die[MAXW];
     __shared__ int8_t s_pt[MAXW];
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(FT) front_factor_kernel(FactorArgs a, int leve
     }
 
     // ---- 2. pivot block into shared memory ----
-    for (int idx = tid; idx < MAXW * (MAXW + 1); idx += FT) {
+    for (int idx = tid; idx < WP * (MAXW + 1); idx += FT) {
         (&Pl[0][0])[idx] = 0.0;
         (&Pw[0][0])[idx] = 0.0;
     }
@@ -248,25 +249,97 @@ __global__ void __launch_bounds__(FT) front_factor_kernel(FactorArgs a, int leve
     // ---- 4. panel rows, 5. contribution block + Schur complement share ----
     double* Wscr = a.W + fd.Woff;
     const int* rowg = a.rowg + fd.rows_off;
-    if (w <= 8) {
-        panel_rows<8>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
-        __syncthreads();
-        update_rows<8>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
-    } else if (w <= 16) {
-        panel_rows<16>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
-        __syncthreads();
-        update_rows<16>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
-    } else {
-        panel_rows<32>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
-        __syncthreads();
-        update_rows<32>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
-    }
+    const bool big = (u >= BIG_U);   // big fronts: the O(u^2 w) update runs in front_update_tiles_kernel
+    panel_rows<WP>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
+    if (big) return;
+    __syncthreads();
+    update_rows<WP>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
     (void)na;
 }
 
-void launch_front_factor(const FactorArgs& a, int level_begin, int nfronts, cudaStream_t s) {
+// cls = width class of every front in [level_begin, level_begin + nfronts): 0: w<=8, 1: w<=16, 2: w<=32
+void launch_front_factor(const FactorArgs& a, int cls, int level_begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    front_factor_kernel<<<nfronts, FT, 0, s>>>(a, level_begin);
+    if (cls == 0) front_factor_kernel<8><<<nfronts, FT, 0, s>>>(a, level_begin);
+    else if (cls == 1) front_factor_kernel<16><<<nfronts, FT, 0, s>>>(a, level_begin);
+    else front_factor_kernel<32><<<nfronts, FT, 0, s>>>(a, level_begin);
+    COUNT_LAUNCH();
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Tiled update of the big fronts on the FP64 tensor pipe: one CTA per 64x64 tile (i-block >= j-block) of
+//   U = L21 * W21^T   (u x u, K = front width padded to 8/16/32),
+// C(i,j) -= U(i,j) for ancestor columns j < na, Schur complement -= U(i,j) for border x border (red.global.add.f64).
+// Operands are staged in shared memory (stride 36 doubles: conflict-free m8n8k4 fragment loads).
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+constexpr int TLD = 36;
+__global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, int64_t tile_begin) {
+    __shared__ double As[TILE * TLD];
+    __shared__ double Bs[TILE * TLD];
+    const TileDesc td = a.tiles[tile_begin + blockIdx.x];
+    const FrontDesc fd = a.fronts[td.front];
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
+    const int wp = padded_width(w);
+    const double* F = a.L + fd.Loff;
+    const double* Wscr = a.W + fd.Woff;
+    const int i0 = td.bi * TILE, j0 = td.bj * TILE;
+    const int tid = threadIdx.x;
+    // A tile: L rows i0.. (column-major panel: coalesced along rows), B tile: W rows j0.. (row-major scratch)
+    for (int idx = tid; idx < TILE * 32; idx += 128) {
+        const int k = idx >> 6, r = idx & 63;
+        As[r * TLD + k] = (k < w && i0 + r < u) ? F[(size_t)k * m + w + i0 + r] : 0.0;
+    }
+    for (int idx = tid; idx < TILE * 32; idx += 128) {
+        const int r = idx >> 5, k = idx & 31;
+        Bs[r * TLD + k] = (k < wp && j0 + r < u) ? Wscr[(size_t)(j0 + r) * wp + k] : 0.0;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    for (int k0 = 0; k0 < wp; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) af[x] = As[(wr + x * 8 + lr) * TLD + k0 + lk];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) bf[y] = Bs[(wc + y * 8 + lr) * TLD + k0 + lk];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+    }
+    double* Cs = a.C + fd.Coff;
+    const int* rowg = a.rowg + fd.rows_off;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int gi = i0 + wr + x * 8 + lr;
+        if (gi >= u) continue;
+        const int64_t scrow = (gi >= na && a.SC) ? (int64_t)rowg[gi] * a.ldsc : 0;
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = j0 + wc + y * 8 + lk * 2 + e;
+                if (gj > gi) continue;
+                const double v = acc[x][y][e];
+                if (gj < na) Cs[(size_t)gj * u + gi] -= v;
+                else if (a.SC) atomicAdd(&a.SC[scrow + rowg[gj]], -v);
+            }
+    }
+}
+void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s) {
+    if (ntiles <= 0) return;
+    front_update_tiles_kernel<<<(unsigned)ntiles, 128, 0, s>>>(a, tile_begin);
     COUNT_LAUNCH();
 }
 
@@ -294,13 +367,42 @@ void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_
 
 constexpr int SW = 4;   // warps (= fronts) per solve CTA
 
-__global__ void __launch_bounds__(SW * 32) fwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
+// All global loads of a front are issued up-front into registers (independent, predicated) so that the substitution
+// loops run on registers + shuffles only: the solves are latency-bound, not bandwidth-bound.
+template <int WP>
+__device__ __forceinline__ void fwd_front(const FrontDesc& fd, const double* __restrict__ F, double* __restrict__ x,
+                                          double* __restrict__ us, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    double lrow[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) lrow[k] = (k < w && lane > k && lane < w) ? F[(size_t)k * m + lane] : 0.0;
+    double y = (lane < w) ? x[fd.col0 + lane] : 0.0;
+#pragma unroll
+    for (int k = 0; k < WP; ++k) {
+        const double yk = __shfl_sync(full, y, k);
+        y = fma(-lrow[k], yk, y);
+    }
+    if (lane < w) x[fd.col0 + lane] = y;
+    for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        double v[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < WP; ++k) acc = fma(v[k], __shfl_sync(full, y, k), acc);
+        if (i < na) us[i] -= acc;
+    }
+}
+
+template <int WP>
+__global__ void __launch_bounds__(SW * 32, (WP == 8 ? 8 : (WP == 16 ? 5 : 3))) fwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * SW + warp;
     if (fi >= nfronts) return;
-    const unsigned full = 0xffffffffu;
     const FrontDesc fd = a.fronts[a.level_fronts[level_begin + fi]];
-    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    const int w = fd.w, na = fd.na;
     double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
     double* upd = a.upd + (int64_t)blockIdx.y * a.upd_stride;
     double* us = upd + fd.upd_off;
@@ -320,57 +422,82 @@ __global__ void __launch_bounds__(SW * 32) fwd_level_kernel(SolveArgs a, int lev
         }
         __syncwarp();
     }
-    double y = (lane < w) ? x[fd.col0 + lane] : 0.0;
-    for (int k = 0; k < w; ++k) {
-        const double yk = __shfl_sync(full, y, k);
-        if (lane > k && lane < w) y -= F[(size_t)k * m + lane] * yk;
-    }
-    if (lane < w) x[fd.col0 + lane] = y;
-    for (int i0 = 0; i0 < na; i0 += 32) {
-        const int i = i0 + lane;
-        double acc = 0.0;
-        for (int k = 0; k < w; ++k) {
-            const double yk = __shfl_sync(full, y, k);
-            if (i < na) acc = fma(F[(size_t)k * m + w + i], yk, acc);
-        }
-        if (i < na) us[i] -= acc;
-    }
+    fwd_front<WP>(fd, F, x, us, lane);
 }
 
-__global__ void __launch_bounds__(SW * 32) bwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fi = blockIdx.x * SW + warp;
-    if (fi >= nfronts) return;
+template <int WP>
+__device__ __forceinline__ void bwd_front(const FrontDesc& fd, const double* __restrict__ F, double* __restrict__ x,
+                                          const int* __restrict__ rowg, int lane) {
     const unsigned full = 0xffffffffu;
-    const FrontDesc fd = a.fronts[a.level_fronts[level_begin + fi]];
     const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
-    double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
-    const double* F = a.L + fd.Loff;
-    const int* rowg = a.rowg + fd.rows_off;
-
-    double t = (lane < w) ? x[fd.col0 + lane] : 0.0;
-    for (int k = 0; k < w; ++k) {
-        double s = 0.0;
-        for (int i = lane; i < na; i += 32) s = fma(F[(size_t)k * m + w + i], x[rowg[i]], s);
+    double lcol[WP];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
-        if (lane == k) t -= s;
+    for (int k = 0; k < WP; ++k) lcol[k] = (lane < k && k < w) ? F[(size_t)lane * m + k] : 0.0;
+    double t = (lane < w) ? x[fd.col0 + lane] : 0.0;
+    double sacc[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) sacc[k] = 0.0;
+    for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        const double xi = (i < na) ? x[rowg[i]] : 0.0;
+        double v[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < WP; ++k) sacc[k] = fma(v[k], xi, sacc[k]);
     }
-    for (int k = w - 1; k >= 0; --k) {
+    // reduce over the 32 lanes: plain xor-reduction for the lane bits >= WP, then a butterfly transpose-reduce;
+    // afterwards lane k (< WP) holds the total of column k
+#pragma unroll
+    for (int o = 16; o >= WP; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < WP; ++j) sacc[j] += __shfl_xor_sync(full, sacc[j], o);
+    }
+#pragma unroll
+    for (int o = (WP < 32 ? WP / 2 : 16); o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const double send = hi ? sacc[j] : sacc[j + o];
+            const double keep = hi ? sacc[j + o] : sacc[j];
+            sacc[j] = keep + __shfl_xor_sync(full, send, o);
+        }
+    }
+    t -= sacc[0];
+#pragma unroll
+    for (int k = WP - 1; k >= 0; --k) {
         const double xk = __shfl_sync(full, t, k);
-        if (lane < k) t -= F[(size_t)lane * m + k] * xk;
+        t = fma(-lcol[k], xk, t);
     }
     if (lane < w) x[fd.col0 + lane] = t;
 }
 
-void launch_fwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
+template <int WP>
+__global__ void __launch_bounds__(SW * 32, (WP == 8 ? 5 : (WP == 16 ? 3 : 2))) bwd_level_kernel(SolveArgs a, int level_begin, int nfronts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SW + warp;
+    if (fi >= nfronts) return;
+    const FrontDesc fd = a.fronts[a.level_fronts[level_begin + fi]];
+    double* x = a.x + (int64_t)blockIdx.y * a.x_stride;
+    const double* F = a.L + fd.Loff;
+    const int* rowg = a.rowg + fd.rows_off;
+    bwd_front<WP>(fd, F, x, rowg, lane);
+}
+
+void launch_fwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
     if (nfronts <= 0 || nrhs <= 0) return;
-    fwd_level_kernel<<<dim3(cdiv(nfronts, SW), nrhs), SW * 32, 0, s>>>(a, level_begin, nfronts);
+    const dim3 g(cdiv(nfronts, SW), nrhs);
+    if (cls == 0) fwd_level_kernel<8><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
+    else if (cls == 1) fwd_level_kernel<16><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
+    else fwd_level_kernel<32><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
     COUNT_LAUNCH();
 }
-void launch_bwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
+void launch_bwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s) {
     if (nfronts <= 0 || nrhs <= 0) return;
-    bwd_level_kernel<<<dim3(cdiv(nfronts, SW), nrhs), SW * 32, 0, s>>>(a, level_begin, nfronts);
+    const dim3 g(cdiv(nfronts, SW), nrhs);
+    if (cls == 0) bwd_level_kernel<8><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
+    else if (cls == 1) bwd_level_kernel<16><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
+    else bwd_level_kernel<32><<<g, SW * 32, 0, s>>>(a, level_begin, nfronts);
     COUNT_LAUNCH();
 }
 
@@ -590,11 +717,6 @@ void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* D
 // trailing update  A(i,j) -= sum_k L(i,kb+k) * W(j,k)  for i >= j >= kb+bw  on the FP64 tensor pipe.
 // CTA tile 64x64, 4 warps x (32x32), K = 32 (one block column); operands staged in shared memory (stride 36
 // doubles => the m8n8k4 fragment loads are bank-conflict free).
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 constexpr int SY_T = 64, SY_LD = 36;
 __global__ void __launch_bounds__(128) dense_syrk_kernel(double* A, int ld, int n, int kb, int bw, const double* __restrict__ Wbuf) {
     const int t0 = kb + bw;

@@ -8,6 +8,10 @@ namespace pipsgpu {
 
 constexpr int MAXW = 32;         // maximum front width (pivot columns); symbolic analysis splits wider supernodes
 constexpr int DENSE_NB = 32;     // block size of the dense root LDL^T
+constexpr int BIG_U = 128;       // fronts with at least this many off-diagonal rows update through the tiled DMMA kernel
+constexpr int TILE = 64;         // output tile of the tiled update
+
+struct TileDesc { int front, bi, bj, pad; };
 
 // One front (supernode) of one scenario block. All offsets index context-wide pools.
 struct FrontDesc {
@@ -30,6 +34,8 @@ struct LeafDev {
 };
 
 __host__ __device__ inline int padded_width(int w) { return w <= 8 ? 8 : (w <= 16 ? 16 : 32); }
+__host__ __device__ inline int width_class(int w) { return w <= 8 ? 0 : (w <= 16 ? 1 : 2); }
+constexpr int NCLS = 3;          // launches are grouped by (tree level, width class)
 
 struct FactorArgs {
     const FrontDesc* fronts;
@@ -48,6 +54,7 @@ struct FactorArgs {
     double* SC;                  // dense Schur complement, lower, row-major (may be null)
     int ldsc;
     int* stats;                  // per leaf: {positive, negative, zero, perturbed}
+    const TileDesc* tiles;       // update tiles of the big fronts, grouped by level
 };
 
 struct SolveArgs {
@@ -67,11 +74,12 @@ struct SolveArgs {
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
 void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
-void launch_front_factor(const FactorArgs& a, int level_begin, int nfronts, cudaStream_t s);
+void launch_front_factor(const FactorArgs& a, int cls, int level_begin, int nfronts, cudaStream_t s);
+void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
 void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
-void launch_fwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s);
-void launch_bwd_level(const SolveArgs& a, int level_begin, int nfronts, int nrhs, cudaStream_t s);
+void launch_fwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s);
+void launch_bwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s);
 void launch_diag_solve(const SolveArgs& a, int64_t npos, int nrhs, cudaStream_t s);
 // b0[bidx[k]] -= val[k] * z[brow[k]]   /   t[brow[k]] += val[k] * u[bidx[k]]
 void launch_border_tmult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* z, double* b0, cudaStream_t s);

@@ -115,6 +115,7 @@ struct pipsgpu_leaf {
     int64_t Lbase = 0, Lsize = 0, Cbase = 0, Csize = 0, kval_off = 0, bval_off = 0, upd_base = 0, upd_size = 0;
     int front_base = 0;
     std::vector<int> level_begin, level_count;   // per global level: sub-range of level_fronts owned by this leaf
+    std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double flops = 0;
     int inertia[3] = {0, 0, 0};
@@ -148,7 +149,9 @@ struct pipsgpu_ctx {
     // pools
     int64_t npos = 0, nfronts = 0, Ltot = 0, Ctot = 0, Wtot = 0, updtot = 0, nnzK = 0, nnzB = 0;
     int nlevels = 0;
-    std::vector<int> level_ptr;     // nlevels+1 into level_fronts, deepest level first: order[0] = deepest
+    std::vector<int> level_ptr;     // nlevels*NCLS+1 into level_fronts; group g = level_order*NCLS + width class, deepest level first
+    std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
+    DevBuf<TileDesc> tiles;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
     DevBuf<int> rowg, relidx, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
     DevBuf<int8_t> ptype, sgn;
@@ -163,7 +166,7 @@ struct pipsgpu_ctx {
         a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p;
         a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p; a.W = W.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
-        a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p;
+        a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         return a;
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
@@ -216,10 +219,11 @@ void analyze_one(pipsgpu_leaf* lf) {
 void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_leaf* only, int64_t npos_range_begin,
                     int64_t npos_range_count) {
     cudaStream_t s = ctx->stream;
-    for (int lv = 0; lv < ctx->nlevels; ++lv) {   // order index 0 = deepest level
-        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
-        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
-        launch_fwd_level(sa, begin, count, nrhs, s);
+    const int ngroups = ctx->nlevels * NCLS;
+    for (int g = 0; g < ngroups; ++g) {   // group 0 = deepest level
+        int begin = ctx->level_ptr[g], count = ctx->level_ptr[g + 1] - ctx->level_ptr[g];
+        if (only) { begin = only->level_begin[g]; count = only->level_count[g]; }
+        launch_fwd_level(sa, g % NCLS, begin, count, nrhs, s);
     }
     {
         SolveArgs d = sa;
@@ -230,10 +234,10 @@ void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_lea
         d.Die = sa.Die + npos_range_begin;
         launch_diag_solve(d, npos_range_count, nrhs, s);
     }
-    for (int lv = ctx->nlevels - 1; lv >= 0; --lv) {
-        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
-        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
-        launch_bwd_level(sa, begin, count, nrhs, s);
+    for (int g = ngroups - 1; g >= 0; --g) {
+        int begin = ctx->level_ptr[g], count = ctx->level_ptr[g + 1] - ctx->level_ptr[g];
+        if (only) { begin = only->level_begin[g]; count = only->level_count[g]; }
+        launch_bwd_level(sa, g % NCLS, begin, count, nrhs, s);
     }
 }
 
@@ -241,9 +245,15 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
     cudaStream_t s = ctx->stream;
     FactorArgs fa = ctx->factor_args(sc);
     for (int lv = 0; lv < ctx->nlevels; ++lv) {
-        int begin = ctx->level_ptr[lv], count = ctx->level_ptr[lv + 1] - ctx->level_ptr[lv];
-        if (only) { begin = only->level_begin[lv]; count = only->level_count[lv]; }
-        launch_front_factor(fa, begin, count, s);
+        for (int c = 0; c < NCLS; ++c) {
+            const int g = lv * NCLS + c;
+            int begin = ctx->level_ptr[g], count = ctx->level_ptr[g + 1] - ctx->level_ptr[g];
+            if (only) { begin = only->level_begin[g]; count = only->level_count[g]; }
+            launch_front_factor(fa, c, begin, count, s);
+        }
+        int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
+        if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
+        launch_front_update_tiles(fa, tb, tc, s);
     }
 }
 
@@ -542,19 +552,23 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     std::vector<int> bg_row((size_t)nnzB), bg_sc((size_t)nnzB), bg_b0((size_t)nnzB);
     std::vector<LeafDev> leafdev((size_t)nl);
     // level lists: order index 0 = deepest level; within a level fronts are grouped by leaf
-    std::vector<int> level_count(nlev, 0);
+    const int ngroups = nlev * NCLS;
+    auto group_of = [&](const LeafSymbolic& S, int s) {
+        return (nlev - 1 - S.sn_level[s]) * NCLS + width_class(S.sn_col[s + 1] - S.sn_col[s]);
+    };
+    std::vector<int> level_count(ngroups, 0);
     for (auto* lf : ctx->leaves)
-        for (int s = 0; s < lf->S.ns; ++s) ++level_count[nlev - 1 - lf->S.sn_level[s]];
-    ctx->level_ptr.assign(nlev + 1, 0);
-    for (int l = 0; l < nlev; ++l) ctx->level_ptr[l + 1] = ctx->level_ptr[l] + level_count[l];
+        for (int s = 0; s < lf->S.ns; ++s) ++level_count[group_of(lf->S, s)];
+    ctx->level_ptr.assign(ngroups + 1, 0);
+    for (int l = 0; l < ngroups; ++l) ctx->level_ptr[l + 1] = ctx->level_ptr[l] + level_count[l];
     std::vector<int> level_fronts((size_t)nfr), lfill(ctx->level_ptr.begin(), ctx->level_ptr.end() - 1);
     std::vector<int64_t> wfill(nlev, 0);
 
     int64_t rows_off = 0, child_off = 0;
     for (auto* lf : ctx->leaves) {
         const LeafSymbolic& S = lf->S;
-        lf->level_begin.assign(nlev, 0); lf->level_count.assign(nlev, 0);
-        for (int l = 0; l < nlev; ++l) lf->level_begin[l] = lfill[l];
+        lf->level_begin.assign(ngroups, 0); lf->level_count.assign(ngroups, 0);
+        for (int l = 0; l < ngroups; ++l) lf->level_begin[l] = lfill[l];
         auto b2sc = [&](int b) { return b < lf->n0 ? b : b + lf->my0; };
         int64_t upd = lf->upd_base;
         for (int s = 0; s < S.ns; ++s) {
@@ -568,8 +582,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.parent = S.sn_parent[s] < 0 ? -1 : lf->front_base + S.sn_parent[s];
             fd.upd_off = upd; upd += fd.na;
             const int ol = nlev - 1 - S.sn_level[s];
-            level_fronts[(size_t)lfill[ol]++] = lf->front_base + s;
-            ++lf->level_count[ol];
+            const int grp = group_of(S, s);
+            level_fronts[(size_t)lfill[grp]++] = lf->front_base + s;
+            ++lf->level_count[grp];
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
@@ -616,6 +631,39 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
+    // ---- update tiles of the big fronts, grouped by (level, leaf) ----
+    std::vector<TileDesc> tiles;
+    {
+        for (auto* lf : ctx->leaves) { lf->tile_begin.assign(nlev, 0); lf->tile_count.assign(nlev, 0); }
+        auto ntiles_of = [](const FrontDesc& fd) -> int64_t {
+            const int u = fd.na + fd.nb;
+            if (u < BIG_U) return 0;
+            const int64_t nt = (u + TILE - 1) / TILE;
+            return nt * (nt + 1) / 2;
+        };
+        for (auto* lf : ctx->leaves)
+            for (int s2 = 0; s2 < lf->S.ns; ++s2)
+                lf->tile_count[nlev - 1 - lf->S.sn_level[s2]] += ntiles_of(fronts[(size_t)lf->front_base + s2]);
+        ctx->tile_ptr.assign(nlev + 1, 0);
+        for (int l = 0; l < nlev; ++l) {
+            int64_t run = ctx->tile_ptr[l];
+            for (auto* lf : ctx->leaves) { lf->tile_begin[l] = run; run += lf->tile_count[l]; }
+            ctx->tile_ptr[l + 1] = run;
+        }
+        tiles.resize((size_t)ctx->tile_ptr[nlev]);
+        for (auto* lf : ctx->leaves) {
+            std::vector<int64_t> fill(lf->tile_begin);
+            for (int s2 = 0; s2 < lf->S.ns; ++s2) {
+                const FrontDesc& fd = fronts[(size_t)lf->front_base + s2];
+                const int u = fd.na + fd.nb;
+                if (u < BIG_U) continue;
+                const int ol = nlev - 1 - lf->S.sn_level[s2];
+                const int nt = (u + TILE - 1) / TILE;
+                for (int bi = 0; bi < nt; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) tiles[(size_t)fill[ol]++] = TileDesc{lf->front_base + s2, bi, bj, 0};
+            }
+        }
+    }
 
     cudaStream_t s = ctx->stream;
     ctx->fronts.upload(fronts, s); ctx->rowg.upload(rowg, s); ctx->relidx.upload(relidx, s);
@@ -624,6 +672,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->diagpos.upload(diagpos, s); ctx->Kval.upload(kval, s); ctx->Bval.upload(bval, s);
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
+    ctx->tiles.upload(tiles, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
     ctx->Die.alloc((size_t)npos + 1);
