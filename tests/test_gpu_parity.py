@@ -220,3 +220,99 @@ def test_dense_root_solver_bunch_kaufman(pkg, kind):
     assert _rel(X, np.linalg.solve(S, B.T).T) <= 1e-9
     sc.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["c1_hier_4blocks", "synthetic_T1"])
+def test_against_committed_golden_fixtures(pkg, name):
+    """CUDA path vs tests/golden/*.npz (oracle output pinned against the reference's end-to-end goldens and a dense
+    numpy evaluation by tests/golden/make_golden.py): Schur complement <= 1e-10 rel. Frobenius on the recorded IPM
+    iterates, solveCompressed <= 1e-8."""
+    import os
+    from test_oracle_golden import GOLD, _split
+    P = pkg.problem
+    lp = {"c1_hier_4blocks": P.c1_hier_4blocks, "synthetic_T1": lambda: P.synthetic("T1")}[name]()
+    fx = np.load(os.path.join(GOLD, name + ".npz"))
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    for k in fx["picks"]:
+        dd, nom = _split(lp, fx[f"k{k}_dd"], "dd"), _split(lp, fx[f"k{k}_nom"], "nom")
+        inertia = gpu.factorize(dd, nom)
+        assert _rel(gpu.schur_complement(), fx[f"k{k}_sc"]) <= 1e-10
+        assert inertia == tuple(fx[f"k{k}_inertia"])
+        rhs = _split(lp, fx[f"k{k}_rhs"], "rhs")
+        got = gpu.solve_compressed([r.copy() for r in rhs])
+        assert _rel(np.concatenate(got), fx[f"k{k}_sol"]) <= 1e-8
+    gpu.close()
+
+
+def _two_gpu_worker(rank, world, port, cfg, q):
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)    # only ships the NCCL unique id
+    try:
+        pkg = g.load_package()
+        P = pkg.problem
+        obj = [pkg.capi.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nblocks = P.CONFIGS[cfg][0]
+        lo, hi = pkg.capi.partition(nblocks, world)[rank]
+        lp = P.synthetic(cfg, block_range=(lo, hi))
+        dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+        sys_ = pkg.linsys.CudaRootLinearSystem(lp, device=rank, rank=rank, n_ranks=world, nccl_uid=obj[0])
+        inertia = sys_.factorize(dd, nom)
+        sc = sys_.schur_complement()
+        rng = np.random.default_rng(11)
+        b0 = rng.standard_normal(sys_.nb0)
+        nK = lp.children[0].n + lp.children[0].my + lp.children[0].mz
+        ball = rng.standard_normal((nblocks, nK))
+        # ranks > 0 pass garbage in b0: the reference ignores it (sLinsysRootAug.C:332-333)
+        rhs = [b0.copy() if rank == 0 else np.full(sys_.nb0, 1e30)] + [ball[i].copy() for i in range(lo, hi)]
+        sol = sys_.solve_compressed(rhs)
+        q.put((rank, lo, hi, inertia, sc, sol[0], np.stack(sol[1:])))
+        dist.barrier()
+        sys_.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", ["T2", "T3"])
+def test_two_gpus_nccl_allreduce_equals_single_rank_oracle(pkg, cfg):
+    """blocks partitioned over 2 GPUs as mapChildrenToNSubTrees does over 2 MPI ranks; reduceKKT and the Lsolve b0
+    reduction run as ncclAllReduce. Needs 2 visible GPUs (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from oracle.linsys import OracleRoot
+    from test_multirank_gloo import _free_port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, cfg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    P = pkg.problem
+    lp = P.synthetic(cfg)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+    ref = OracleRoot(lp)
+    ref.put_diagonals(dd, nom)
+    ref.factor2()
+    rng = np.random.default_rng(11)
+    b0 = rng.standard_normal(res[0][5].shape[0])
+    nK = lp.children[0].n + lp.children[0].my + lp.children[0].mz
+    ball = rng.standard_normal((len(lp.children), nK))
+    want = ref.solve_compressed([b0.copy()] + [ball[i].copy() for i in range(len(lp.children))])
+    for rank, lo, hi, inertia, sc, sol0, soll in res:
+        assert _rel(sc, np.tril(ref.SC)) <= 1e-10
+        assert inertia == ref.inertia()
+        assert _rel(sol0, want[0]) <= 1e-8
+        assert _rel(soll, np.stack(want[1 + lo:1 + hi])) <= 1e-8

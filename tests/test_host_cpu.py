@@ -1,0 +1,203 @@
+"""CPU tests (-m "not gpu") of the host side of the product: the C-ABI library loads and exports every symbol
+include/pipsgpu.h declares, fails loudly without a device (no CPU fallback), the rank partition equals the
+reference's mapChildrenToNSubTrees, and the symbolic analysis (matching, nested dissection, supernodes, front tree)
+produces a structurally valid elimination plan."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "pipsgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pipsgpu_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.capi.lib()
+    names = _declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.pipsgpu_version() >= 100
+
+
+def test_no_device_means_error_not_fallback(pkg):
+    """without a GPU every compute entry point must fail with PIPSGPU_ERR_NO_DEVICE (2) - never compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.capi.PipsGpuError) as e:
+        pkg.capi.Context(0)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch oracle/"""
+    pkgdir = os.path.join(ROOT, "pips-ipmpp_b200")
+    for dp, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".hpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "oracle/" not in src or f.endswith(".py") is False or "import" not in src.split("oracle/")[0][-40:], f
+
+
+def _reference_partition(N, P):
+    """mapChildrenToNSubTrees restated independently (Readers/Distributed/DistributedTree.C:437-475)"""
+    sizes = [N // P] * P
+    left = N % P
+    if left:
+        free = P - left
+        after, extra = divmod(free, left)
+        i = assigned = 0
+        while i < P:
+            sizes[i] += 1
+            i += 1
+            if extra != assigned:
+                i += 1
+                assigned += 1
+            i += after
+    out, off = [], 0
+    for s in sizes:
+        out.append((off, off + s))
+        off += s
+    return out
+
+
+@pytest.mark.parametrize("N,P", [(4, 2), (64, 1), (512, 8), (128, 8), (8192, 8), (10, 4), (7, 3), (13, 5), (9, 8), (5, 5)])
+def test_partition_matches_reference(pkg, N, P):
+    from oracle.linsys import partition_children
+    got = pkg.capi.partition(N, P)
+    assert got == _reference_partition(N, P) == partition_children(N, P)
+    assert got[0][0] == 0 and got[-1][1] == N
+    assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    sizes = [hi - lo for lo, hi in got]
+    assert max(sizes) - min(sizes) <= 1 and sum(sizes) == N
+
+
+def test_partition_rejects_more_ranks_than_children(pkg):
+    with pytest.raises(pkg.capi.PipsGpuError):
+        pkg.capi.partition(3, 4)      # DistributedTree.C:56-60 enforces P <= N
+
+
+def _symbolic(pkg, lp, i, max_width=0):
+    from oracle import mf
+    ch = lp.children[i]
+    krow, jcol, val, diag_pos, nB, brow, bcol, bval = mf.leaf_kkt_and_border(lp, i)
+    sym = pkg.capi.Symbolic(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol, max_width)
+    return sym, (krow, jcol, val, nB, brow, bcol)
+
+
+@pytest.mark.parametrize("cfg,max_width", [("T1", 0), ("T2", 0), ("T3", 8), ("T3", 32)])
+def test_symbolic_analysis_invariants(pkg, cfg, max_width):
+    lp = pkg.problem.synthetic(cfg)
+    ch = lp.children[0]
+    sym, (krow, jcol, val, nB, brow, bcol) = _symbolic(pkg, lp, 0, max_width)
+    a = sym.export()
+    n, ns = a["n"], a["ns"]
+    perm = a["perm"]
+    assert sorted(perm.tolist()) == list(range(n))
+    iperm = np.empty(n, int); iperm[perm] = np.arange(n)
+    # 2x2 pivots: (primal, equality-row) pairs adjacent, first is a primal column, second an equality row
+    pt = a["ptype"]
+    firsts = np.nonzero(pt == 1)[0]
+    assert np.all(pt[firsts + 1] == 2) and sym.sizes["n_pairs"] == len(firsts)
+    assert np.all(perm[firsts] < ch.n) and np.all((perm[firsts + 1] >= ch.n) & (perm[firsts + 1] < ch.n + ch.my))
+    # every equality row (zero diagonal) is covered by a 2x2 pivot
+    assert len(firsts) == ch.my
+    assert np.all(a["sgn"] == np.where(perm < ch.n, 1, -1))
+    # supernodes: contiguous cover, bounded width, never split a pair
+    col = a["sn_col"]
+    assert col[0] == 0 and col[-1] == n and np.all(np.diff(col) >= 1)
+    assert np.diff(col).max() <= (max_width or 32)
+    assert not np.any(pt[col[1:-1]] == 2)
+    # rows of each front ascending, strictly after its columns; parent = front owning the first non-border row
+    rp, rows = a["sn_rowptr"], a["rowidx"]
+    sn_of = np.repeat(np.arange(ns), np.diff(col))
+    for s in range(ns):
+        r = rows[rp[s]:rp[s + 1]]
+        assert np.all(np.diff(r) > 0)
+        assert len(r) == a["sn_na"][s] + a["sn_nb"][s]
+        if len(r):
+            assert r[0] >= col[s + 1]
+        na = a["sn_na"][s]
+        assert np.all(r[:na] < n) and np.all(r[na:] >= n) and np.all(r[na:] < n + nB)
+        p = a["sn_parent"][s]
+        if na > 0:
+            assert p == sn_of[r[0]] and a["sn_level"][s] == a["sn_level"][p] + 1
+            # relative indices address the same global row in the parent front
+            prow = np.concatenate([np.arange(col[p], col[p + 1]), rows[rp[p]:rp[p + 1]]])
+            assert np.array_equal(prow[a["relidx"][rp[s]:rp[s + 1]]], r)
+        else:
+            assert p == -1 and a["sn_level"][s] == 0
+    # every entry of K and of the border lands inside its front panel, no two entries on the same slot
+    assert len(np.unique(a["kmap"])) == len(a["kmap"])
+    assert a["kmap"].min() >= 0 and a["kmap"].max() < a["Loff"][-1]
+    if len(a["bmap"]):
+        both = np.concatenate([a["kmap"], a["bmap"]])
+        assert len(np.unique(both)) == len(both) and a["bmap"].max() < a["Loff"][-1]
+    # the symbolic structure contains the exact Cholesky structure of P K P^T (checked against a dense symbolic run)
+    if n <= 400:
+        S = np.zeros((n, n), bool)
+        for i in range(n):
+            for q in range(krow[i], krow[i + 1]):
+                pi, pj = iperm[i], iperm[jcol[q]]
+                S[max(pi, pj), min(pi, pj)] = True
+        for j in range(n):
+            r = np.nonzero(S[j + 1:, j])[0] + j + 1
+            if len(r):
+                S[np.ix_(r, r)] |= np.tri(len(r), dtype=bool)
+        for s in range(ns):
+            front_rows = set(range(col[s], col[s + 1])) | set(int(v) for v in rows[rp[s]:rp[s + 1]] if v < n)
+            for j in range(col[s], col[s + 1]):
+                need = set(np.nonzero(S[j:, j])[0] + j)
+                assert need <= front_rows
+        assert sym.sizes["nnzL"] == int(np.tril(S).sum())
+
+
+def test_symbolic_is_deterministic_and_counts_flops(pkg):
+    lp = pkg.problem.synthetic("T2")
+    s1, _ = _symbolic(pkg, lp, 1)
+    s2, _ = _symbolic(pkg, lp, 1)
+    a, b = s1.export(), s2.export()
+    assert all(np.array_equal(a[k], b[k]) for k in a if isinstance(a[k], np.ndarray))
+    assert s1.flops == s2.flops > 0
+    # sum_j eta_j (eta_j + 2) >= 3 * eta(L) for eta_j >= 1
+    eta = s1.sizes["nnzL"] - s1.sizes["n"]
+    assert s1.flops >= eta
+
+
+def test_create_kkt_lower_layout(pkg):
+    """create_kkt (DistributedLeafLinearSystem.C:52-72): lower CSR, full diagonal, W rows at nx.., D rows at nx+my.."""
+    lp = pkg.problem.synthetic("T1")
+    ch = lp.children[0]
+    krow, jcol, val = pkg.linsys.create_kkt_lower(ch)
+    nK = ch.n + ch.my + ch.mz
+    assert len(krow) == nK + 1 and krow[-1] == len(jcol) == nK + ch.W.nnz + ch.D.nnz
+    for i in range(nK):
+        cols = jcol[krow[i]:krow[i + 1]]
+        assert np.all(np.diff(cols) > 0) and cols[-1] == i
+    import scipy.sparse as sp
+    K = sp.csr_matrix((val, jcol, krow), shape=(nK, nK)).toarray()
+    assert np.array_equal(K[ch.n:ch.n + ch.my, :ch.n], ch.W.toarray())
+    assert np.array_equal(K[ch.n + ch.my:, :ch.n], ch.D.toarray())
+    assert np.all(np.diag(K) == 0)
+
+
+def test_synthetic_generator_is_deterministic_and_shaped(pkg):
+    P = pkg.problem
+    a, b = P.synthetic("T2"), P.synthetic("T2")
+    assert (a.children[3].W != b.children[3].W).nnz == 0
+    # a rank's slice of the blocks is identical to the same blocks of the whole problem (contiguous partition)
+    part = P.synthetic("T2", block_range=(2, 4))
+    assert len(part.children) == 2 and (part.children[0].W != a.children[2].W).nnz == 0
+    nb, my, mz, n, n0, my0, mz0, myl, mzl = P.CONFIGS["C3"]
+    assert (nb, n + my + mz, n0 + my0 + myl + mzl) == (512, 110000, 2700)
+    nb, my, mz, n, n0, my0, mz0, myl, mzl = P.CONFIGS["C2"]
+    assert (nb, n + my + mz, n0 + my0 + myl + mzl) == (64, 44000, 800)
