@@ -182,6 +182,9 @@ pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* kkt);
 /* device time in ms of the stages of the last factorize: out[0]=H2D+assembly, [1]=leaf LDL^T + Schur terms,
  * [2]=allreduce, [3]=finalize, [4]=root LDL^T ; and of the last solve_compressed: [5]=Lsolve, [6]=Dsolve, [7]=Ltsolve */
 int pipsgpu_kkt_stage_times(pipsgpu_kkt* kkt, double out[8]);
+/* measured FP64 tensor-pipe (DMMA, mma.sync m8n8k4 f64) peak of this GPU in TFLOP/s: register-resident chains on all
+ * SMs, CUDA-event timed; the denominator of the "fraction of FP64 tensor peak" figures (no reference counterpart) */
+int pipsgpu_bench_dmma_peak(pipsgpu_ctx* ctx, double* tflops);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 int64_t pipsgpu_ctx_launch_count(pipsgpu_ctx* ctx);
 

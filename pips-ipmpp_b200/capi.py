@@ -143,6 +143,12 @@ class Context:
     def factorize_leaves(self, sc=None):
         _check(lib().pipsgpu_ctx_factorize_leaves(self.h, sc.h if sc is not None else None))
 
+    def dmma_peak_tflops(self):
+        """measured FP64 tensor-pipe peak of this GPU (register-resident DMMA chains)"""
+        v = C.c_double(0)
+        _check(lib().pipsgpu_bench_dmma_peak(self.h, C.byref(v)))
+        return v.value
+
     def launch_count(self):
         return int(lib().pipsgpu_ctx_launch_count(self.h))
 

@@ -1102,3 +1102,237 @@ void launch_vec_zero(double* dst, int64_t n, cudaStream_t s) {
 }
 
 }  // namespace pipsgpu
+
+// =====================================================================================================
+// FP64 tensor-pipe (DMMA) peak microbenchmark: register-resident mma.sync chains, 8 independent accumulator
+// tiles per warp. Gives the denominator for the "fraction of FP64 tensor peak" figures (SURVEY.md 8(d) asks for an
+// in-repo DGEMM-pipe peak next to the nominal one).
+// =====================================================================================================
+namespace pipsgpu {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+    if (s == 12345.678) out[0] = s;   // keep the chain alive
+}
+// returns the flops one launch performs
+double launch_dmma_peak(double* out, int iters, int ctas, cudaStream_t s) {
+    dmma_peak_kernel<<<ctas, 256, 0, s>>>(out, iters);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (double)ctas * 8.0 /*warps*/ * (double)iters * 8.0 /*tiles*/ * 512.0;
+}
+}  // namespace pipsgpu
+
+// =====================================================================================================
+// Persistent, dependency-driven supernodal solve: ONE launch applies K_i^-1 for every scenario block of the GPU.
+//
+// The level-scheduled kernels above pay one launch per (tree level, width class) and direction: ~120 dependent
+// launches of a few microseconds for a tree that is 19 levels deep. Here warps pull fronts from a global ticket
+// counter in level order (deepest level first for the forward sweep, the reverse for the backward sweep) and wait on
+// per-front completion flags instead of kernel boundaries. Because a front's prerequisites always hold EARLIER
+// tickets, every flag a warp spins on belongs to a warp that is already resident and running: no deadlock, no
+// cooperative launch needed.
+//   tickets [0, n)   forward : wait children (flag >= epoch+1) ; y = L11^-1 (b + child updates) ; upd = -L21 y ;
+//                              x = D^-1 y (block diagonal folded in) ; flag = epoch+1
+//   tickets [n, 2n)  backward: wait parent (flag >= epoch+2) ; x = L11^-T (x - L21^T x_anc) ; out ; flag = epoch+2
+// The permutation gather of the right-hand side and the scatter of the solution are fused in (in[gidx], out[gidx]).
+// Data written by other SMs (x, upd) is read with ld.global.cg; producers fence before publishing their flag.
+// =====================================================================================================
+namespace pipsgpu {
+
+__device__ __forceinline__ int ld_flag(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int WP>
+__device__ __forceinline__ void psolve_fwd(const PSolveArgs& a, const FrontDesc& fd, int lane, double* ybuf) {
+    const unsigned full = 0xffffffffu;
+    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    const double* __restrict__ F = a.L + fd.Loff;
+    double* us = a.upd + fd.upd_off;
+    // L11 row of this lane: issue the loads before waiting on anything
+    double lrow[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) lrow[k] = (k < w && lane > k && lane < w) ? F[(size_t)k * m + lane] : 0.0;
+    const int p = fd.col0 + lane;
+    double y = (lane < w) ? a.in[a.gidx[p]] : 0.0;
+    // ---- children: wait, then pull their update vectors ----
+    for (int c = fd.child_begin + lane; c < fd.child_end; c += 32) {
+        const int* fl = a.flags + a.child_list[c];
+        while (ld_flag(fl) < a.epoch + 1) __nanosleep(40);
+    }
+    __syncwarp();
+    ybuf[lane] = 0.0;                       // contributions to the pivot-block rows, indexed by local row
+    for (int i = lane; i < na; i += 32) us[i] = 0.0;
+    __syncwarp();
+    for (int c = fd.child_begin; c < fd.child_end; ++c) {
+        const FrontDesc& cd = a.fronts[a.child_list[c]];
+        const int cna = cd.na;
+        const int* rel = a.relidx + cd.rows_off;
+        const double* uc = a.upd + cd.upd_off;
+        for (int i = lane; i < cna; i += 32) {      // the rows of one child map to distinct parent rows
+            const int li = rel[i];
+            const double v = __ldcg(uc + i);
+            if (li < w) ybuf[li] += v;
+            else us[li - w] += v;
+        }
+        __syncwarp();
+    }
+    y += ybuf[lane];
+    // ---- y = L11^-1 y ----
+#pragma unroll
+    for (int k = 0; k < WP; ++k) {
+        const double yk = __shfl_sync(full, y, k);
+        y = fma(-lrow[k], yk, y);
+    }
+    // ---- upd = -(L21 y) (on top of the children's contributions) ----
+    for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        double v[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < WP; ++k) acc = fma(v[k], __shfl_sync(full, y, k), acc);
+        if (i < na) us[i] -= acc;
+    }
+    // ---- z = D^-1 y (1x1 and 2x2 pivots; pairs never straddle a front) ----
+    {
+        const int t = (lane < w) ? a.ptype[p] : 0;
+        const double dd = (lane < w) ? a.Did[p] : 0.0;
+        const double de = (lane < w) ? a.Die[p] : 0.0;
+        const double ynext = __shfl_down_sync(full, y, 1);
+        const double yprev = __shfl_up_sync(full, y, 1);
+        const double deprev = __shfl_up_sync(full, de, 1);
+        double z = dd * y;
+        if (t == 1) z += de * ynext;
+        else if (t == 2) z += deprev * yprev;
+        if (lane < w) a.x[p] = z;
+    }
+}
+
+template <int WP>
+__device__ __forceinline__ void psolve_bwd(const PSolveArgs& a, const FrontDesc& fd, int self, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
+    const double* __restrict__ F = a.L + fd.Loff;
+    const int* __restrict__ rowg = a.rowg + fd.rows_off;
+    double lcol[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) lcol[k] = (lane < k && k < w) ? F[(size_t)lane * m + k] : 0.0;
+    // a non-root front waits for its parent's backward step (which transitively implies that the forward sweep of the
+    // whole tree - this front included - is complete); a root waits for its own forward step
+    if (lane == 0) {
+        const int* fl = (fd.parent >= 0) ? a.flags + fd.parent : a.flags + self;
+        const int target = a.epoch + ((fd.parent >= 0) ? 2 : 1);
+        while (ld_flag(fl) < target) __nanosleep(40);
+    }
+    __syncwarp();
+    const int p = fd.col0 + lane;
+    double t = (lane < w) ? __ldcg(a.x + p) : 0.0;
+    double sacc[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) sacc[k] = 0.0;
+    for (int i0 = 0; i0 < na; i0 += 32) {
+        const int i = i0 + lane;
+        const double xi = (i < na) ? __ldcg(a.x + rowg[i]) : 0.0;
+        double v[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
+#pragma unroll
+        for (int k = 0; k < WP; ++k) sacc[k] = fma(v[k], xi, sacc[k]);
+    }
+#pragma unroll
+    for (int o = 16; o >= WP; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < WP; ++j) sacc[j] += __shfl_xor_sync(full, sacc[j], o);
+    }
+#pragma unroll
+    for (int o = (WP < 32 ? WP / 2 : 16); o > 0; o >>= 1) {
+        const bool hi = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+            const double send = hi ? sacc[j] : sacc[j + o];
+            const double keep = hi ? sacc[j + o] : sacc[j];
+            sacc[j] = keep + __shfl_xor_sync(full, send, o);
+        }
+    }
+    t -= sacc[0];
+#pragma unroll
+    for (int k = WP - 1; k >= 0; --k) {
+        const double xk = __shfl_sync(full, t, k);
+        t = fma(-lcol[k], xk, t);
+    }
+    if (lane < w) {
+        a.x[p] = t;
+        const int g = a.gidx[p];
+        a.out[g] = (a.out_mode == 0) ? t : a.out[g] - t;   // 0: out = K^-1 in ; 1: out -= K^-1 in
+    }
+}
+
+constexpr int PS_WARPS = 4;
+__global__ void __launch_bounds__(PS_WARPS * 32, 3) psolve_kernel(PSolveArgs a) {
+    __shared__ double s_ybuf[PS_WARPS][32];
+    double* ybuf = s_ybuf[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    const int n = a.nfronts;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.counters, 1);
+        t = __shfl_sync(full, t, 0);
+        if (t >= 2 * n) break;
+        const bool fwd = t < n;
+        const int f = a.order[fwd ? t : 2 * n - 1 - t];
+        const FrontDesc fd = a.fronts[f];
+        const int cls = width_class(fd.w);
+        if (fwd) {
+            if (cls == 0) psolve_fwd<8>(a, fd, lane, ybuf);
+            else if (cls == 1) psolve_fwd<16>(a, fd, lane, ybuf);
+            else psolve_fwd<32>(a, fd, lane, ybuf);
+        } else {
+            if (cls == 0) psolve_bwd<8>(a, fd, f, lane);
+            else if (cls == 1) psolve_bwd<16>(a, fd, f, lane);
+            else psolve_bwd<32>(a, fd, f, lane);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_flag(a.flags + f, a.epoch + (fwd ? 1 : 2));
+    }
+    // the last warp to leave re-arms the ticket counter for the next launch
+    if (lane == 0) {
+        const int total = gridDim.x * PS_WARPS;
+        const int done = atomicAdd(a.counters + 1, 1);
+        if (done == total - 1) {
+            a.counters[1] = 0;
+            __threadfence();
+            a.counters[0] = 0;
+        }
+    }
+}
+
+void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s) {
+    if (a.nfronts <= 0) return;
+    int ctas = sm_count * 3;
+    const int need = (2 * a.nfronts + PS_WARPS - 1) / PS_WARPS;
+    if (ctas > need) ctas = need;
+    psolve_kernel<<<ctas, PS_WARPS * 32, 0, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+}  // namespace pipsgpu

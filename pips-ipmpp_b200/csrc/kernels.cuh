@@ -71,6 +71,29 @@ struct SolveArgs {
     int64_t x_stride, upd_stride;
 };
 
+// persistent dependency-driven solve (one launch = K^-1 for every block): see psolve_kernel
+struct PSolveArgs {
+    const FrontDesc* fronts;
+    const int* order;            // all fronts, deepest level first (= level_fronts)
+    const int* child_list;
+    const int* rowg;
+    const int* relidx;
+    const int* gidx;             // per position: index of that row in the caller's (unpermuted, concatenated) vectors
+    const int8_t* ptype;
+    const double* L;
+    const double* Did; const double* Die;
+    const double* in;            // right-hand side, original order
+    double* out;                 // solution, original order
+    double* x;                   // work: permuted order
+    double* upd;                 // work: per-front update vectors
+    int* flags;                  // per front: epoch+1 after the forward step, epoch+2 after the backward step
+    int* counters;               // [0] ticket, [1] exit count (self re-arming)
+    int nfronts;
+    int epoch;
+    int out_mode;                // 0: out = K^-1 in, 1: out -= K^-1 in
+};
+void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s);
+
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
 void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
@@ -115,5 +138,7 @@ void launch_vec_copy(double* dst, const double* src, int n, cudaStream_t s);
 void launch_vec_zero(double* dst, int64_t n, cudaStream_t s);
 
 int64_t kernel_launch_count();
+// FP64 tensor-pipe peak microbenchmark (register-resident DMMA chains); returns the flops of the launch
+double launch_dmma_peak(double* out, int iters, int ctas, cudaStream_t s);
 
 }  // namespace pipsgpu

@@ -158,6 +158,9 @@ struct pipsgpu_ctx {
     DevBuf<FrontDesc> fronts;
     DevBuf<LeafDev> leafdev;
     DevBuf<int64_t> kmap, bmap, diagpos;
+    DevBuf<int> ps_flags, ps_counters;   // persistent solve: per-front completion flags, ticket / exit counters
+    int ps_epoch = 0;
+    int sm_count = 148;
     double* h_dvals = nullptr;      // pinned staging of all leaf diagonals (npos)
     bool own_stream = true;
 
@@ -168,6 +171,21 @@ struct pipsgpu_ctx {
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         return a;
+    }
+    // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
+    void psolve(const double* in, double* out, int out_mode) {
+        if (nfronts <= 0) return;
+        if (ps_epoch > (1 << 30)) {   // flags are monotone in the epoch: re-arm long before the counter wraps
+            cudaMemsetAsync(ps_flags.p, 0, sizeof(int) * (size_t)nfronts, stream);
+            ps_epoch = 0;
+        }
+        PSolveArgs a;
+        a.fronts = fronts.p; a.order = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p; a.relidx = relidx.p;
+        a.gidx = gidx.p; a.ptype = ptype.p; a.L = L.p; a.Did = Did.p; a.Die = Die.p; a.in = in; a.out = out; a.x = x.p;
+        a.upd = upd.p; a.flags = ps_flags.p; a.counters = ps_counters.p; a.nfronts = (int)nfronts; a.epoch = ps_epoch;
+        a.out_mode = out_mode;
+        launch_psolve(a, sm_count, stream);
+        ps_epoch += 2;
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
         SolveArgs a;
@@ -357,6 +375,7 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     CUDA_CHECK(cudaSetDevice(device));
     auto ctx = std::make_unique<pipsgpu_ctx>();
     ctx->device = device;
+    CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     *out = ctx.release();
     PIPSGPU_CATCH
@@ -393,6 +412,35 @@ int pipsgpu_ctx_synchronize(pipsgpu_ctx* ctx) {
 }
 
 int64_t pipsgpu_ctx_launch_count(pipsgpu_ctx*) { return kernel_launch_count(); }
+
+int pipsgpu_bench_dmma_peak(pipsgpu_ctx* ctx, double* tflops) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (!tflops) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_bench_dmma_peak: null output");
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+    DevBuf<double> out;
+    out.alloc(8);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    const int ctas = prop.multiProcessorCount * 4, iters = 20000;
+    launch_dmma_peak(out.p, 2000, ctas, ctx->stream);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+        const double fl = launch_dmma_peak(out.p, iters, ctas, ctx->stream);
+        CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    PIPSGPU_CATCH
+}
 
 int pipsgpu_nccl_unique_id(char id[128]) {
     PIPSGPU_TRY
@@ -679,6 +727,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->x.alloc((size_t)npos + 1); ctx->upd.alloc((size_t)updtot + 1); ctx->dvals.alloc((size_t)npos + 1);
     ctx->work.alloc((size_t)npos + 1);
     ctx->stats.alloc((size_t)4 * std::max(nl, 1));
+    ctx->ps_flags.alloc((size_t)nfr + 1); ctx->ps_counters.alloc(2);
+    CUDA_CHECK(cudaMemsetAsync(ctx->ps_flags.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
+    CUDA_CHECK(cudaMemsetAsync(ctx->ps_counters.p, 0, sizeof(int) * 2, s));
     CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMemsetAsync(ctx->De.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMallocHost(&ctx->h_dvals, sizeof(double) * ((size_t)npos + 1)));
@@ -1147,11 +1198,8 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
     const int64_t N = ctx->npos;
     if (ctx->rank > 0) launch_vec_zero(k->b0.p, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
     else launch_vec_copy(k->b0.p, k->b0_in.p, nb0, s);
-    SolveArgs sa = ctx->solve_args(ctx->x.p, N, ctx->upd.p, ctx->updtot);
     // ---- Lsolve: z_i = K_i^-1 b_i ; b0 -= Bord_i^T z_i ; allreduce ----
-    launch_gather_perm(ctx->gidx.p, k->bl_in.p, ctx->x.p, N, 1, N, s);
-    run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
-    launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->bl.p, N, 1, N, s);
+    ctx->psolve(k->bl_in.p, k->bl.p, 0);
     launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, k->bl.p, k->b0.p, s);
     if (ctx->comm && ctx->nranks > 1) {
         NcclApi& api = NcclApi::get();
@@ -1181,10 +1229,7 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
     if (N > 0) {
         launch_vec_zero(k->tl.p, N, s);
         launch_border_mult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, b, k->tl.p, s);
-        launch_gather_perm(ctx->gidx.p, k->tl.p, ctx->x.p, N, 1, N, s);
-        run_leaf_solve(ctx, sa, 1, nullptr, 0, N);
-        launch_scatter_perm(ctx->gidx.p, ctx->x.p, k->tl.p, N, 1, N, s);
-        launch_axpy(-1.0, k->tl.p, k->bl.p, N, s);
+        ctx->psolve(k->tl.p, k->bl.p, 1);
     }
 }
 
