@@ -47,66 +47,201 @@ void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, dou
 }
 
 // =====================================================================================================
-// multifrontal numeric factorisation: one CTA per front
+// multifrontal numeric factorisation (push formulation, no extend-add pass)
+//
+//  Every front's panel F (m x w, column-major) starts as zeros + its own K / border entries (scatter_values_kernel).
+//  A front's update  U = L21 * (L21 D)^T  is PUSHED, entry by entry, to where it is needed next:
+//     ancestor x ancestor / border x ancestor  ->  the parent front's panel (pivot columns) or the parent's pass-through
+//                                                  block C (remaining ancestor columns), red.global.add.f64;
+//     border x border                          ->  the dense Schur complement  (SC -= Bord^T K^-1 Bord).
+//  What the children pushed into this front's C is forwarded in the same pass (v = C - U), so a contribution entry is
+//  written once per tree level it travels and no separate extend-add kernel exists.
+//
+//  small fronts (fewer than BIG_U rows below the pivot block): ONE WARP per front, whole front in one pass;
+//  big fronts: pivot_panel_big_kernel (one CTA per front) + front_update_tiles_kernel (one CTA per 64x64 tile, DMMA).
 // =====================================================================================================
-constexpr int FT = 128;   // threads per front CTA
+struct PivotSmem {              // per front: unit-lower L11 and the block diagonal, read by the panel rows (broadcast)
+    double L[MAXW][MAXW + 1];
+    double did[MAXW], die[MAXW];
+    int8_t pt[MAXW];
+};
 
-// panel rows below the pivot block: W = A - L * Wp^T (left-looking by row, row kept in registers), L = W * D^-1
+// LDL^T of the w x w pivot block by one warp, right-looking, rows in registers (lane i holds row i: a[k] = A(i,k),
+// k <= i), static 1x1 / 2x2 pivots, tiny pivots replaced by +-eps and counted. Leaves L11 in ps->L (unit diagonal
+// implied, zeros above), D^-1 in ps->did/die, writes L11 / D / D^-1 to global memory and the inertia counts to stats.
 template <int WP>
-__device__ __forceinline__ void panel_rows(const FrontDesc& fd, double* __restrict__ F, double* __restrict__ Wscr,
-                                           const double (*Pw)[MAXW + 1], const int8_t* s_pt, const double* s_did,
-                                           const double* s_die) {
-    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
-    for (int r = threadIdx.x; r < u; r += FT) {
-        double l[WP], wv[WP];
+__device__ __forceinline__ void pivot_block_warp(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
+                                                 PivotSmem* ps, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int w = fd.w, m = w + fd.na + fd.nb;
+    double r[WP];
 #pragma unroll
-        for (int k = 0; k < WP; ++k) {
-            l[k] = (k < w) ? F[(size_t)k * m + w + r] : 0.0;
-            wv[k] = 0.0;
-        }
+    for (int k = 0; k < WP; ++k) r[k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
+    const int g0 = fd.col0;
+    const int myt = (lane < w) ? a.ptype[g0 + lane] : 0;
+    const double mysg = (lane < w) ? (double)a.sgn[g0 + lane] : 1.0;
+    const unsigned firstmask = __ballot_sync(full, myt == 1);
+    const unsigned secondmask = __ballot_sync(full, myt == 2);
+    const double eps = a.leaves[fd.leaf].eps;
+    int npos = 0, nneg = 0, nzero = 0, npert = 0;
+    double my_dd = 0.0, my_de = 0.0, my_did = 0.0, my_die = 0.0;   // lane k keeps the D entries of column k
 #pragma unroll
-        for (int k = 0; k < WP; ++k) {
-            if (k < w) {
-                double acc = l[k];
+    for (int k = 0; k < WP; ++k) {
+        if (k >= w) break;
+        if ((secondmask >> k) & 1u) continue;                      // handled together with column k-1
+        const bool pair = ((firstmask >> k) & 1u) && (k + 1 < WP);
+        if (!pair) {
+            double d = __shfl_sync(full, r[k], k);
+            const double sg = __shfl_sync(full, mysg, k);
+            if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
+            if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
+            const double inv = 1.0 / d;
+            const double wk = (lane > k) ? r[k] : 0.0;             // unscaled W(i,k)
+            const double lk = wk * inv;
 #pragma unroll
-                for (int j = 0; j < k; ++j) acc -= l[j] * Pw[k][j];
-                const int t = s_pt[k];
-                if (t == 0) {
-                    wv[k] = acc;
-                    l[k] = acc * s_did[k];
-                } else if (t == 1) {
-                    l[k] = acc;   // r1, finalised together with the second column (Pw[k+1][k] == 0)
-                } else if (k > 0) {
-                    const double r1 = l[k - 1], r2 = acc;
-                    wv[k - 1] = r1;
-                    wv[k] = r2;
-                    l[k - 1] = r1 * s_did[k - 1] + r2 * s_die[k - 1];
-                    l[k] = r1 * s_die[k - 1] + r2 * s_did[k];
-                }
+            for (int j = k + 1; j < WP; ++j) r[j] = fma(-lk, __shfl_sync(full, wk, j), r[j]);
+            if (lane > k) r[k] = lk;
+            if (lane == k) { my_dd = d; my_de = 0.0; my_did = inv; my_die = 0.0; }
+        } else if (k + 1 < WP) {
+            double da = __shfl_sync(full, r[k], k);
+            const double db = __shfl_sync(full, r[k], k + 1);
+            double dc = __shfl_sync(full, r[k + 1], k + 1);
+            double det = da * dc - db * db;
+            if (!(det <= -eps * eps)) {
+                if (da < eps) da = eps;
+                if (dc > -eps) dc = -eps;
+                det = da * dc - db * db;
+                ++npert;
             }
+            if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
+            const double ia = dc / det, ib = -db / det, ic = da / det;
+            const double w1 = (lane > k + 1) ? r[k] : 0.0;
+            const double w2 = (lane > k + 1) ? r[k + 1] : 0.0;
+            const double l1 = w1 * ia + w2 * ib, l2 = w1 * ib + w2 * ic;
+#pragma unroll
+            for (int j = k + 2; j < WP; ++j) {
+                r[j] = fma(-l1, __shfl_sync(full, w1, j), r[j]);
+                r[j] = fma(-l2, __shfl_sync(full, w2, j), r[j]);
+            }
+            if (lane > k + 1) { r[k] = l1; r[k + 1] = l2; }
+            if (lane == k + 1) r[k] = 0.0;                          // L(k+1,k) = 0 by convention (block pivot)
+            if (lane == k) { my_dd = da; my_de = db; my_did = ia; my_die = ib; }
+            if (lane == k + 1) { my_dd = dc; my_de = 0.0; my_did = ic; my_die = 0.0; }
         }
+    }
+    // publish: L11 (smem for the panel rows, global for the solves), D, D^-1
 #pragma unroll
-        for (int k = 0; k < WP; ++k)
-            if (k < w) F[(size_t)k * m + w + r] = l[k];
-        double* wr = Wscr + (size_t)r * WP;
-#pragma unroll
-        for (int k = 0; k < WP; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(wv[k], wv[k + 1]);
+    for (int k = 0; k < WP; ++k) {
+        if (lane < WP) ps->L[lane][k] = (k < lane && lane < w) ? r[k] : 0.0;
+        if (lane < w && k < w) {
+            if (k < lane) F[(size_t)k * m + lane] = r[k];
+            else if (k == lane) F[(size_t)k * m + lane] = 1.0;
+        }
+    }
+    if (lane < WP) {
+        ps->did[lane] = (lane < w) ? my_did : 0.0;
+        ps->die[lane] = (lane < w) ? my_die : 0.0;
+        ps->pt[lane] = (int8_t)((lane < w) ? myt : 0);
+    }
+    if (lane < w) {
+        a.Dd[g0 + lane] = my_dd; a.De[g0 + lane] = my_de; a.Did[g0 + lane] = my_did; a.Die[g0 + lane] = my_die;
+    }
+    if (lane == 0 && a.stats) {
+        int* st = a.stats + 4 * fd.leaf;
+        if (npos) atomicAdd(st + 0, npos);
+        if (nneg) atomicAdd(st + 1, nneg);
+        if (nzero) atomicAdd(st + 2, nzero);
+        if (npert) atomicAdd(st + 3, npert);
     }
 }
 
-// contribution block C(i,j) -= L_i . W_j  (j < na) and the border x border part straight into the Schur complement
+// one row below the pivot block, right-looking: w_k = a_k - sum_{j<k} w_j L(k,j) ;  L21 row = w * D^-1.
+// On exit l[] holds the L21 row (written back to the panel) and the unscaled row w went to the scratch row wr.
 template <int WP>
-__device__ __forceinline__ void update_rows(const FrontDesc& fd, const double* __restrict__ F,
-                                            const double* __restrict__ Wscr, double* __restrict__ Cs,
-                                            const int* __restrict__ rowg, double* __restrict__ SC, int ldsc) {
+__device__ __forceinline__ void panel_row(const PivotSmem* ps, int w, double (&l)[WP], double* __restrict__ wr) {
+#pragma unroll
+    for (int k = 0; k < WP; ++k) {
+        if (k >= w) { l[k] = 0.0; continue; }
+        const double wk = l[k];
+#pragma unroll
+        for (int j = k + 1; j < WP; ++j) l[j] = fma(-wk, ps->L[j][k], l[j]);
+    }
+    // l[] now holds the unscaled row w = L21 D: it goes to the scratch, then l is scaled by the block diagonal
+#pragma unroll
+    for (int k = 0; k < WP; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(l[k], l[k + 1]);
+#pragma unroll
+    for (int k = 0; k < WP; ++k) {
+        if (k >= w) break;
+        const int t = ps->pt[k];
+        if (t == 0) l[k] *= ps->did[k];
+        else if (t == 1 && k + 1 < WP) {
+            const double x = l[k], y = l[k + 1];
+            l[k] = x * ps->did[k] + y * ps->die[k];
+            l[k + 1] = x * ps->die[k] + y * ps->did[k + 1];
+        }
+    }
+}
+
+// destination of the update entry (front row i, front column j < na) in the parent front
+struct PushTarget {
+    double* Fp;      // parent panel
+    double* Cp;      // parent pass-through block
+    int wp, mp, up;
+};
+__device__ __forceinline__ PushTarget push_target(const FactorArgs& a, const FrontDesc& fd) {
+    PushTarget t;
+    t.Fp = nullptr; t.Cp = nullptr; t.wp = 0; t.mp = 0; t.up = 0;
+    if (fd.parent >= 0) {
+        const FrontDesc& pd = a.fronts[fd.parent];
+        t.wp = pd.w; t.up = pd.na + pd.nb; t.mp = t.wp + t.up;
+        t.Fp = a.L + pd.Loff; t.Cp = a.C + pd.Coff;
+    }
+    return t;
+}
+__device__ __forceinline__ void push_entry(const PushTarget& t, int ri, int rj, double v) {
+    double* dst = (rj < t.wp) ? t.Fp + (size_t)rj * t.mp + ri : t.Cp + (size_t)(rj - t.wp) * t.up + (ri - t.wp);
+    atomicAdd(dst, v);
+}
+
+constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
+
+template <int WP>
+__device__ __forceinline__ void small_front(const FactorArgs& a, const FrontDesc& fd, PivotSmem* ps, int lane) {
     const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
-    for (int r = threadIdx.x; r < u; r += FT) {
+    double* F = a.L + fd.Loff;
+    pivot_block_warp<WP>(a, fd, F, ps, lane);
+    if (u == 0) return;
+    __syncwarp();
+    double* Wscr = a.W + fd.Woff;
+    const double* Cs = a.C + fd.Coff;
+    const int* rowg = a.rowg + fd.rows_off;
+    const int* rel = a.relidx + fd.rows_off;
+    const PushTarget pt = push_target(a, fd);
+    // ---- panel rows (all chunks first: the update needs the W rows of every earlier row) ----
+    for (int i0 = 0; i0 < u; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < u) {
+            double l[WP];
+#pragma unroll
+            for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + i] : 0.0;
+            panel_row<WP>(ps, w, l, Wscr + (size_t)i * WP);
+#pragma unroll
+            for (int k = 0; k < WP; ++k)
+                if (k < w) F[(size_t)k * m + w + i] = l[k];
+        }
+    }
+    __syncwarp();
+    // ---- update + push ----
+    for (int i0 = 0; i0 < u; i0 += 32) {
+        const int i = i0 + lane;
+        const bool act = i < u;
         double l[WP];
 #pragma unroll
-        for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + r] : 0.0;
-        const int jend = (SC != nullptr) ? r : min(r, na - 1);
-        const int64_t scrow = (r >= na) ? (int64_t)rowg[r] * ldsc : 0;
-        for (int j = 0; j <= jend; ++j) {
+        for (int k = 0; k < WP; ++k) l[k] = (act && k < w) ? F[(size_t)k * m + w + i] : 0.0;
+        const int ri = act ? rel[i] : 0;
+        const int64_t scrow = (act && i >= na && a.SC) ? (int64_t)rowg[i] * a.ldsc : 0;
+        const int jmax = min(i0 + 31, u - 1);
+        for (int j = 0; j <= jmax; ++j) {
             const double* wj = Wscr + (size_t)j * WP;
             double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
@@ -115,154 +250,61 @@ __device__ __forceinline__ void update_rows(const FrontDesc& fd, const double* _
                 acc0 = fma(l[k], wk.x, acc0);
                 acc1 = fma(l[k + 1], wk.y, acc1);
             }
+            if (!act || j > i) continue;
             const double acc = acc0 + acc1;
-            if (j < na) Cs[(size_t)j * u + r] -= acc;
-            else atomicAdd(&SC[scrow + rowg[j]], -acc);
+            if (j < na) push_entry(pt, ri, rel[j], Cs[(size_t)j * u + i] - acc);
+            else if (a.SC) atomicAdd(&a.SC[scrow + rowg[j]], -acc);
         }
     }
 }
 
-template <int WP>
-__global__ void __launch_bounds__(FT, (WP == 8 ? 5 : (WP == 16 ? 3 : 2))) front_factor_kernel(FactorArgs a, int level_begin) {
-    __shared__ double Pl[WP][MAXW + 1];   // pivot block: A on entry, strict lower L on exit
-    __shared__ double Pw[WP][MAXW + 1];   // pivot block: W = L*D (strictly below the pivot blocks)
-    __shared__ double s_did[MAXW], s_die[MAXW];
-    __shared__ int8_t s_pt[MAXW];
-
-    const int tid = threadIdx.x;
-    const int f = a.level_fronts[level_begin + blockIdx.x];
-    const FrontDesc fd = a.fronts[f];
-    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
-    double* F = a.L + fd.Loff;
-    double* Cs = a.C + fd.Coff;
-
-    // ---- 1. extend-add of the children's contribution blocks (children sequential, entries parallel) ----
-    for (int c = fd.child_begin; c < fd.child_end; ++c) {
-        const FrontDesc cd = a.fronts[a.child_list[c]];
-        const int uc = cd.na + cd.nb, nac = cd.na;
-        const double* Cc = a.C + cd.Coff;
-        const int* rel = a.relidx + cd.rows_off;
-        const int total = uc * nac;
-        for (int idx = tid; idx < total; idx += FT) {
-            const int j = idx / uc, i = idx - j * uc;
-            if (i < j) continue;
-            const double v = Cc[idx];
-            const int li = rel[i], lj = rel[j];
-            if (lj < w) F[(size_t)lj * m + li] += v;
-            else Cs[(size_t)(lj - w) * u + (li - w)] += v;
-        }
-        __syncthreads();
-    }
-
-    // ---- 2. pivot block into shared memory ----
-    for (int idx = tid; idx < WP * (MAXW + 1); idx += FT) {
-        (&Pl[0][0])[idx] = 0.0;
-        (&Pw[0][0])[idx] = 0.0;
-    }
-    if (tid < MAXW) {
-        s_pt[tid] = (tid < w) ? a.ptype[fd.col0 + tid] : (int8_t)0;
-        s_did[tid] = 0.0;
-        s_die[tid] = 0.0;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < w * w; idx += FT) {
-        const int j = idx / w, i = idx - j * w;
-        if (i >= j) Pl[i][j] = F[(size_t)j * m + i];
-    }
-    __syncthreads();
-
-    // ---- 3. LDL^T of the pivot block by warp 0: lane i owns row i, lock-step over pivots ----
-    if (tid < 32) {
-        const int lane = tid;
-        const unsigned full = 0xffffffffu;
-        const double eps = a.leaves[fd.leaf].eps;
-        int npos = 0, nneg = 0, nzero = 0, npert = 0;
-        int k = 0;
-        while (k < w) {
-            const bool pair = (s_pt[k] == 1) && (k + 1 < w);
-            double r1 = 0.0, r2 = 0.0;
-            if (lane >= k && lane < w) {
-                r1 = Pl[lane][k];
-                for (int j = 0; j < k; ++j) r1 -= Pl[lane][j] * Pw[k][j];
-                if (pair && lane >= k + 1) {
-                    r2 = Pl[lane][k + 1];
-                    for (int j = 0; j < k; ++j) r2 -= Pl[lane][j] * Pw[k + 1][j];
-                }
-            }
-            const int g = fd.col0 + k;
-            if (!pair) {
-                double d = __shfl_sync(full, r1, k);
-                const double sg = (double)a.sgn[g];
-                if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-                if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
-                const double inv = 1.0 / d;
-                if (lane > k && lane < w) { Pw[lane][k] = r1; Pl[lane][k] = r1 * inv; }
-                if (lane == k) {
-                    a.Dd[g] = d; a.De[g] = 0.0; a.Did[g] = inv; a.Die[g] = 0.0;
-                    s_did[k] = inv; s_die[k] = 0.0;
-                }
-                k += 1;
-            } else {
-                double da = __shfl_sync(full, r1, k);
-                const double db = __shfl_sync(full, r1, k + 1);
-                double dc = __shfl_sync(full, r2, k + 1);
-                double det = da * dc - db * db;
-                if (!(det <= -eps * eps)) {
-                    if (da < eps) da = eps;
-                    if (dc > -eps) dc = -eps;
-                    det = da * dc - db * db;
-                    ++npert;
-                }
-                if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
-                const double ia = dc / det, ib = -db / det, ic = da / det;
-                if (lane > k + 1 && lane < w) {
-                    Pw[lane][k] = r1; Pw[lane][k + 1] = r2;
-                    Pl[lane][k] = r1 * ia + r2 * ib;
-                    Pl[lane][k + 1] = r1 * ib + r2 * ic;
-                }
-                if (lane == k + 1) { Pl[k + 1][k] = 0.0; Pw[k + 1][k] = 0.0; }
-                if (lane == k) {
-                    a.Dd[g] = da; a.De[g] = db; a.Dd[g + 1] = dc; a.De[g + 1] = 0.0;
-                    a.Did[g] = ia; a.Die[g] = ib; a.Did[g + 1] = ic; a.Die[g + 1] = 0.0;
-                    s_did[k] = ia; s_die[k] = ib; s_did[k + 1] = ic; s_die[k + 1] = 0.0;
-                }
-                k += 2;
-            }
-            __syncwarp();
-        }
-        if (lane == 0 && a.stats) {
-            int* st = a.stats + 4 * fd.leaf;
-            if (npos) atomicAdd(st + 0, npos);
-            if (nneg) atomicAdd(st + 1, nneg);
-            if (nzero) atomicAdd(st + 2, nzero);
-            if (npert) atomicAdd(st + 3, npert);
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < w * w; idx += FT) {
-        const int j = idx / w, i = idx - j * w;
-        if (i > j) F[(size_t)j * m + i] = Pl[i][j];
-        else if (i == j) F[(size_t)j * m + i] = 1.0;
-    }
-    if (u == 0) return;
-
-    // ---- 4. panel rows, 5. contribution block + Schur complement share ----
-    double* Wscr = a.W + fd.Woff;
-    const int* rowg = a.rowg + fd.rows_off;
-    const bool big = (u >= BIG_U);   // big fronts: the O(u^2 w) update runs in front_update_tiles_kernel
-    panel_rows<WP>(fd, F, Wscr, Pw, s_pt, s_did, s_die);
-    if (big) return;
-    __syncthreads();
-    update_rows<WP>(fd, F, Wscr, Cs, rowg, a.SC, a.ldsc);
-    (void)na;
+__global__ void __launch_bounds__(SF_WARPS * 32) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
+    __shared__ PivotSmem s_ps[SF_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SF_WARPS + warp;
+    if (fi >= nfronts) return;
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
+    const int cls = width_class(fd.w);
+    if (cls == 0) small_front<8>(a, fd, &s_ps[warp], lane);
+    else if (cls == 1) small_front<16>(a, fd, &s_ps[warp], lane);
+    else small_front<32>(a, fd, &s_ps[warp], lane);
 }
-
-// cls = width class of every front in [level_begin, level_begin + nfronts): 0: w<=8, 1: w<=16, 2: w<=32
-void launch_front_factor(const FactorArgs& a, int cls, int level_begin, int nfronts, cudaStream_t s) {
+void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    if (cls == 0) front_factor_kernel<8><<<nfronts, FT, 0, s>>>(a, level_begin);
-    else if (cls == 1) front_factor_kernel<16><<<nfronts, FT, 0, s>>>(a, level_begin);
-    else front_factor_kernel<32><<<nfronts, FT, 0, s>>>(a, level_begin);
+    small_fronts_kernel<<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, 0, s>>>(a, begin, nfronts);
+    COUNT_LAUNCH();
+}
+
+// big fronts: pivot block by warp 0, then one thread per row for the panel (L21 in place, W21 = L21 D to the scratch)
+constexpr int BF_T = 256;
+template <int WP>
+__device__ __forceinline__ void big_front_panel(const FactorArgs& a, const FrontDesc& fd, PivotSmem* ps) {
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
+    double* F = a.L + fd.Loff;
+    if (threadIdx.x < 32) pivot_block_warp<WP>(a, fd, F, ps, threadIdx.x);
+    __syncthreads();
+    double* Wscr = a.W + fd.Woff;
+    for (int i = threadIdx.x; i < u; i += BF_T) {
+        double l[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + i] : 0.0;
+        panel_row<WP>(ps, w, l, Wscr + (size_t)i * WP);
+#pragma unroll
+        for (int k = 0; k < WP; ++k)
+            if (k < w) F[(size_t)k * m + w + i] = l[k];
+    }
+}
+__global__ void __launch_bounds__(BF_T) pivot_panel_big_kernel(FactorArgs a, int begin) {
+    __shared__ PivotSmem s_ps;
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
+    const int cls = width_class(fd.w);
+    if (cls == 0) big_front_panel<8>(a, fd, &s_ps);
+    else if (cls == 1) big_front_panel<16>(a, fd, &s_ps);
+    else big_front_panel<32>(a, fd, &s_ps);
+}
+void launch_pivot_panel_big(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
+    if (nfronts <= 0) return;
+    pivot_panel_big_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
     COUNT_LAUNCH();
 }
 
@@ -318,13 +360,16 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
 #pragma unroll
             for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
     }
-    double* Cs = a.C + fd.Coff;
+    const double* Cs = a.C + fd.Coff;
     const int* rowg = a.rowg + fd.rows_off;
+    const int* rel = a.relidx + fd.rows_off;
+    const PushTarget pt = push_target(a, fd);
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
         const int gi = i0 + wr + x * 8 + lr;
         if (gi >= u) continue;
         const int64_t scrow = (gi >= na && a.SC) ? (int64_t)rowg[gi] * a.ldsc : 0;
+        const int ri = rel[gi];
 #pragma unroll
         for (int y = 0; y < 4; ++y)
 #pragma unroll
@@ -332,7 +377,7 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
                 const int gj = j0 + wc + y * 8 + lk * 2 + e;
                 if (gj > gi) continue;
                 const double v = acc[x][y][e];
-                if (gj < na) Cs[(size_t)gj * u + gi] -= v;
+                if (gj < na) push_entry(pt, ri, rel[gj], Cs[(size_t)gj * u + gi] - v);
                 else if (a.SC) atomicAdd(&a.SC[scrow + rowg[gj]], -v);
             }
     }
@@ -1291,28 +1336,34 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 3) psolve_kernel(PSolveArgs a) 
     double* ybuf = s_ybuf[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned full = 0xffffffffu;
-    const int n = a.nfronts;
+    const int nb = a.nbatches;
     for (;;) {
+        // one ticket = one batch of consecutive fronts of the level order (a single hot counter would otherwise
+        // serialise ~2 x nfronts atomics in L2)
         int t = 0;
         if (lane == 0) t = atomicAdd(a.counters, 1);
         t = __shfl_sync(full, t, 0);
-        if (t >= 2 * n) break;
-        const bool fwd = t < n;
-        const int f = a.order[fwd ? t : 2 * n - 1 - t];
-        const FrontDesc fd = a.fronts[f];
-        const int cls = width_class(fd.w);
-        if (fwd) {
-            if (cls == 0) psolve_fwd<8>(a, fd, lane, ybuf);
-            else if (cls == 1) psolve_fwd<16>(a, fd, lane, ybuf);
-            else psolve_fwd<32>(a, fd, lane, ybuf);
-        } else {
-            if (cls == 0) psolve_bwd<8>(a, fd, f, lane);
-            else if (cls == 1) psolve_bwd<16>(a, fd, f, lane);
-            else psolve_bwd<32>(a, fd, f, lane);
+        if (t >= 2 * nb) break;
+        const bool fwd = t < nb;
+        const int b = fwd ? t : 2 * nb - 1 - t;
+        const int lo = a.batch_ptr[b], hi = a.batch_ptr[b + 1];
+        for (int q = 0; q < hi - lo; ++q) {
+            const int f = a.order[fwd ? lo + q : hi - 1 - q];
+            const FrontDesc fd = a.fronts[f];
+            const int cls = width_class(fd.w);
+            if (fwd) {
+                if (cls == 0) psolve_fwd<8>(a, fd, lane, ybuf);
+                else if (cls == 1) psolve_fwd<16>(a, fd, lane, ybuf);
+                else psolve_fwd<32>(a, fd, lane, ybuf);
+            } else {
+                if (cls == 0) psolve_bwd<8>(a, fd, f, lane);
+                else if (cls == 1) psolve_bwd<16>(a, fd, f, lane);
+                else psolve_bwd<32>(a, fd, f, lane);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_flag(a.flags + f, a.epoch + (fwd ? 1 : 2));
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_flag(a.flags + f, a.epoch + (fwd ? 1 : 2));
     }
     // the last warp to leave re-arms the ticket counter for the next launch
     if (lane == 0) {
@@ -1329,7 +1380,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 3) psolve_kernel(PSolveArgs a) 
 void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s) {
     if (a.nfronts <= 0) return;
     int ctas = sm_count * 3;
-    const int need = (2 * a.nfronts + PS_WARPS - 1) / PS_WARPS;
+    const int need = (2 * a.nbatches + PS_WARPS - 1) / PS_WARPS;
     if (ctas > need) ctas = need;
     psolve_kernel<<<ctas, PS_WARPS * 32, 0, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -40,6 +40,7 @@ constexpr int NCLS = 3;          // launches are grouped by (tree level, width c
 struct FactorArgs {
     const FrontDesc* fronts;
     const int* level_fronts;     // front ids grouped by level, deepest level first
+    const int* fl_fronts;        // front ids grouped by (level, small|big) for the factorisation launches
     const int* child_list;
     const int* rowg;             // per front row: global position (non-border) or Schur-complement index (border)
     const int* relidx;           // per front row: local row index in the parent front
@@ -75,6 +76,8 @@ struct SolveArgs {
 struct PSolveArgs {
     const FrontDesc* fronts;
     const int* order;            // all fronts, deepest level first (= level_fronts)
+    const int* batch_ptr;        // nbatches+1 offsets into order: one ticket = one batch of consecutive fronts
+    int nbatches;
     const int* child_list;
     const int* rowg;
     const int* relidx;
@@ -97,7 +100,8 @@ void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s);
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
 void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
-void launch_front_factor(const FactorArgs& a, int cls, int level_begin, int nfronts, cudaStream_t s);
+void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);      // fronts fl_fronts[begin..)
+void launch_pivot_panel_big(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
 void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);

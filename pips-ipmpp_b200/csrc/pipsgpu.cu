@@ -115,6 +115,7 @@ struct pipsgpu_leaf {
     int64_t Lbase = 0, Lsize = 0, Cbase = 0, Csize = 0, kval_off = 0, bval_off = 0, upd_base = 0, upd_size = 0;
     int front_base = 0;
     std::vector<int> level_begin, level_count;   // per global level: sub-range of level_fronts owned by this leaf
+    std::vector<int> fl_begin, fl_count;         // per (global level, small|big): sub-range of fl_fronts owned by this leaf
     std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double flops = 0;
@@ -153,12 +154,15 @@ struct pipsgpu_ctx {
     std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
     DevBuf<TileDesc> tiles;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
+    std::vector<int> fl_ptr;        // nlevels*2+1 into fl_fronts; group = level_order*2 + (0 small | 1 big)
+    DevBuf<int> fl_fronts;
     DevBuf<int> rowg, relidx, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
     DevBuf<int8_t> ptype, sgn;
     DevBuf<FrontDesc> fronts;
     DevBuf<LeafDev> leafdev;
     DevBuf<int64_t> kmap, bmap, diagpos;
-    DevBuf<int> ps_flags, ps_counters;   // persistent solve: per-front completion flags, ticket / exit counters
+    DevBuf<int> ps_flags, ps_counters, ps_batch_ptr;   // persistent solve: completion flags, ticket / exit counters, ticket batches
+    int ps_nbatches = 0;
     int ps_epoch = 0;
     int sm_count = 148;
     double* h_dvals = nullptr;      // pinned staging of all leaf diagonals (npos)
@@ -166,8 +170,9 @@ struct pipsgpu_ctx {
 
     FactorArgs factor_args(pipsgpu_sc* sc) {
         FactorArgs a;
-        a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p;
-        a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p; a.W = W.p;
+        a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.fl_fronts = fl_fronts.p; a.child_list = child_list.p;
+        a.rowg = rowg.p; a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p;
+        a.W = W.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         return a;
@@ -183,6 +188,7 @@ struct pipsgpu_ctx {
         a.fronts = fronts.p; a.order = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p; a.relidx = relidx.p;
         a.gidx = gidx.p; a.ptype = ptype.p; a.L = L.p; a.Did = Did.p; a.Die = Die.p; a.in = in; a.out = out; a.x = x.p;
         a.upd = upd.p; a.flags = ps_flags.p; a.counters = ps_counters.p; a.nfronts = (int)nfronts; a.epoch = ps_epoch;
+        a.batch_ptr = ps_batch_ptr.p; a.nbatches = ps_nbatches;
         a.out_mode = out_mode;
         launch_psolve(a, sm_count, stream);
         ps_epoch += 2;
@@ -262,12 +268,13 @@ void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_lea
 void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
     cudaStream_t s = ctx->stream;
     FactorArgs fa = ctx->factor_args(sc);
-    for (int lv = 0; lv < ctx->nlevels; ++lv) {
-        for (int c = 0; c < NCLS; ++c) {
-            const int g = lv * NCLS + c;
-            int begin = ctx->level_ptr[g], count = ctx->level_ptr[g + 1] - ctx->level_ptr[g];
-            if (only) { begin = only->level_begin[g]; count = only->level_count[g]; }
-            launch_front_factor(fa, c, begin, count, s);
+    for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
+        for (int kind = 0; kind < 2; ++kind) {
+            const int g = lv * 2 + kind;
+            int begin = ctx->fl_ptr[g], count = ctx->fl_ptr[g + 1] - ctx->fl_ptr[g];
+            if (only) { begin = only->fl_begin[g]; count = only->fl_count[g]; }
+            if (kind == 0) launch_small_fronts(fa, begin, count, s);
+            else launch_pivot_panel_big(fa, begin, count, s);
         }
         int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
         if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
@@ -679,6 +686,27 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
+    // ---- factorisation launch lists: fronts grouped by (level, small|big), by leaf inside a group ----
+    std::vector<int> fl_fronts((size_t)nfr);
+    {
+        auto kind_of = [&](const FrontDesc& fd) { return (fd.na + fd.nb >= BIG_U) ? 1 : 0; };
+        std::vector<int> cnt2(nlev * 2 + 1, 0);
+        for (auto* lf : ctx->leaves)
+            for (int s2 = 0; s2 < lf->S.ns; ++s2)
+                ++cnt2[(nlev - 1 - lf->S.sn_level[s2]) * 2 + kind_of(fronts[(size_t)lf->front_base + s2]) + 1];
+        ctx->fl_ptr.assign(nlev * 2 + 1, 0);
+        for (int g = 0; g < nlev * 2; ++g) ctx->fl_ptr[g + 1] = ctx->fl_ptr[g] + cnt2[g + 1];
+        std::vector<int> fill(ctx->fl_ptr.begin(), ctx->fl_ptr.end() - 1);
+        for (auto* lf : ctx->leaves) {
+            lf->fl_begin.assign(nlev * 2, 0); lf->fl_count.assign(nlev * 2, 0);
+            for (int g = 0; g < nlev * 2; ++g) lf->fl_begin[g] = fill[g];
+            for (int s2 = 0; s2 < lf->S.ns; ++s2) {
+                const int g = (nlev - 1 - lf->S.sn_level[s2]) * 2 + kind_of(fronts[(size_t)lf->front_base + s2]);
+                fl_fronts[(size_t)fill[g]++] = lf->front_base + s2;
+                ++lf->fl_count[g];
+            }
+        }
+    }
     // ---- update tiles of the big fronts, grouped by (level, leaf) ----
     std::vector<TileDesc> tiles;
     {
@@ -721,6 +749,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
+    ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
     ctx->Die.alloc((size_t)npos + 1);
@@ -728,6 +757,19 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->work.alloc((size_t)npos + 1);
     ctx->stats.alloc((size_t)4 * std::max(nl, 1));
     ctx->ps_flags.alloc((size_t)nfr + 1); ctx->ps_counters.alloc(2);
+    {
+        // ticket batches of the persistent solve: up to 8 consecutive fronts of one level per ticket, fewer where a
+        // level is too small to keep ~4000 warps busy
+        std::vector<int> bp;
+        for (int lv = 0; lv < nlev; ++lv) {
+            const int b = ctx->level_ptr[lv * NCLS], e = ctx->level_ptr[(lv + 1) * NCLS];
+            const int bs = std::max(1, std::min(8, (e - b + 4095) / 4096));
+            for (int i = b; i < e; i += bs) bp.push_back(i);
+        }
+        bp.push_back((int)nfr);
+        ctx->ps_nbatches = (int)bp.size() - 1;
+        ctx->ps_batch_ptr.upload(bp, s);
+    }
     CUDA_CHECK(cudaMemsetAsync(ctx->ps_flags.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
     CUDA_CHECK(cudaMemsetAsync(ctx->ps_counters.p, 0, sizeof(int) * 2, s));
     CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));

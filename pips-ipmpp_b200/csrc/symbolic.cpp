@@ -7,6 +7,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <stdexcept>
 
@@ -82,7 +83,9 @@ void match_rows(int n, int nx, int ny, const std::vector<int>& xadj, const std::
 }  // namespace
 
 void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jcol, const double* val, int nB,
-                  int64_t nnzB, const int* brow, const int* bcol, const SymbolicOptions& opt, LeafSymbolic& S) {
+                  int64_t nnzB, const int* brow, const int* bcol, const SymbolicOptions& opt_in, LeafSymbolic& S) {
+    SymbolicOptions opt = opt_in;
+    if (const char* e = std::getenv("PIPSGPU_SUBTREE_WIDTH")) opt.subtree_width = std::atoi(e);   // tuning knob
     if (nx + ny + nz != n) throw std::runtime_error("analyze_leaf: nx+ny+nz != n");
     S = LeafSymbolic();
     S.n = n; S.nx = nx; S.ny = ny; S.nz = nz; S.nB = nB;
@@ -196,7 +199,7 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
     {
         std::vector<int> sz(n, 1);
         for (int j = 0; j < n; ++j) if (parent0[j] >= 0) sz[parent0[j]] += sz[j];
-        // children lists; ordering: pair partner (j-1 matched with j) last, otherwise larger subtree later
+        // children lists; ordering: pair partner (j-1 matched with j) last, otherwise larger subtrees first
         std::vector<int> cptr(n + 2, 0);
         for (int j = 0; j < n; ++j) ++cptr[(parent0[j] < 0 ? n : parent0[j]) + 1];
         for (int j = 0; j <= n; ++j) cptr[j + 1] += cptr[j];
@@ -209,7 +212,7 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
             std::stable_sort(clist.begin() + cptr[v], clist.begin() + cptr[v + 1], [&](int a, int b) {
                 const bool pa = is_partner(a, v), pb = is_partner(b, v);
                 if (pa != pb) return pb;          // partner goes last
-                return sz[a] < sz[b];
+                return sz[a] > sz[b];             // small subtrees next to the parent: they are the ones that merge
             });
         }
         // iterative DFS from the virtual root n
@@ -297,6 +300,8 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
     }
 
     // ---- 7. supernodes: fundamental + forced pairs, relaxed amalgamation, width-bounded splitting -------
+    std::vector<int> desc(n, 1);   // subtree sizes in the elimination tree of the final order
+    for (int j = 0; j < n; ++j) if (parent[j] >= 0) desc[parent[j]] += desc[j];
     struct SN { int a, b; double zeros; };
     std::vector<SN> sn;
     auto merge_ok = [&](const SN& c, const SN& p) {
@@ -334,7 +339,19 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
             while (sn.size() >= 2) {
                 const SN& p = sn.back();
                 const SN& c = sn[sn.size() - 2];
-                if (c.b != p.a || !merge_ok(c, p)) break;
+                if (c.b != p.a) break;
+                bool ok = merge_ok(c, p);
+                if (!ok && opt.subtree_width > 0) {
+                    // subtree amalgamation: a child whose WHOLE subtree already sits in one supernode is absorbed as
+                    // long as the merged front stays narrow. Thousands of 4-8 column fronts at the bottom of the
+                    // nested-dissection tree become a few hundred 16-32 column fronts: the device pays per front
+                    // (dependency latency), not per flop, down there.
+                    const int par = parent[c.b - 1];
+                    const bool child = par >= p.a && par < p.b;
+                    const bool whole = (c.b - c.a) == desc[c.b - 1];
+                    ok = child && whole && (p.b - c.a) <= std::min(opt.subtree_width, opt.max_width);
+                }
+                if (!ok) break;
                 const int wc = c.b - c.a, wp = p.b - p.a;
                 const double z = (double)wc * (wp + (double)cnt[p.b - 1] - (double)cnt[c.b - 1]) + c.zeros + p.zeros;
                 SN m{c.a, p.b, z};

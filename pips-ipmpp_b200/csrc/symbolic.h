@@ -52,6 +52,7 @@ struct SymbolicOptions {
     int max_width = 32;      // supernodes wider than this are split into chains
     int use_metis = 1;
     int relax = 1;
+    int subtree_width = 32;  // bottom subtrees with at most this many columns are merged into one front (0 = off)
 };
 
 // krow/jcol/val: lower CSR (0-based, full diagonal present) of the n x n leaf KKT matrix, block sizes nx/ny/nz.
