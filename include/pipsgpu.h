@@ -104,6 +104,10 @@ int pipsgpu_leaf_get_inertia(pipsgpu_leaf* leaf, int inertia[3], int* n_perturbe
  * entries, out[3]=#fronts, out[4]=#levels, out[5]=#2x2 pivots, out[6]=max front rows, out[7]=contribution entries;
  * *flops = sum_j eta_j(eta_j+2) (SURVEY.md 8(d) stage-1 count) */
 int pipsgpu_leaf_get_stats(pipsgpu_leaf* leaf, int64_t out[8], double* flops);
+/* factor download for parity checks: L = the leaf's panel pool (out[2] = stored panel entries of get_stats; per front an
+ * m x w column-major panel, unit diagonal, layout of pipsgpu_symbolic_export), dinv_d / dinv_e = block-diagonal D^-1
+ * (length n each, permuted order; dinv_e[k] couples k and k+1 of a 2x2 pivot). Any pointer may be NULL. */
+int pipsgpu_leaf_download_factor(pipsgpu_leaf* leaf, double* L, double* dinv_d, double* dinv_e);
 int pipsgpu_leaf_destroy(pipsgpu_leaf* leaf);
 
 /* batched numeric factorisation of all changed leaves of the context AND accumulation of their Schur terms:

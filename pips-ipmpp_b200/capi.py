@@ -221,6 +221,14 @@ class Leaf:
         d["flops"] = fl.value
         return d
 
+    def download_factor(self):
+        """(L panel pool, dinv_d, dinv_e) of the last factorisation - same layout as oracle/mf_ldlt.c"""
+        L = np.zeros(max(self.stats()["stored"], 1))
+        dd = np.zeros(self.n)
+        de = np.zeros(self.n)
+        _check(lib().pipsgpu_leaf_download_factor(self.h, _ip(L), _ip(dd), _ip(de)))
+        return L, dd, de
+
     def add_schur(self, sc):
         _check(lib().pipsgpu_leaf_add_schur(self.h, sc.h))
 

@@ -57,127 +57,182 @@ void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, dou
 //  What the children pushed into this front's C is forwarded in the same pass (v = C - U), so a contribution entry is
 //  written once per tree level it travels and no separate extend-add kernel exists.
 //
-//  small fronts (fewer than BIG_U rows below the pivot block): ONE WARP per front, whole front in one pass;
-//  big fronts: pivot_panel_big_kernel (one CTA per front) + front_update_tiles_kernel (one CTA per 64x64 tile, DMMA).
+//  Per tree level (deepest first), four launches over ALL scenario blocks of the GPU:
+//   pivot_kernel        one warp per front: LDL^T of the w x w pivot block in shared memory (static 1x1 / 2x2 pivots,
+//                       tiny pivots perturbed and counted), then X = L11^-1 to a scratch, so that the panel below
+//                       becomes a small GEMM  W21 = A21 X^T  on the FP64 tensor pipe (+ the scaling L21 = W21 D^-1)
+//   small_fronts_kernel one warp per front with < BIG_U rows: panel + update + push, all in m8n8k4 DMMA tiles
+//   big_panel_kernel    one CTA per big front: panel only
+//   front_update_tiles_kernel  one CTA per 64x64 tile of a big front's update (DMMA) + push
+//  All loops run over shared / global memory with run-time bounds: the code stays a few thousand instructions (the
+//  first, register-array version of these kernels was 63k instructions and spent 58% of its time in instruction-cache
+//  misses, profiles/r1_*).
 // =====================================================================================================
-struct PivotSmem {              // per front: unit-lower L11 and the block diagonal, read by the panel rows (broadcast)
-    double L[MAXW][MAXW + 1];
-    double did[MAXW], die[MAXW];
-    int8_t pt[MAXW];
-};
-
-// LDL^T of the w x w pivot block by one warp, right-looking, rows in registers (lane i holds row i: a[k] = A(i,k),
-// k <= i), static 1x1 / 2x2 pivots, tiny pivots replaced by +-eps and counted. Leaves L11 in ps->L (unit diagonal
-// implied, zeros above), D^-1 in ps->did/die, writes L11 / D / D^-1 to global memory and the inertia counts to stats.
-template <int WP>
-__device__ __forceinline__ void pivot_block_warp(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
-                                                 PivotSmem* ps, int lane) {
-    const unsigned full = 0xffffffffu;
-    const int w = fd.w, m = w + fd.na + fd.nb;
-    double r[WP];
-#pragma unroll
-    for (int k = 0; k < WP; ++k) r[k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
-    const int g0 = fd.col0;
-    const int myt = (lane < w) ? a.ptype[g0 + lane] : 0;
-    const double mysg = (lane < w) ? (double)a.sgn[g0 + lane] : 1.0;
-    const unsigned firstmask = __ballot_sync(full, myt == 1);
-    const unsigned secondmask = __ballot_sync(full, myt == 2);
-    const double eps = a.leaves[fd.leaf].eps;
-    int npos = 0, nneg = 0, nzero = 0, npert = 0;
-    double my_dd = 0.0, my_de = 0.0, my_did = 0.0, my_die = 0.0;   // lane k keeps the D entries of column k
-#pragma unroll
-    for (int k = 0; k < WP; ++k) {
-        if (k >= w) break;
-        if ((secondmask >> k) & 1u) continue;                      // handled together with column k-1
-        const bool pair = ((firstmask >> k) & 1u) && (k + 1 < WP);
-        if (!pair) {
-            double d = __shfl_sync(full, r[k], k);
-            const double sg = __shfl_sync(full, mysg, k);
-            if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-            if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
-            const double inv = 1.0 / d;
-            const double wk = (lane > k) ? r[k] : 0.0;             // unscaled W(i,k)
-            const double lk = wk * inv;
-#pragma unroll
-            for (int j = k + 1; j < WP; ++j) r[j] = fma(-lk, __shfl_sync(full, wk, j), r[j]);
-            if (lane > k) r[k] = lk;
-            if (lane == k) { my_dd = d; my_de = 0.0; my_did = inv; my_die = 0.0; }
-        } else if (k + 1 < WP) {
-            double da = __shfl_sync(full, r[k], k);
-            const double db = __shfl_sync(full, r[k], k + 1);
-            double dc = __shfl_sync(full, r[k + 1], k + 1);
-            double det = da * dc - db * db;
-            if (!(det <= -eps * eps)) {
-                if (da < eps) da = eps;
-                if (dc > -eps) dc = -eps;
-                det = da * dc - db * db;
-                ++npert;
-            }
-            if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
-            const double ia = dc / det, ib = -db / det, ic = da / det;
-            const double w1 = (lane > k + 1) ? r[k] : 0.0;
-            const double w2 = (lane > k + 1) ? r[k + 1] : 0.0;
-            const double l1 = w1 * ia + w2 * ib, l2 = w1 * ib + w2 * ic;
-#pragma unroll
-            for (int j = k + 2; j < WP; ++j) {
-                r[j] = fma(-l1, __shfl_sync(full, w1, j), r[j]);
-                r[j] = fma(-l2, __shfl_sync(full, w2, j), r[j]);
-            }
-            if (lane > k + 1) { r[k] = l1; r[k + 1] = l2; }
-            if (lane == k + 1) r[k] = 0.0;                          // L(k+1,k) = 0 by convention (block pivot)
-            if (lane == k) { my_dd = da; my_de = db; my_did = ia; my_die = ib; }
-            if (lane == k + 1) { my_dd = dc; my_de = 0.0; my_did = ic; my_die = 0.0; }
-        }
-    }
-    // publish: L11 (smem for the panel rows, global for the solves), D, D^-1
-#pragma unroll
-    for (int k = 0; k < WP; ++k) {
-        if (lane < WP) ps->L[lane][k] = (k < lane && lane < w) ? r[k] : 0.0;
-        if (lane < w && k < w) {
-            if (k < lane) F[(size_t)k * m + lane] = r[k];
-            else if (k == lane) F[(size_t)k * m + lane] = 1.0;
-        }
-    }
-    if (lane < WP) {
-        ps->did[lane] = (lane < w) ? my_did : 0.0;
-        ps->die[lane] = (lane < w) ? my_die : 0.0;
-        ps->pt[lane] = (int8_t)((lane < w) ? myt : 0);
-    }
-    if (lane < w) {
-        a.Dd[g0 + lane] = my_dd; a.De[g0 + lane] = my_de; a.Did[g0 + lane] = my_did; a.Die[g0 + lane] = my_die;
-    }
-    if (lane == 0 && a.stats) {
-        int* st = a.stats + 4 * fd.leaf;
-        if (npos) atomicAdd(st + 0, npos);
-        if (nneg) atomicAdd(st + 1, nneg);
-        if (nzero) atomicAdd(st + 2, nzero);
-        if (npert) atomicAdd(st + 3, npert);
-    }
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
-// one row below the pivot block, right-looking: w_k = a_k - sum_{j<k} w_j L(k,j) ;  L21 row = w * D^-1.
-// On exit l[] holds the L21 row (written back to the panel) and the unscaled row w went to the scratch row wr.
-template <int WP>
-__device__ __forceinline__ void panel_row(const PivotSmem* ps, int w, double (&l)[WP], double* __restrict__ wr) {
-#pragma unroll
-    for (int k = 0; k < WP; ++k) {
-        if (k >= w) { l[k] = 0.0; continue; }
-        const double wk = l[k];
-#pragma unroll
-        for (int j = k + 1; j < WP; ++j) l[j] = fma(-wk, ps->L[j][k], l[j]);
+constexpr int PV_WARPS = 2;       // fronts per CTA in pivot_kernel (2 x 2 x 32 x 33 doubles of shared memory)
+constexpr int PLD = MAXW + 1;
+
+__global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int begin, int nfronts) {
+    __shared__ double s_l[PV_WARPS][MAXW * PLD];   // A11 on entry, then L11 (strict lower)
+    __shared__ double s_w[PV_WARPS][MAXW * PLD];   // W11 = L11 D (strict lower), then X = L11^-1
+    __shared__ double s_did[PV_WARPS][MAXW], s_die[PV_WARPS][MAXW];
+    __shared__ int8_t s_pt[PV_WARPS][MAXW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * PV_WARPS + warp;
+    if (fi >= nfronts) return;
+    const unsigned full = 0xffffffffu;
+    const FrontDesc fd = a.fronts[a.level_fronts[begin + fi]];
+    const int w = fd.w, m = w + fd.na + fd.nb, wp = padded_width(w);
+    double* F = a.L + fd.Loff;
+    double* Pl = s_l[warp];
+    double* Pw = s_w[warp];
+    double* did = s_did[warp];
+    double* die = s_die[warp];
+    int8_t* pt = s_pt[warp];
+    for (int k = 0; k < wp; ++k) {
+        Pl[lane * PLD + k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
+        Pw[lane * PLD + k] = 0.0;
     }
-    // l[] now holds the unscaled row w = L21 D: it goes to the scratch, then l is scaled by the block diagonal
+    pt[lane] = (lane < w) ? a.ptype[fd.col0 + lane] : (int8_t)0;
+    did[lane] = 0.0;
+    die[lane] = 0.0;
+    __syncwarp();
+    // ---- LDL^T, left-looking: lane i owns row i, lock-step over the pivots ----
+    {
+        const double eps = a.leaves[fd.leaf].eps;
+        int npos = 0, nneg = 0, nzero = 0, npert = 0;
+        int k = 0;
+        while (k < w) {
+            const bool pair = (pt[k] == 1) && (k + 1 < w);
+            double r1 = 0.0, r2 = 0.0;
+            if (lane >= k && lane < w) {
+                r1 = Pl[lane * PLD + k];
+                for (int j = 0; j < k; ++j) r1 = fma(-Pl[lane * PLD + j], Pw[k * PLD + j], r1);
+                if (pair && lane >= k + 1) {
+                    r2 = Pl[lane * PLD + k + 1];
+                    for (int j = 0; j < k; ++j) r2 = fma(-Pl[lane * PLD + j], Pw[(k + 1) * PLD + j], r2);
+                }
+            }
+            const int g = fd.col0 + k;
+            if (!pair) {
+                double d = __shfl_sync(full, r1, k);
+                const double sg = (double)a.sgn[g];
+                if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
+                if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
+                const double inv = 1.0 / d;
+                if (lane > k && lane < w) { Pw[lane * PLD + k] = r1; Pl[lane * PLD + k] = r1 * inv; }
+                if (lane == k) {
+                    a.Dd[g] = d; a.De[g] = 0.0; a.Did[g] = inv; a.Die[g] = 0.0;
+                    did[k] = inv; die[k] = 0.0;
+                }
+                k += 1;
+            } else {
+                double da = __shfl_sync(full, r1, k);
+                const double db = __shfl_sync(full, r1, k + 1);
+                double dc = __shfl_sync(full, r2, k + 1);
+                double det = da * dc - db * db;
+                if (!(det <= -eps * eps)) {
+                    if (da < eps) da = eps;
+                    if (dc > -eps) dc = -eps;
+                    det = da * dc - db * db;
+                    ++npert;
+                }
+                if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
+                const double ia = dc / det, ib = -db / det, ic = da / det;
+                if (lane > k + 1 && lane < w) {
+                    Pw[lane * PLD + k] = r1; Pw[lane * PLD + k + 1] = r2;
+                    Pl[lane * PLD + k] = r1 * ia + r2 * ib;
+                    Pl[lane * PLD + k + 1] = r1 * ib + r2 * ic;
+                }
+                if (lane == k + 1) { Pl[(k + 1) * PLD + k] = 0.0; Pw[(k + 1) * PLD + k] = 0.0; }
+                if (lane == k) {
+                    a.Dd[g] = da; a.De[g] = db; a.Dd[g + 1] = dc; a.De[g + 1] = 0.0;
+                    a.Did[g] = ia; a.Die[g] = ib; a.Did[g + 1] = ic; a.Die[g + 1] = 0.0;
+                    did[k] = ia; die[k] = ib; did[k + 1] = ic; die[k + 1] = 0.0;
+                }
+                k += 2;
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && a.stats) {
+            int* st = a.stats + 4 * fd.leaf;
+            if (npos) atomicAdd(st + 0, npos);
+            if (nneg) atomicAdd(st + 1, nneg);
+            if (nzero) atomicAdd(st + 2, nzero);
+            if (npert) atomicAdd(st + 3, npert);
+        }
+    }
+    // ---- L11 to the panel (unit diagonal) ----
+    for (int k = 0; k < w; ++k)
+        if (lane < w && lane >= k) F[(size_t)k * m + lane] = (lane == k) ? 1.0 : Pl[lane * PLD + k];
+    if (fd.na + fd.nb == 0) return;
+    // ---- X = L11^-1 (lane = column c of X, forward substitution; overwrites W11) ----
+    for (int i = 0; i < wp; ++i) {
+        double acc = 0.0;
+        if (i < w)
+            for (int j = 0; j < i; ++j) acc = fma(Pl[i * PLD + j], Pw[j * PLD + lane], acc);
+        __syncwarp();
+        Pw[i * PLD + lane] = (i == lane && i < w) ? 1.0 : ((i > lane && i < w) ? -acc : 0.0);
+        __syncwarp();
+    }
+    // ---- X to the scratch, row-major [n][kk] with leading dimension wp (zero padded) ----
+    double* X = a.XY + fd.XYoff;
+    if (lane < wp)
+        for (int n = 0; n < wp; ++n) X[(size_t)n * wp + lane] = Pw[n * PLD + lane];
+}
+void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
+    if (nfronts <= 0) return;
+    pivot_kernel<<<cdiv(nfronts, PV_WARPS), PV_WARPS * 32, 0, s>>>(a, begin, nfronts);
+    COUNT_LAUNCH();
+}
+
+// 32 rows [i0, i0+32) of the panel by one warp:  W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so
+// column tile y only needs A21(:, 0 .. 8y+7)), stored k-major in the scratch; then L21 = W21 D^-1 (block diagonal, 2x2
+// blocks couple neighbouring columns) row by row, written over A21.
+__device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
+                                            double* __restrict__ Wt, const double* __restrict__ X, int i0, int lane) {
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
+    const int lr = lane >> 2, lk = lane & 3;
+    double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
+    for (int y = 0; y < wp / 8; ++y) {
+        double aw[4][2];
 #pragma unroll
-    for (int k = 0; k < WP; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(l[k], l[k + 1]);
+        for (int x = 0; x < 4; ++x) aw[x][0] = aw[x][1] = 0.0;
+        const int kend = (y + 1) * 8;
+        const int n = y * 8 + lr;              // output column of this lane's B fragment
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            const int k = k0 + lk;
+            const double bx = X[(size_t)n * wp + k];
 #pragma unroll
-    for (int k = 0; k < WP; ++k) {
-        if (k >= w) break;
-        const int t = ps->pt[k];
-        if (t == 0) l[k] *= ps->did[k];
-        else if (t == 1 && k + 1 < WP) {
-            const double x = l[k], y = l[k + 1];
-            l[k] = x * ps->did[k] + y * ps->die[k];
-            l[k + 1] = x * ps->die[k] + y * ps->did[k + 1];
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x * 8 + lr;
+                const double af = (i < u && k < w) ? A21[(size_t)k * m + i] : 0.0;
+                dmma_m8n8k4(aw[x][0], aw[x][1], af, bx);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int i = i0 + x * 8 + lr;
+            if (i >= u) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Wt[(size_t)(y * 8 + lk * 2 + e) * u + i] = aw[x][e];
+        }
+    }
+    __syncwarp();
+    const int i = i0 + lane;
+    if (i < u) {
+        const int g0 = fd.col0;
+        for (int k = 0; k < w; ++k) {
+            const int t = a.ptype[g0 + k];
+            double l = Wt[(size_t)k * u + i] * a.Did[g0 + k];
+            if (t == 1) l = fma(Wt[(size_t)(k + 1) * u + i], a.Die[g0 + k], l);
+            else if (t == 2) l = fma(Wt[(size_t)(k - 1) * u + i], a.Die[g0 + k - 1], l);
+            A21[(size_t)k * m + i] = l;
         }
     }
 }
@@ -205,69 +260,69 @@ __device__ __forceinline__ void push_entry(const PushTarget& t, int ri, int rj, 
 
 constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
 
-template <int WP>
-__device__ __forceinline__ void small_front(const FactorArgs& a, const FrontDesc& fd, PivotSmem* ps, int lane) {
-    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
-    double* F = a.L + fd.Loff;
-    pivot_block_warp<WP>(a, fd, F, ps, lane);
-    if (u == 0) return;
-    __syncwarp();
-    double* Wscr = a.W + fd.Woff;
-    const double* Cs = a.C + fd.Coff;
-    const int* rowg = a.rowg + fd.rows_off;
-    const int* rel = a.relidx + fd.rows_off;
-    const PushTarget pt = push_target(a, fd);
-    // ---- panel rows (all chunks first: the update needs the W rows of every earlier row) ----
-    for (int i0 = 0; i0 < u; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < u) {
-            double l[WP];
-#pragma unroll
-            for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + i] : 0.0;
-            panel_row<WP>(ps, w, l, Wscr + (size_t)i * WP);
-#pragma unroll
-            for (int k = 0; k < WP; ++k)
-                if (k < w) F[(size_t)k * m + w + i] = l[k];
-        }
-    }
-    __syncwarp();
-    // ---- update + push ----
-    for (int i0 = 0; i0 < u; i0 += 32) {
-        const int i = i0 + lane;
-        const bool act = i < u;
-        double l[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) l[k] = (act && k < w) ? F[(size_t)k * m + w + i] : 0.0;
-        const int ri = act ? rel[i] : 0;
-        const int64_t scrow = (act && i >= na && a.SC) ? (int64_t)rowg[i] * a.ldsc : 0;
-        const int jmax = min(i0 + 31, u - 1);
-        for (int j = 0; j <= jmax; ++j) {
-            const double* wj = Wscr + (size_t)j * WP;
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < WP; k += 2) {
-                const double2 wk = *reinterpret_cast<const double2*>(wj + k);
-                acc0 = fma(l[k], wk.x, acc0);
-                acc1 = fma(l[k + 1], wk.y, acc1);
-            }
-            if (!act || j > i) continue;
-            const double acc = acc0 + acc1;
-            if (j < na) push_entry(pt, ri, rel[j], Cs[(size_t)j * u + i] - acc);
-            else if (a.SC) atomicAdd(&a.SC[scrow + rowg[j]], -acc);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SF_WARPS * 32) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
-    __shared__ PivotSmem s_ps[SF_WARPS];
+__global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * SF_WARPS + warp;
     if (fi >= nfronts) return;
     const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
-    const int cls = width_class(fd.w);
-    if (cls == 0) small_front<8>(a, fd, &s_ps[warp], lane);
-    else if (cls == 1) small_front<16>(a, fd, &s_ps[warp], lane);
-    else small_front<32>(a, fd, &s_ps[warp], lane);
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
+    if (u == 0) return;
+    double* F = a.L + fd.Loff;
+    double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
+    const double* X = a.XY + fd.XYoff;
+    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
+    __syncwarp();
+    // ---- update + push: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp) ----
+    const double* Cs = a.C + fd.Coff;
+    const int* rowg = a.rowg + fd.rows_off;
+    const int* rel = a.relidx + fd.rows_off;
+    const PushTarget pt = push_target(a, fd);
+    const int lr = lane >> 2, lk = lane & 3;
+    const double* L21 = F + w;                 // L21(i,k) = L21[k*m + i]
+    for (int bi = 0; bi * 32 < u; ++bi) {
+        for (int bj = 0; bj <= bi; ++bj) {
+            double acc[4][4][2];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+            for (int k0 = 0; k0 < wp; k0 += 4) {
+                double af[4], bf[4];
+                const int k = k0 + lk;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = bi * 32 + x * 8 + lr;
+                    af[x] = (i < u && k < w) ? L21[(size_t)k * m + i] : 0.0;
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int j = bj * 32 + y * 8 + lr;
+                    bf[y] = (j < u) ? Wt[(size_t)k * u + j] : 0.0;
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = bi * 32 + x * 8 + lr;
+                if (i >= u) continue;
+                const int ri = rel[i];
+                const int64_t scrow = (i >= na && a.SC) ? (int64_t)rowg[i] * a.ldsc : 0;
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = bj * 32 + y * 8 + lk * 2 + e;
+                        if (j > i) continue;
+                        const double v = acc[x][y][e];
+                        if (j < na) push_entry(pt, ri, rel[j], Cs[(size_t)j * u + i] - v);
+                        else if (a.SC) atomicAdd(&a.SC[scrow + rowg[j]], -v);
+                    }
+            }
+        }
+    }
 }
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
@@ -275,36 +330,21 @@ void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream
     COUNT_LAUNCH();
 }
 
-// big fronts: pivot block by warp 0, then one thread per row for the panel (L21 in place, W21 = L21 D to the scratch)
+// big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-template <int WP>
-__device__ __forceinline__ void big_front_panel(const FactorArgs& a, const FrontDesc& fd, PivotSmem* ps) {
-    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
-    double* F = a.L + fd.Loff;
-    if (threadIdx.x < 32) pivot_block_warp<WP>(a, fd, F, ps, threadIdx.x);
-    __syncthreads();
-    double* Wscr = a.W + fd.Woff;
-    for (int i = threadIdx.x; i < u; i += BF_T) {
-        double l[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) l[k] = (k < w) ? F[(size_t)k * m + w + i] : 0.0;
-        panel_row<WP>(ps, w, l, Wscr + (size_t)i * WP);
-#pragma unroll
-        for (int k = 0; k < WP; ++k)
-            if (k < w) F[(size_t)k * m + w + i] = l[k];
-    }
-}
-__global__ void __launch_bounds__(BF_T) pivot_panel_big_kernel(FactorArgs a, int begin) {
-    __shared__ PivotSmem s_ps;
+__global__ void __launch_bounds__(BF_T) big_panel_kernel(FactorArgs a, int begin) {
     const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
-    const int cls = width_class(fd.w);
-    if (cls == 0) big_front_panel<8>(a, fd, &s_ps);
-    else if (cls == 1) big_front_panel<16>(a, fd, &s_ps);
-    else big_front_panel<32>(a, fd, &s_ps);
+    const int w = fd.w, u = fd.na + fd.nb;
+    double* F = a.L + fd.Loff;
+    double* Wt = a.W + fd.Woff;
+    const double* X = a.XY + fd.XYoff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    (void)w;
+    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
 }
-void launch_pivot_panel_big(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
+void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    pivot_panel_big_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
+    big_panel_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
     COUNT_LAUNCH();
 }
 
@@ -314,11 +354,6 @@ void launch_pivot_panel_big(const FactorArgs& a, int begin, int nfronts, cudaStr
 // C(i,j) -= U(i,j) for ancestor columns j < na, Schur complement -= U(i,j) for border x border (red.global.add.f64).
 // Operands are staged in shared memory (stride 36 doubles: conflict-free m8n8k4 fragment loads).
 // -----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 constexpr int TLD = 36;
 __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, int64_t tile_begin) {
     __shared__ double As[TILE * TLD];
@@ -337,8 +372,8 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
         As[r * TLD + k] = (k < w && i0 + r < u) ? F[(size_t)k * m + w + i0 + r] : 0.0;
     }
     for (int idx = tid; idx < TILE * 32; idx += 128) {
-        const int r = idx >> 5, k = idx & 31;
-        Bs[r * TLD + k] = (k < wp && j0 + r < u) ? Wscr[(size_t)(j0 + r) * wp + k] : 0.0;
+        const int k = idx >> 6, r = idx & 63;
+        Bs[r * TLD + k] = (k < wp && j0 + r < u) ? Wscr[(size_t)k * u + j0 + r] : 0.0;
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;

@@ -18,7 +18,8 @@ struct FrontDesc {
     int64_t Loff;      // panel: m x w column-major (ld = m), rows = [pivot cols | ancestor rows | border rows]
     int64_t Coff;      // contribution block: (na+nb) x na column-major (ld = na+nb), lower trapezoid
     int64_t rows_off;  // into rowg / relidx (na+nb entries)
-    int64_t Woff;      // per-level scratch: W21 = L21*D, (na+nb) rows, row-major with stride wp(w)
+    int64_t Woff;      // per-level scratch: W21 = L21*D, (na+nb) x wp(w), k-major: W21(j,k) = W[k*(na+nb) + j]
+    int64_t XYoff;     // per-level scratch: X = L11^-1, wp x wp row-major
     int64_t upd_off;   // solve-phase update vector (na entries)
     int w, na, nb;
     int col0;          // global position of the first pivot column
@@ -50,6 +51,7 @@ struct FactorArgs {
     double* L;
     double* C;
     double* W;                   // per-level scratch
+    double* XY;                  // per-level scratch
     double* Dd; double* De;      // D      (diagonal / coupling to the next position for 2x2 pivots)
     double* Did; double* Die;    // D^-1
     double* SC;                  // dense Schur complement, lower, row-major (may be null)
@@ -100,8 +102,9 @@ void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s);
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
 void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
+void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);             // fronts level_fronts[begin..)
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);      // fronts fl_fronts[begin..)
-void launch_pivot_panel_big(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);
+void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
 void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);

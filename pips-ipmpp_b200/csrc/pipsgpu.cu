@@ -153,6 +153,8 @@ struct pipsgpu_ctx {
     std::vector<int> level_ptr;     // nlevels*NCLS+1 into level_fronts; group g = level_order*NCLS + width class, deepest level first
     std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
     DevBuf<TileDesc> tiles;
+    DevBuf<double> XY;
+    int64_t XYtot = 0;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
     std::vector<int> fl_ptr;        // nlevels*2+1 into fl_fronts; group = level_order*2 + (0 small | 1 big)
     DevBuf<int> fl_fronts;
@@ -172,7 +174,7 @@ struct pipsgpu_ctx {
         FactorArgs a;
         a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.fl_fronts = fl_fronts.p; a.child_list = child_list.p;
         a.rowg = rowg.p; a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p;
-        a.W = W.p;
+        a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         return a;
@@ -269,12 +271,18 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
     cudaStream_t s = ctx->stream;
     FactorArgs fa = ctx->factor_args(sc);
     for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
+        if (only) {
+            for (int c = 0; c < NCLS; ++c) launch_pivot(fa, only->level_begin[lv * NCLS + c], only->level_count[lv * NCLS + c], s);
+        } else {
+            const int begin = ctx->level_ptr[lv * NCLS];
+            launch_pivot(fa, begin, ctx->level_ptr[(lv + 1) * NCLS] - begin, s);
+        }
         for (int kind = 0; kind < 2; ++kind) {
             const int g = lv * 2 + kind;
             int begin = ctx->fl_ptr[g], count = ctx->fl_ptr[g + 1] - ctx->fl_ptr[g];
             if (only) { begin = only->fl_begin[g]; count = only->fl_count[g]; }
             if (kind == 0) launch_small_fronts(fa, begin, count, s);
-            else launch_pivot_panel_big(fa, begin, count, s);
+            else launch_big_panel(fa, begin, count, s);
         }
         int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
         if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
@@ -617,7 +625,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->level_ptr.assign(ngroups + 1, 0);
     for (int l = 0; l < ngroups; ++l) ctx->level_ptr[l + 1] = ctx->level_ptr[l] + level_count[l];
     std::vector<int> level_fronts((size_t)nfr), lfill(ctx->level_ptr.begin(), ctx->level_ptr.end() - 1);
-    std::vector<int64_t> wfill(nlev, 0);
+    std::vector<int64_t> wfill(nlev, 0), xyfill(nlev, 0);
 
     int64_t rows_off = 0, child_off = 0;
     for (auto* lf : ctx->leaves) {
@@ -643,6 +651,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
+            fd.XYoff = xyfill[ol];
+            xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
         }
         for (size_t t = 0; t < S.rowidx.size(); ++t) {
             const int r = S.rowidx[t];
@@ -686,6 +696,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
+    ctx->XYtot = 0;
+    for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
     // ---- factorisation launch lists: fronts grouped by (level, small|big), by leaf inside a group ----
     std::vector<int> fl_fronts((size_t)nfr);
     {
@@ -750,7 +762,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
     ctx->fl_fronts.upload(fl_fronts, s);
-    ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2);
+    ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
     ctx->Die.alloc((size_t)npos + 1);
     ctx->x.alloc((size_t)npos + 1); ctx->upd.alloc((size_t)updtot + 1); ctx->dvals.alloc((size_t)npos + 1);
@@ -932,6 +944,21 @@ int pipsgpu_leaf_get_stats(pipsgpu_leaf* lf, int64_t out[8], double* flops) {
         out[4] = S.nlevels; out[5] = S.n_pairs; out[6] = S.max_m; out[7] = S.Coff.empty() ? 0 : S.Coff.back();
         if (flops) *flops = S.flops_factor;
     }
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_download_factor(pipsgpu_leaf* lf, double* L, double* dinv_d, double* dinv_e) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_download_factor: null leaf");
+    pipsgpu_ctx* ctx = lf->ctx;
+    require_device(ctx);
+    if (!lf->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_download_factor: leaf not factorized");
+    cudaStream_t s = ctx->stream;
+    if (L && lf->Lsize > 0)
+        CUDA_CHECK(cudaMemcpyAsync(L, ctx->L.p + lf->Lbase, sizeof(double) * (size_t)lf->Lsize, cudaMemcpyDeviceToHost, s));
+    if (dinv_d) CUDA_CHECK(cudaMemcpyAsync(dinv_d, ctx->Did.p + lf->pos_off, sizeof(double) * (size_t)lf->n, cudaMemcpyDeviceToHost, s));
+    if (dinv_e) CUDA_CHECK(cudaMemcpyAsync(dinv_e, ctx->Die.p + lf->pos_off, sizeof(double) * (size_t)lf->n, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
     PIPSGPU_CATCH
 }
 

@@ -321,3 +321,37 @@ def test_two_gpus_nccl_allreduce_equals_single_rank_oracle(pkg, cfg):
         assert inertia == ref.inertia()
         assert _rel(sol0, want[0]) <= 1e-8
         assert _rel(soll, np.stack(want[1 + lo:1 + hi])) <= 1e-8
+
+
+@pytest.mark.parametrize("cfg", ["T1", "T3"])
+def test_factor_entries_match_c_oracle(pkg, cfg):
+    """factor-level parity: the L panels and D^-1 downloaded from the device against oracle/mf_ldlt.c on the SAME
+    symbolic structure (identical layout), front by front. 1e-9 relative to the largest factor entry (the device sums
+    in DMMA-tile order, the oracle left to right)."""
+    from oracle import mf
+    P = pkg.problem
+    lp = P.synthetic(cfg)
+    dd, nom = _iterate(pkg, lp, cfg)
+    ctx = pkg.capi.Context(0)
+    ch = lp.children[0]
+    n = ch.n + ch.my + ch.mz
+    krow, jcol, val = pkg.linsys.create_kkt_lower(ch)
+    leaf = pkg.capi.Leaf(ctx, n, ch.n, ch.my, ch.mz, krow, jcol, val)
+    ctx.commit()
+    leaf.set_diagonal(dd[1], nom[1])
+    assert leaf.factorize() == (ch.n, ch.my + ch.mz, 0)
+    Lg, dg, eg = leaf.download_factor()
+    krow2, jcol2, val2, diag_pos, nB, brow, bcol, bval = mf.leaf_kkt_and_border(lp, 0)
+    val2 = val2.copy()
+    val2[diag_pos[:ch.n]] = dd[1]
+    val2[diag_pos[ch.n + ch.my:]] = nom[1]
+    none = np.zeros(0, np.int32)
+    sym = pkg.capi.Symbolic(n, ch.n, ch.my, ch.mz, krow2, jcol2, val2, 0, none, none).export()
+    ref = mf.MfLeaf(sym)
+    assert ref.factorize(val2, np.zeros(0)) == ((ch.n, ch.my + ch.mz, 0), 0)
+    assert len(Lg) == int(sym["Loff"][-1])
+    scale = np.abs(ref.L[:len(Lg)]).max()
+    assert np.abs(Lg - ref.L[:len(Lg)]).max() <= 1e-9 * scale
+    assert np.abs(dg - ref.dinv_d[:n]).max() <= 1e-9 * np.abs(ref.dinv_d[:n]).max()
+    assert np.abs(eg - ref.dinv_e[:n]).max() <= 1e-9 * max(np.abs(ref.dinv_e[:n]).max(), 1e-300)
+    ctx.close()
