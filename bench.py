@@ -290,12 +290,15 @@ def main():
     sampler.start()
     l0 = sys_.ctx.launch_count()
     stage_acc = {}
+    ktime_acc = {}
     ms_res = 0.0
     # resident timing, one step at a time so that the per-stage event timers can be averaged
     for _ in range(args.steps):
         ms_res += timed(step_resident, 1)
         for k_, v_ in kkt.stage_times().items():
             stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
+        for k_, v_ in kkt.kernel_times().items():
+            ktime_acc[k_] = ktime_acc.get(k_, 0.0) + v_
     launches = sys_.ctx.launch_count() - l0
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop()
@@ -303,18 +306,38 @@ def main():
     ms_per_step = ms_res / args.steps
     ms_per_step_e2e = ms_e2e / args.steps
 
-    # ---- algorithmic counts and roofline of the dominant kernel (front_factor_kernel: leaf LDL^T + Schur terms) ----
+    # ---- algorithmic counts and the rooflines of the two kernels groups that make up the step ----
     cnt = canonical_counts(lp, leaf_stats, args.solves)
     peak_gbs, peak_src = measured_peaks()
+    pools = sys_.ctx.pool_sizes()
+    nnzL = sum(s["nnzL"] for s in leaf_stats)
+    # (1) streaming solve: one launch = one K^-1 application over all blocks of the rank; algorithmic bytes = 24 nnz(L)
+    #     (factor entry + index read once forward, once backward: B4 / 2 applications per solveCompressed)
+    t_ps = ktime_acc["psolve"] / args.steps * 1e-3
+    ps_bytes = 24.0 * nnzL
+    ps_ach = ps_bytes / t_ps / 1e9
+    roof_solve = {"kernel": "psolve_stream_kernel (persistent supernodal forward+backward solve of all blocks, one launch per K^-1)",
+                  "bound": "hbm", "achieved": ps_ach, "peak": peak_gbs, "unit": "GB/s", "frac": ps_ach / peak_gbs,
+                  "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ps_bytes,
+                  "avg_launch_ms": t_ps * 1e3, "launches_per_step": 2 * args.solves,
+                  "share_of_step": 2 * args.solves * t_ps * 1e3 / ms_per_step,
+                  "stored_bytes_per_launch": 16.0 * pools["solve_pool"],
+                  "stored_bytes_GBps": 16.0 * pools["solve_pool"] / t_ps / 1e9}
+    # (2) leaf factorisation + fused Schur terms: all level launches of one factorize; algorithmic bytes = B1 + B2
     t_leaf = stage_ms["leaf_ldlt_schur"] * 1e-3
     nlev = max(s["nlevels"] for s in leaf_stats)
     achieved = (cnt["B1"] + cnt["B2"]) / t_leaf / 1e9
-    roofline = {"kernel": "front_factor_kernel (leaf LDL^T + Schur terms, one launch per tree level)",
-                "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": cnt["B1"] + cnt["B2"], "launches_per_step": nlev,
-                "avg_launch_ms": stage_ms["leaf_ldlt_schur"] / nlev,
-                "stage1_only_GBps": cnt["B1"] / t_leaf / 1e9}
+    roof_leaf = {"kernel": "leaf LDL^T + Schur terms (pivot / small_fronts / big_panel / front_update_tiles kernels, "
+                           "one launch set per tree level, + pack_solve)",
+                 "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                 "traffic": None, "peak_source": peak_src,
+                 "algorithmic_bytes_per_step": cnt["B1"] + cnt["B2"], "tree_levels": nlev,
+                 "share_of_step": stage_ms["leaf_ldlt_schur"] / ms_per_step,
+                 "stage1_only_GBps": cnt["B1"] / t_leaf / 1e9,
+                 "stored_factor_GBps": 8.0 * (pools["L"] + 2 * pools["C"]) / t_leaf / 1e9,
+                 "credited_F1_F2_tflops": (cnt["F1"] + cnt["F2"]) / t_leaf / 1e12}
+    roofline = roof_solve if roof_solve["share_of_step"] >= roof_leaf["share_of_step"] else roof_leaf
+    roofline_other = roof_leaf if roofline is roof_solve else roof_solve
     t_root = stage_ms["root_ldlt"] * 1e-3
     schur_tflops = (cnt["F2"] + cnt["F3"]) / (t_leaf + t_root) / 1e12
     nbytes = 8
@@ -339,7 +362,10 @@ def main():
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": roofline,
+                "roofline_other": roofline_other,
+                "pools": pools,
                 "stages_ms": stage_ms,
+                "kernels_ms": {k_: v_ / args.steps for k_, v_ in ktime_acc.items()},
                 "schur_fp64_tflops_credited": schur_tflops,
                 "canonical_counts": cnt,
                 "cpu_baseline": cpu}

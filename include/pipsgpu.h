@@ -186,6 +186,13 @@ pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* kkt);
 /* device time in ms of the stages of the last factorize: out[0]=H2D+assembly, [1]=leaf LDL^T + Schur terms,
  * [2]=allreduce, [3]=finalize, [4]=root LDL^T ; and of the last solve_compressed: [5]=Lsolve, [6]=Dsolve, [7]=Ltsolve */
 int pipsgpu_kkt_stage_times(pipsgpu_kkt* kkt, double out[8]);
+/* device time in ms of single kernels, CUDA events on the context's stream: out[0] = the streaming solve launch of the
+ * last Lsolve (one K^-1 application over all blocks), [1] = factor -> solve-pool pack of the last factorize,
+ * [2] = dense root solve kernel of the last Dsolve, [3] reserved (measurement only, no reference counterpart) */
+int pipsgpu_kkt_kernel_times(pipsgpu_kkt* kkt, double out[4]);
+/* sizes of the context pools after commit: out = {L entries, C entries, solve-pool entries, fronts, KKT rows, tree
+ * levels, nnz(K), nnz(Bord)} (measurement only) */
+int pipsgpu_ctx_pool_sizes(pipsgpu_ctx* ctx, int64_t out[8]);
 /* measured FP64 tensor-pipe (DMMA, mma.sync m8n8k4 f64) peak of this GPU in TFLOP/s: register-resident chains on all
  * SMs, CUDA-event timed; the denominator of the "fraction of FP64 tensor peak" figures (no reference counterpart) */
 int pipsgpu_bench_dmma_peak(pipsgpu_ctx* ctx, double* tflops);

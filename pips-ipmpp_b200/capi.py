@@ -152,6 +152,12 @@ class Context:
     def launch_count(self):
         return int(lib().pipsgpu_ctx_launch_count(self.h))
 
+    def pool_sizes(self):
+        out = np.zeros(8, dtype=np.int64)
+        _check(lib().pipsgpu_ctx_pool_sizes(self.h, _ip(out)))
+        keys = ("L", "C", "solve_pool", "fronts", "rows", "levels", "nnzK", "nnzB")
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def close(self):
         if self.h:
             _check(lib().pipsgpu_ctx_destroy(self.h))
@@ -341,6 +347,11 @@ class KKT:
         _check(lib().pipsgpu_kkt_stage_times(self.h, _ip(out)))
         keys = ("h2d_assembly", "leaf_ldlt_schur", "allreduce", "finalize", "root_ldlt", "lsolve", "dsolve", "ltsolve")
         return dict(zip(keys, out.tolist()))
+
+    def kernel_times(self):
+        out = np.zeros(4)
+        _check(lib().pipsgpu_kkt_kernel_times(self.h, _ip(out)))
+        return dict(zip(("psolve", "pack_solve", "dense_solve"), out.tolist()))
 
     def close(self):
         if self.h:

@@ -17,6 +17,7 @@ namespace pipsgpu {
 
 static std::atomic<int64_t> g_launches{0};
 int64_t kernel_launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -47,31 +48,43 @@ void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, dou
 }
 
 // =====================================================================================================
-// multifrontal numeric factorisation (push formulation, no extend-add pass)
+// multifrontal numeric factorisation (pull formulation: every front is written by its owner only)
 //
 //  Every front's panel F (m x w, column-major) starts as zeros + its own K / border entries (scatter_values_kernel).
-//  A front's update  U = L21 * (L21 D)^T  is PUSHED, entry by entry, to where it is needed next:
-//     ancestor x ancestor / border x ancestor  ->  the parent front's panel (pivot columns) or the parent's pass-through
-//                                                  block C (remaining ancestor columns), red.global.add.f64;
-//     border x border                          ->  the dense Schur complement  (SC -= Bord^T K^-1 Bord).
-//  What the children pushed into this front's C is forwarded in the same pass (v = C - U), so a contribution entry is
-//  written once per tree level it travels and no separate extend-add kernel exists.
+//  The assembled value of an entry (r, s) of front p (local row indices, r >= s) is
+//        own(r, s) + sum over children c of  C_c(inv_c[r], inv_c[s])      (inv_c = inverse of the child's relative indices)
+//  and is GATHERED by whoever consumes it - the pivot block by pivot_kernel, the panel rows by panel_chunk, the
+//  pass-through part by the update kernels, which write   C_p = (children's pass-through) - L21 (L21 D)^T   with plain
+//  stores. No extend-add pass, no zero-fill of the contribution pool, and no atomics except for the border x border part
+//  of the update, which is this front's share of  SC -= Bord^T K^-1 Bord  and goes straight to the dense Schur complement
+//  (red.global.add.f64). (The first version pushed every update entry to the parent with atomics: it was bound by the
+//  RED issue rate of the SMs, ~1.3 cycles per lane - profiles/README.md.)
 //
 //  Per tree level (deepest first), four launches over ALL scenario blocks of the GPU:
-//   pivot_kernel        one warp per front: LDL^T of the w x w pivot block in shared memory (static 1x1 / 2x2 pivots,
-//                       tiny pivots perturbed and counted), then X = L11^-1 to a scratch, so that the panel below
+//   pivot_kernel        one warp per front: assembly + LDL^T of the w x w pivot block in shared memory (static 1x1 / 2x2
+//                       pivots, tiny pivots perturbed and counted), then X = L11^-1 to a scratch, so that the panel below
 //                       becomes a small GEMM  W21 = A21 X^T  on the FP64 tensor pipe (+ the scaling L21 = W21 D^-1)
-//   small_fronts_kernel one warp per front with < BIG_U rows: panel + update + push, all in m8n8k4 DMMA tiles
+//   small_fronts_kernel one warp per front with < BIG_U rows: panel + update, all in m8n8k4 DMMA tiles
 //   big_panel_kernel    one CTA per big front: panel only
-//   front_update_tiles_kernel  one CTA per 64x64 tile of a big front's update (DMMA) + push
-//  All loops run over shared / global memory with run-time bounds: the code stays a few thousand instructions (the
-//  first, register-array version of these kernels was 63k instructions and spent 58% of its time in instruction-cache
-//  misses, profiles/r1_*).
+//   front_update_tiles_kernel  one CTA per 64x64 tile of a big front's update (DMMA)
 // =====================================================================================================
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// one child of a front as seen by the parent's gathers
+struct ChildRef {
+    const double* C;     // child's contribution block, (na+nb) x na column-major
+    const int* inv;      // parent local row -> child row (0 .. na+nb-1) or -1
+    int u;               // child's na + nb
+};
+__device__ __forceinline__ ChildRef child_ref(const FactorArgs& a, int c) {
+    const FrontDesc& cd = a.fronts[a.child_list[c]];
+    ChildRef r;
+    r.C = a.C + cd.Coff; r.inv = a.invmap + cd.inv_off; r.u = cd.na + cd.nb;
+    return r;
 }
 
 constexpr int PV_WARPS = 2;       // fronts per CTA in pivot_kernel (2 x 2 x 32 x 33 doubles of shared memory)
@@ -97,6 +110,15 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     for (int k = 0; k < wp; ++k) {
         Pl[lane * PLD + k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
         Pw[lane * PLD + k] = 0.0;
+    }
+    // children's contributions to the pivot block: lane = row, inverse indices of the columns by shuffle
+    for (int c = fd.child_begin; c < fd.child_end; ++c) {
+        const ChildRef ch = child_ref(a, c);
+        const int ci = (lane < w) ? ch.inv[lane] : -1;
+        for (int k = 0; k < w; ++k) {
+            const int cj = __shfl_sync(full, ci, k);
+            if (cj >= 0 && ci >= 0 && lane >= k) Pl[lane * PLD + k] += ch.C[(size_t)cj * ch.u + ci];
+        }
     }
     pt[lane] = (lane < w) ? a.ptype[fd.col0 + lane] : (int8_t)0;
     did[lane] = 0.0;
@@ -199,6 +221,20 @@ __device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc
     const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
     const int lr = lane >> 2, lk = lane & 3;
     double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
+    // children's contributions to these 32 panel rows (in place: the panel is written by its owner only)
+    if (fd.child_end > fd.child_begin) {
+        const int i = i0 + lane;
+        for (int c = fd.child_begin; c < fd.child_end; ++c) {
+            const ChildRef ch = child_ref(a, c);
+            const int ci = (i < u) ? ch.inv[w + i] : -1;
+            const int cjl = (lane < w) ? ch.inv[lane] : -1;
+            for (int k = 0; k < w; ++k) {
+                const int cj = __shfl_sync(0xffffffffu, cjl, k);
+                if (cj >= 0 && ci >= 0) A21[(size_t)k * m + i] += ch.C[(size_t)cj * ch.u + ci];
+            }
+        }
+        __syncwarp();
+    }
     for (int y = 0; y < wp / 8; ++y) {
         double aw[4][2];
 #pragma unroll
@@ -237,27 +273,6 @@ __device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc
     }
 }
 
-// destination of the update entry (front row i, front column j < na) in the parent front
-struct PushTarget {
-    double* Fp;      // parent panel
-    double* Cp;      // parent pass-through block
-    int wp, mp, up;
-};
-__device__ __forceinline__ PushTarget push_target(const FactorArgs& a, const FrontDesc& fd) {
-    PushTarget t;
-    t.Fp = nullptr; t.Cp = nullptr; t.wp = 0; t.mp = 0; t.up = 0;
-    if (fd.parent >= 0) {
-        const FrontDesc& pd = a.fronts[fd.parent];
-        t.wp = pd.w; t.up = pd.na + pd.nb; t.mp = t.wp + t.up;
-        t.Fp = a.L + pd.Loff; t.Cp = a.C + pd.Coff;
-    }
-    return t;
-}
-__device__ __forceinline__ void push_entry(const PushTarget& t, int ri, int rj, double v) {
-    double* dst = (rj < t.wp) ? t.Fp + (size_t)rj * t.mp + ri : t.Cp + (size_t)(rj - t.wp) * t.up + (ri - t.wp);
-    atomicAdd(dst, v);
-}
-
 constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
 
 __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
@@ -272,13 +287,12 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
     const double* X = a.XY + fd.XYoff;
     for (int i0 = 0; i0 < u; i0 += 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
     __syncwarp();
-    // ---- update + push: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp) ----
-    const double* Cs = a.C + fd.Coff;
+    // ---- update: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U ----
+    double* Cs = a.C + fd.Coff;
     const int* rowg = a.rowg + fd.rows_off;
-    const int* rel = a.relidx + fd.rows_off;
-    const PushTarget pt = push_target(a, fd);
     const int lr = lane >> 2, lk = lane & 3;
     const double* L21 = F + w;                 // L21(i,k) = L21[k*m + i]
+    const int nch = fd.child_end - fd.child_begin;
     for (int bi = 0; bi * 32 < u; ++bi) {
         for (int bj = 0; bj <= bi; ++bj) {
             double acc[4][4][2];
@@ -304,11 +318,41 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
 #pragma unroll
                     for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
             }
+            // acc <- -U + children's pass-through entries (ancestor columns only)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) { acc[x][y][0] = -acc[x][y][0]; acc[x][y][1] = -acc[x][y][1]; }
+            if (bj * 32 < na) {
+                for (int c = 0; c < nch; ++c) {
+                    const ChildRef ch = child_ref(a, fd.child_begin + c);
+                    int ci[4], cj[4][2];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = bi * 32 + x * 8 + lr;
+                        ci[x] = (i < u) ? ch.inv[w + i] : -1;
+                    }
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = bj * 32 + y * 8 + lk * 2 + e;
+                            cj[y][e] = (j < na) ? ch.inv[w + j] : -1;
+                        }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+                                if (ci[x] >= 0 && cj[y][e] >= 0 && ci[x] >= cj[y][e])
+                                    acc[x][y][e] += ch.C[(size_t)cj[y][e] * ch.u + ci[x]];
+                }
+            }
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const int i = bi * 32 + x * 8 + lr;
                 if (i >= u) continue;
-                const int ri = rel[i];
                 const int64_t scrow = (i >= na && a.SC) ? (int64_t)rowg[i] * a.ldsc : 0;
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
@@ -317,8 +361,8 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
                         const int j = bj * 32 + y * 8 + lk * 2 + e;
                         if (j > i) continue;
                         const double v = acc[x][y][e];
-                        if (j < na) push_entry(pt, ri, rel[j], Cs[(size_t)j * u + i] - v);
-                        else if (a.SC) atomicAdd(&a.SC[scrow + rowg[j]], -v);
+                        if (j < na) Cs[(size_t)j * u + i] = v;
+                        else if (a.SC) atomicAdd(&a.SC[scrow + rowg[j]], v);
                     }
             }
         }
@@ -395,16 +439,41 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
 #pragma unroll
             for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
     }
-    const double* Cs = a.C + fd.Coff;
+    double* Cs = a.C + fd.Coff;
     const int* rowg = a.rowg + fd.rows_off;
-    const int* rel = a.relidx + fd.rows_off;
-    const PushTarget pt = push_target(a, fd);
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) { acc[x][y][0] = -acc[x][y][0]; acc[x][y][1] = -acc[x][y][1]; }
+    // children's pass-through entries of this tile (ancestor columns only): inverse indices staged in shared memory
+    if (j0 < na) {
+        int* s_ci = reinterpret_cast<int*>(As);        // operands are dead: reuse the staging buffers
+        int* s_cj = s_ci + TILE;
+        for (int c = fd.child_begin; c < fd.child_end; ++c) {
+            const ChildRef ch = child_ref(a, c);
+            __syncthreads();
+            if (tid < TILE) s_ci[tid] = (i0 + tid < u) ? ch.inv[w + i0 + tid] : -1;
+            else s_cj[tid - TILE] = (j0 + tid - TILE < na) ? ch.inv[w + j0 + tid - TILE] : -1;
+            __syncthreads();
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int ci = s_ci[wr + x * 8 + lr];
+                if (ci < 0) continue;
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cj = s_cj[wc + y * 8 + lk * 2 + e];
+                        if (cj >= 0 && ci >= cj) acc[x][y][e] += ch.C[(size_t)cj * ch.u + ci];
+                    }
+            }
+        }
+    }
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
         const int gi = i0 + wr + x * 8 + lr;
         if (gi >= u) continue;
         const int64_t scrow = (gi >= na && a.SC) ? (int64_t)rowg[gi] * a.ldsc : 0;
-        const int ri = rel[gi];
 #pragma unroll
         for (int y = 0; y < 4; ++y)
 #pragma unroll
@@ -412,8 +481,8 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
                 const int gj = j0 + wc + y * 8 + lk * 2 + e;
                 if (gj > gi) continue;
                 const double v = acc[x][y][e];
-                if (gj < na) push_entry(pt, ri, rel[gj], Cs[(size_t)gj * u + gi] - v);
-                else if (a.SC) atomicAdd(&a.SC[scrow + rowg[gj]], -v);
+                if (gj < na) Cs[(size_t)gj * u + gi] = v;
+                else if (a.SC) atomicAdd(&a.SC[scrow + rowg[gj]], v);
             }
     }
 }
@@ -1213,212 +1282,3 @@ double launch_dmma_peak(double* out, int iters, int ctas, cudaStream_t s) {
 }
 }  // namespace pipsgpu
 
-// =====================================================================================================
-// Persistent, dependency-driven supernodal solve: ONE launch applies K_i^-1 for every scenario block of the GPU.
-//
-// The level-scheduled kernels above pay one launch per (tree level, width class) and direction: ~120 dependent
-// launches of a few microseconds for a tree that is 19 levels deep. Here warps pull fronts from a global ticket
-// counter in level order (deepest level first for the forward sweep, the reverse for the backward sweep) and wait on
-// per-front completion flags instead of kernel boundaries. Because a front's prerequisites always hold EARLIER
-// tickets, every flag a warp spins on belongs to a warp that is already resident and running: no deadlock, no
-// cooperative launch needed.
-//   tickets [0, n)   forward : wait children (flag >= epoch+1) ; y = L11^-1 (b + child updates) ; upd = -L21 y ;
-//                              x = D^-1 y (block diagonal folded in) ; flag = epoch+1
-//   tickets [n, 2n)  backward: wait parent (flag >= epoch+2) ; x = L11^-T (x - L21^T x_anc) ; out ; flag = epoch+2
-// The permutation gather of the right-hand side and the scatter of the solution are fused in (in[gidx], out[gidx]).
-// Data written by other SMs (x, upd) is read with ld.global.cg; producers fence before publishing their flag.
-// =====================================================================================================
-namespace pipsgpu {
-
-__device__ __forceinline__ int ld_flag(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-template <int WP>
-__device__ __forceinline__ void psolve_fwd(const PSolveArgs& a, const FrontDesc& fd, int lane, double* ybuf) {
-    const unsigned full = 0xffffffffu;
-    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
-    const double* __restrict__ F = a.L + fd.Loff;
-    double* us = a.upd + fd.upd_off;
-    // L11 row of this lane: issue the loads before waiting on anything
-    double lrow[WP];
-#pragma unroll
-    for (int k = 0; k < WP; ++k) lrow[k] = (k < w && lane > k && lane < w) ? F[(size_t)k * m + lane] : 0.0;
-    const int p = fd.col0 + lane;
-    double y = (lane < w) ? a.in[a.gidx[p]] : 0.0;
-    // ---- children: wait, then pull their update vectors ----
-    for (int c = fd.child_begin + lane; c < fd.child_end; c += 32) {
-        const int* fl = a.flags + a.child_list[c];
-        while (ld_flag(fl) < a.epoch + 1) __nanosleep(40);
-    }
-    __syncwarp();
-    ybuf[lane] = 0.0;                       // contributions to the pivot-block rows, indexed by local row
-    for (int i = lane; i < na; i += 32) us[i] = 0.0;
-    __syncwarp();
-    for (int c = fd.child_begin; c < fd.child_end; ++c) {
-        const FrontDesc& cd = a.fronts[a.child_list[c]];
-        const int cna = cd.na;
-        const int* rel = a.relidx + cd.rows_off;
-        const double* uc = a.upd + cd.upd_off;
-        for (int i = lane; i < cna; i += 32) {      // the rows of one child map to distinct parent rows
-            const int li = rel[i];
-            const double v = __ldcg(uc + i);
-            if (li < w) ybuf[li] += v;
-            else us[li - w] += v;
-        }
-        __syncwarp();
-    }
-    y += ybuf[lane];
-    // ---- y = L11^-1 y ----
-#pragma unroll
-    for (int k = 0; k < WP; ++k) {
-        const double yk = __shfl_sync(full, y, k);
-        y = fma(-lrow[k], yk, y);
-    }
-    // ---- upd = -(L21 y) (on top of the children's contributions) ----
-    for (int i0 = 0; i0 < na; i0 += 32) {
-        const int i = i0 + lane;
-        double v[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < WP; ++k) acc = fma(v[k], __shfl_sync(full, y, k), acc);
-        if (i < na) us[i] -= acc;
-    }
-    // ---- z = D^-1 y (1x1 and 2x2 pivots; pairs never straddle a front) ----
-    {
-        const int t = (lane < w) ? a.ptype[p] : 0;
-        const double dd = (lane < w) ? a.Did[p] : 0.0;
-        const double de = (lane < w) ? a.Die[p] : 0.0;
-        const double ynext = __shfl_down_sync(full, y, 1);
-        const double yprev = __shfl_up_sync(full, y, 1);
-        const double deprev = __shfl_up_sync(full, de, 1);
-        double z = dd * y;
-        if (t == 1) z += de * ynext;
-        else if (t == 2) z += deprev * yprev;
-        if (lane < w) a.x[p] = z;
-    }
-}
-
-template <int WP>
-__device__ __forceinline__ void psolve_bwd(const PSolveArgs& a, const FrontDesc& fd, int self, int lane) {
-    const unsigned full = 0xffffffffu;
-    const int w = fd.w, na = fd.na, m = w + fd.na + fd.nb;
-    const double* __restrict__ F = a.L + fd.Loff;
-    const int* __restrict__ rowg = a.rowg + fd.rows_off;
-    double lcol[WP];
-#pragma unroll
-    for (int k = 0; k < WP; ++k) lcol[k] = (lane < k && k < w) ? F[(size_t)lane * m + k] : 0.0;
-    // a non-root front waits for its parent's backward step (which transitively implies that the forward sweep of the
-    // whole tree - this front included - is complete); a root waits for its own forward step
-    if (lane == 0) {
-        const int* fl = (fd.parent >= 0) ? a.flags + fd.parent : a.flags + self;
-        const int target = a.epoch + ((fd.parent >= 0) ? 2 : 1);
-        while (ld_flag(fl) < target) __nanosleep(40);
-    }
-    __syncwarp();
-    const int p = fd.col0 + lane;
-    double t = (lane < w) ? __ldcg(a.x + p) : 0.0;
-    double sacc[WP];
-#pragma unroll
-    for (int k = 0; k < WP; ++k) sacc[k] = 0.0;
-    for (int i0 = 0; i0 < na; i0 += 32) {
-        const int i = i0 + lane;
-        const double xi = (i < na) ? __ldcg(a.x + rowg[i]) : 0.0;
-        double v[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) v[k] = (k < w && i < na) ? F[(size_t)k * m + w + i] : 0.0;
-#pragma unroll
-        for (int k = 0; k < WP; ++k) sacc[k] = fma(v[k], xi, sacc[k]);
-    }
-#pragma unroll
-    for (int o = 16; o >= WP; o >>= 1) {
-#pragma unroll
-        for (int j = 0; j < WP; ++j) sacc[j] += __shfl_xor_sync(full, sacc[j], o);
-    }
-#pragma unroll
-    for (int o = (WP < 32 ? WP / 2 : 16); o > 0; o >>= 1) {
-        const bool hi = (lane & o) != 0;
-#pragma unroll
-        for (int j = 0; j < o; ++j) {
-            const double send = hi ? sacc[j] : sacc[j + o];
-            const double keep = hi ? sacc[j + o] : sacc[j];
-            sacc[j] = keep + __shfl_xor_sync(full, send, o);
-        }
-    }
-    t -= sacc[0];
-#pragma unroll
-    for (int k = WP - 1; k >= 0; --k) {
-        const double xk = __shfl_sync(full, t, k);
-        t = fma(-lcol[k], xk, t);
-    }
-    if (lane < w) {
-        a.x[p] = t;
-        const int g = a.gidx[p];
-        a.out[g] = (a.out_mode == 0) ? t : a.out[g] - t;   // 0: out = K^-1 in ; 1: out -= K^-1 in
-    }
-}
-
-constexpr int PS_WARPS = 4;
-__global__ void __launch_bounds__(PS_WARPS * 32, 3) psolve_kernel(PSolveArgs a) {
-    __shared__ double s_ybuf[PS_WARPS][32];
-    double* ybuf = s_ybuf[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned full = 0xffffffffu;
-    const int nb = a.nbatches;
-    for (;;) {
-        // one ticket = one batch of consecutive fronts of the level order (a single hot counter would otherwise
-        // serialise ~2 x nfronts atomics in L2)
-        int t = 0;
-        if (lane == 0) t = atomicAdd(a.counters, 1);
-        t = __shfl_sync(full, t, 0);
-        if (t >= 2 * nb) break;
-        const bool fwd = t < nb;
-        const int b = fwd ? t : 2 * nb - 1 - t;
-        const int lo = a.batch_ptr[b], hi = a.batch_ptr[b + 1];
-        for (int q = 0; q < hi - lo; ++q) {
-            const int f = a.order[fwd ? lo + q : hi - 1 - q];
-            const FrontDesc fd = a.fronts[f];
-            const int cls = width_class(fd.w);
-            if (fwd) {
-                if (cls == 0) psolve_fwd<8>(a, fd, lane, ybuf);
-                else if (cls == 1) psolve_fwd<16>(a, fd, lane, ybuf);
-                else psolve_fwd<32>(a, fd, lane, ybuf);
-            } else {
-                if (cls == 0) psolve_bwd<8>(a, fd, f, lane);
-                else if (cls == 1) psolve_bwd<16>(a, fd, f, lane);
-                else psolve_bwd<32>(a, fd, f, lane);
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_flag(a.flags + f, a.epoch + (fwd ? 1 : 2));
-        }
-    }
-    // the last warp to leave re-arms the ticket counter for the next launch
-    if (lane == 0) {
-        const int total = gridDim.x * PS_WARPS;
-        const int done = atomicAdd(a.counters + 1, 1);
-        if (done == total - 1) {
-            a.counters[1] = 0;
-            __threadfence();
-            a.counters[0] = 0;
-        }
-    }
-}
-
-void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s) {
-    if (a.nfronts <= 0) return;
-    int ctas = sm_count * 3;
-    const int need = (2 * a.nbatches + PS_WARPS - 1) / PS_WARPS;
-    if (ctas > need) ctas = need;
-    psolve_kernel<<<ctas, PS_WARPS * 32, 0, s>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-}
-
-}  // namespace pipsgpu

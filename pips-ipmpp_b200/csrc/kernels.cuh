@@ -21,6 +21,7 @@ struct FrontDesc {
     int64_t Woff;      // per-level scratch: W21 = L21*D, (na+nb) x wp(w), k-major: W21(j,k) = W[k*(na+nb) + j]
     int64_t XYoff;     // per-level scratch: X = L11^-1, wp x wp row-major
     int64_t upd_off;   // solve-phase update vector (na entries)
+    int64_t inv_off;   // into invmap: for every local row of the PARENT front the row of this front's C or -1
     int w, na, nb;
     int col0;          // global position of the first pivot column
     int child_begin, child_end;   // into child_list (global front ids)
@@ -45,6 +46,7 @@ struct FactorArgs {
     const int* child_list;
     const int* rowg;             // per front row: global position (non-border) or Schur-complement index (border)
     const int* relidx;           // per front row: local row index in the parent front
+    const int* invmap;           // per front: inverse of relidx over the parent's local rows (see FrontDesc::inv_off)
     const int8_t* ptype;
     const int8_t* sgn;
     const LeafDev* leaves;
@@ -74,30 +76,40 @@ struct SolveArgs {
     int64_t x_stride, upd_stride;
 };
 
-// persistent dependency-driven solve (one launch = K^-1 for every block): see psolve_kernel
-struct PSolveArgs {
-    const FrontDesc* fronts;
-    const int* order;            // all fronts, deepest level first (= level_fronts)
-    const int* batch_ptr;        // nbatches+1 offsets into order: one ticket = one batch of consecutive fronts
-    int nbatches;
-    const int* child_list;
+// ---- streaming persistent solve (psolve.cu): one launch = K^-1 for every block of the GPU ----
+constexpr int PS_WARPS = 8;      // warps per CTA, one CTA per SM
+constexpr int PS_BUF = 1536;     // doubles per staging buffer (12 KB), two buffers per warp
+constexpr int PS_XA = 128;       // max rows per chunk
+struct SolveFront {              // one per front, in sweep order (deepest tree level first)
+    int64_t blob;                // offset (doubles, even) of [L11 ; L21] row-major in the solve pool
+    int col0;                    // global position of the first pivot column
+    int rows_off;                // into rowg (first na entries = ancestor rows)
+    int w, na, ldr;              // ldr = w | 1 (odd leading dimension)
+    int parent;                  // sweep-order index of the parent front or -1
+    int nchild;
+    int front;                   // global front id (FrontDesc index)
+};
+struct PStreamArgs {
+    const SolveFront* sf;
+    int nfronts;
+    const double* SL;            // solve pool
     const int* rowg;
-    const int* relidx;
     const int* gidx;             // per position: index of that row in the caller's (unpermuted, concatenated) vectors
     const int8_t* ptype;
-    const double* L;
     const double* Did; const double* Die;
     const double* in;            // right-hand side, original order
     double* out;                 // solution, original order
     double* x;                   // work: permuted order
-    double* upd;                 // work: per-front update vectors
-    int* flags;                  // per front: epoch+1 after the forward step, epoch+2 after the backward step
-    int* counters;               // [0] ticket, [1] exit count (self re-arming)
-    int nfronts;
+    double* acc;                 // per position: updates pushed by descendants (zero between solves)
+    int* fcnt;                   // per front: completed children, cumulative over solves
+    int* bflag;                  // per front: 2*epoch+1 = forward sweep of the tree done (roots), 2*epoch+2 = backward step done
     int epoch;
     int out_mode;                // 0: out = K^-1 in, 1: out -= K^-1 in
 };
-void launch_psolve(const PSolveArgs& a, int sm_count, cudaStream_t s);
+void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s);
+void launch_pack_solve(const SolveFront* sf, const int* slab_front, const int* slab_row0, int nslabs, const FrontDesc* fronts,
+                       const double* L, double* SL, cudaStream_t s);
+void count_launch();
 
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);

@@ -158,14 +158,18 @@ struct pipsgpu_ctx {
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
     std::vector<int> fl_ptr;        // nlevels*2+1 into fl_fronts; group = level_order*2 + (0 small | 1 big)
     DevBuf<int> fl_fronts;
-    DevBuf<int> rowg, relidx, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
+    DevBuf<int> rowg, relidx, invmap, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
     DevBuf<int8_t> ptype, sgn;
     DevBuf<FrontDesc> fronts;
     DevBuf<LeafDev> leafdev;
     DevBuf<int64_t> kmap, bmap, diagpos;
-    DevBuf<int> ps_flags, ps_counters, ps_batch_ptr;   // persistent solve: completion flags, ticket / exit counters, ticket batches
-    int ps_nbatches = 0;
-    int ps_epoch = 0;
+    // streaming persistent solve (psolve.cu): solve pool + per-front descriptors in sweep order
+    DevBuf<SolveFront> sfront;
+    DevBuf<double> SL, acc;
+    DevBuf<int> fcnt, bflag, slab_front, slab_row0;
+    int nslabs = 0;
+    int64_t SLtot = 0;
+    int ps_epoch = 0, ps_epoch_max = 1 << 16;
     int sm_count = 148;
     double* h_dvals = nullptr;      // pinned staging of all leaf diagonals (npos)
     bool own_stream = true;
@@ -173,7 +177,7 @@ struct pipsgpu_ctx {
     FactorArgs factor_args(pipsgpu_sc* sc) {
         FactorArgs a;
         a.fronts = fronts.p; a.level_fronts = level_fronts.p; a.fl_fronts = fl_fronts.p; a.child_list = child_list.p;
-        a.rowg = rowg.p; a.relidx = relidx.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p;
+        a.rowg = rowg.p; a.relidx = relidx.p; a.invmap = invmap.p; a.ptype = ptype.p; a.sgn = sgn.p; a.leaves = leafdev.p; a.L = L.p; a.C = C.p;
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
@@ -182,18 +186,21 @@ struct pipsgpu_ctx {
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
     void psolve(const double* in, double* out, int out_mode) {
         if (nfronts <= 0) return;
-        if (ps_epoch > (1 << 30)) {   // flags are monotone in the epoch: re-arm long before the counter wraps
-            cudaMemsetAsync(ps_flags.p, 0, sizeof(int) * (size_t)nfronts, stream);
+        if (ps_epoch >= ps_epoch_max) {   // counters / flags are monotone in the epoch: re-arm long before they wrap
+            cudaMemsetAsync(fcnt.p, 0, sizeof(int) * (size_t)nfronts, stream);
+            cudaMemsetAsync(bflag.p, 0, sizeof(int) * (size_t)nfronts, stream);
             ps_epoch = 0;
         }
-        PSolveArgs a;
-        a.fronts = fronts.p; a.order = level_fronts.p; a.child_list = child_list.p; a.rowg = rowg.p; a.relidx = relidx.p;
-        a.gidx = gidx.p; a.ptype = ptype.p; a.L = L.p; a.Did = Did.p; a.Die = Die.p; a.in = in; a.out = out; a.x = x.p;
-        a.upd = upd.p; a.flags = ps_flags.p; a.counters = ps_counters.p; a.nfronts = (int)nfronts; a.epoch = ps_epoch;
-        a.batch_ptr = ps_batch_ptr.p; a.nbatches = ps_nbatches;
-        a.out_mode = out_mode;
-        launch_psolve(a, sm_count, stream);
-        ps_epoch += 2;
+        PStreamArgs a;
+        a.sf = sfront.p; a.nfronts = (int)nfronts; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p; a.ptype = ptype.p;
+        a.Did = Did.p; a.Die = Die.p; a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.fcnt = fcnt.p; a.bflag = bflag.p;
+        a.epoch = ps_epoch; a.out_mode = out_mode;
+        launch_psolve_stream(a, sm_count, stream);
+        ps_epoch += 1;
+    }
+    // factor panels -> solve pool (after every numeric factorisation)
+    void pack_solve() {
+        launch_pack_solve(sfront.p, slab_front.p, slab_row0.p, nslabs, fronts.p, L.p, SL.p, stream);
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
         SolveArgs a;
@@ -216,7 +223,8 @@ struct pipsgpu_kkt {
     double last_regDy = 0.0;
     int64_t sum_nx = 0, sum_nz = 0, sum_n = 0;
     double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[16] = {};
+    double ktimes[4] = {0, 0, 0, 0};
     bool ev_init = false;
 };
 
@@ -694,6 +702,22 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         std::vector<int>().swap(Sm.rowidx); std::vector<int>().swap(Sm.relidx);
         std::vector<int64_t>().swap(Sm.kmap); std::vector<int64_t>().swap(Sm.bmap);
     }
+    // inverse relative indices: for every front with a parent, parent local row -> row of this front's C (or -1)
+    std::vector<int> invmap;
+    {
+        int64_t tot = 0;
+        for (int64_t f = 0; f < nfr; ++f) {
+            FrontDesc& fd = fronts[(size_t)f];
+            fd.inv_off = tot;
+            if (fd.parent >= 0) { const FrontDesc& pd = fronts[(size_t)fd.parent]; tot += pd.w + pd.na + pd.nb; }
+        }
+        invmap.assign((size_t)tot, -1);
+        for (int64_t f = 0; f < nfr; ++f) {
+            const FrontDesc& fd = fronts[(size_t)f];
+            if (fd.parent < 0) continue;
+            for (int t = 0; t < fd.na + fd.nb; ++t) invmap[(size_t)fd.inv_off + relidx[(size_t)fd.rows_off + t]] = t;
+        }
+    }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
     ctx->XYtot = 0;
@@ -754,7 +778,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
 
     cudaStream_t s = ctx->stream;
-    ctx->fronts.upload(fronts, s); ctx->rowg.upload(rowg, s); ctx->relidx.upload(relidx, s);
+    ctx->fronts.upload(fronts, s); ctx->rowg.upload(rowg, s); ctx->relidx.upload(relidx, s); ctx->invmap.upload(invmap, s);
     ctx->child_list.upload(child_list, s); ctx->level_fronts.upload(level_fronts, s); ctx->gidx.upload(gidx, s);
     ctx->ptype.upload(ptype, s); ctx->sgn.upload(sgn, s); ctx->kmap.upload(kmap, s); ctx->bmap.upload(bmap, s);
     ctx->diagpos.upload(diagpos, s); ctx->Kval.upload(kval, s); ctx->Bval.upload(bval, s);
@@ -768,22 +792,38 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->x.alloc((size_t)npos + 1); ctx->upd.alloc((size_t)updtot + 1); ctx->dvals.alloc((size_t)npos + 1);
     ctx->work.alloc((size_t)npos + 1);
     ctx->stats.alloc((size_t)4 * std::max(nl, 1));
-    ctx->ps_flags.alloc((size_t)nfr + 1); ctx->ps_counters.alloc(2);
     {
-        // ticket batches of the persistent solve: up to 8 consecutive fronts of one level per ticket, fewer where a
-        // level is too small to keep ~4000 warps busy
-        std::vector<int> bp;
-        for (int lv = 0; lv < nlev; ++lv) {
-            const int b = ctx->level_ptr[lv * NCLS], e = ctx->level_ptr[(lv + 1) * NCLS];
-            const int bs = std::max(1, std::min(8, (e - b + 4095) / 4096));
-            for (int i = b; i < e; i += bs) bp.push_back(i);
+        // sweep order of the streaming solve = level_fronts (deepest level first); blobs laid out in that order
+        std::vector<int> tinv((size_t)nfr, -1);
+        for (int64_t t = 0; t < nfr; ++t) tinv[(size_t)level_fronts[(size_t)t]] = (int)t;
+        std::vector<SolveFront> sf((size_t)nfr);
+        std::vector<int> slab_front, slab_row0;
+        int64_t off = 0;
+        int maxchild = 1;
+        for (int64_t t = 0; t < nfr; ++t) {
+            const FrontDesc& fd = fronts[(size_t)level_fronts[(size_t)t]];
+            SolveFront& f = sf[(size_t)t];
+            f.blob = off; f.col0 = fd.col0; f.rows_off = (int)fd.rows_off; f.w = fd.w; f.na = fd.na; f.ldr = fd.w | 1;
+            f.parent = fd.parent >= 0 ? tinv[(size_t)fd.parent] : -1;
+            f.nchild = fd.child_end - fd.child_begin;
+            maxchild = std::max(maxchild, f.nchild);
+            f.front = level_fronts[(size_t)t];
+            if (fd.rows_off > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "row index pool too large for one context");
+            const int rows = fd.w + fd.na;
+            off += ((int64_t)rows * f.ldr + 1) & ~int64_t(1);
+            for (int r0 = 0; r0 < rows; r0 += 32) { slab_front.push_back((int)t); slab_row0.push_back(r0); }
         }
-        bp.push_back((int)nfr);
-        ctx->ps_nbatches = (int)bp.size() - 1;
-        ctx->ps_batch_ptr.upload(bp, s);
+        ctx->SLtot = off;
+        ctx->ps_epoch_max = (1 << 30) / maxchild - 2;   // the child counters are cumulative: nchild * epoch must not wrap
+        ctx->nslabs = (int)slab_front.size();
+        ctx->sfront.upload(sf, s); ctx->slab_front.upload(slab_front, s); ctx->slab_row0.upload(slab_row0, s);
+        ctx->SL.alloc((size_t)off + 2);
+        ctx->acc.alloc((size_t)npos + 1);
+        ctx->fcnt.alloc((size_t)nfr + 1); ctx->bflag.alloc((size_t)nfr + 1);
+        CUDA_CHECK(cudaMemsetAsync(ctx->acc.p, 0, sizeof(double) * ((size_t)npos + 1), s));
+        CUDA_CHECK(cudaMemsetAsync(ctx->fcnt.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
+        CUDA_CHECK(cudaMemsetAsync(ctx->bflag.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
     }
-    CUDA_CHECK(cudaMemsetAsync(ctx->ps_flags.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
-    CUDA_CHECK(cudaMemsetAsync(ctx->ps_counters.p, 0, sizeof(int) * 2, s));
     CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMemsetAsync(ctx->De.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMallocHost(&ctx->h_dvals, sizeof(double) * ((size_t)npos + 1)));
@@ -840,13 +880,11 @@ static void factor_prepare(pipsgpu_ctx* ctx, pipsgpu_leaf* only) {
     cudaStream_t s = ctx->stream;
     if (only) {
         launch_vec_zero(ctx->L.p + only->Lbase, only->Lsize, s);
-        launch_vec_zero(ctx->C.p + only->Cbase, only->Csize, s);
         launch_scatter_values(ctx->kmap.p + only->kval_off, ctx->Kval.p + only->kval_off, (int64_t)only->val.size(), ctx->L.p, s);
         launch_scatter_values(ctx->bmap.p + only->bval_off, ctx->Bval.p + only->bval_off, (int64_t)only->bval.size(), ctx->L.p, s);
         CUDA_CHECK(cudaMemsetAsync(ctx->stats.p + 4 * only->index, 0, sizeof(int) * 4, s));
     } else {
         launch_vec_zero(ctx->L.p, ctx->Ltot, s);
-        launch_vec_zero(ctx->C.p, ctx->Ctot, s);
         launch_scatter_values(ctx->kmap.p, ctx->Kval.p, ctx->nnzK, ctx->L.p, s);
         launch_scatter_values(ctx->bmap.p, ctx->Bval.p, ctx->nnzB, ctx->L.p, s);
         CUDA_CHECK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(int) * 4 * ctx->leaves.size(), s));
@@ -861,6 +899,7 @@ int pipsgpu_leaf_factorize(pipsgpu_leaf* lf, int inertia[3]) {
     require_device(ctx);
     factor_prepare(ctx, lf);
     run_factor_levels(ctx, nullptr, lf);
+    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     lf->factorized = true;
     if (inertia) { inertia[0] = lf->inertia[0]; inertia[1] = lf->inertia[1]; inertia[2] = lf->inertia[2]; }
@@ -873,6 +912,7 @@ int pipsgpu_ctx_factorize_leaves(pipsgpu_ctx* ctx, pipsgpu_sc* sc) {
     if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_ctx_factorize_leaves: context not committed");
     factor_prepare(ctx, nullptr);
     run_factor_levels(ctx, sc, nullptr);
+    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     for (auto* lf : ctx->leaves) lf->factorized = true;
     PIPSGPU_CATCH
@@ -886,6 +926,7 @@ int pipsgpu_leaf_add_schur(pipsgpu_leaf* lf, pipsgpu_sc* sc) {
     // the Schur term is a by-product of the elimination: redo this leaf's numeric phase with the SC attached
     factor_prepare(ctx, lf);
     run_factor_levels(ctx, sc, lf);
+    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     lf->factorized = true;
     PIPSGPU_CATCH
@@ -1186,6 +1227,9 @@ static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[
     factor_prepare(ctx, nullptr);
     CUDA_CHECK(cudaEventRecord(k->ev[1], s));
     run_factor_levels(ctx, sc, nullptr);
+    CUDA_CHECK(cudaEventRecord(k->ev[12], s));
+    ctx->pack_solve();
+    CUDA_CHECK(cudaEventRecord(k->ev[13], s));
     CUDA_CHECK(cudaEventRecord(k->ev[2], s));
     // ---- reduceKKT ----
     sc_allreduce_impl(sc);
@@ -1210,6 +1254,8 @@ static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[
         CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[i], k->ev[i + 1]));
         k->times[i] = ms;
     }
+    CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[12], k->ev[13]));
+    k->ktimes[1] = ms;
 }
 
 int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,
@@ -1268,7 +1314,9 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
     if (ctx->rank > 0) launch_vec_zero(k->b0.p, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
     else launch_vec_copy(k->b0.p, k->b0_in.p, nb0, s);
     // ---- Lsolve: z_i = K_i^-1 b_i ; b0 -= Bord_i^T z_i ; allreduce ----
+    CUDA_CHECK(cudaEventRecord(k->ev[10], s));
     ctx->psolve(k->bl_in.p, k->bl.p, 0);
+    CUDA_CHECK(cudaEventRecord(k->ev[11], s));
     launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, k->bl.p, k->b0.p, s);
     if (ctx->comm && ctx->nranks > 1) {
         NcclApi& api = NcclApi::get();
@@ -1286,7 +1334,9 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
         launch_vec_div(k->t3.p, k->zdiag0.p, mz0, s);
         launch_csr_tmult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, k->t3.p, r, s);
     }
+    CUDA_CHECK(cudaEventRecord(k->ev[14], s));
     launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, r, 1, sc->n, sc->swork.p, s);
+    CUDA_CHECK(cudaEventRecord(k->ev[15], s));
     launch_vec_copy(b, r, n0 + my0, s);
     if (mz0 > 0) {
         launch_csr_mult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, r, b + n0 + my0, s);
@@ -1308,6 +1358,10 @@ static void kkt_solve_times(pipsgpu_kkt* k) {
         CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[6 + i], k->ev[7 + i]));
         k->times[5 + i] = ms;
     }
+    CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[10], k->ev[11]));
+    k->ktimes[0] = ms;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[14], k->ev[15]));
+    k->ktimes[2] = ms;
 }
 
 int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
@@ -1359,6 +1413,26 @@ int pipsgpu_kkt_stage_times(pipsgpu_kkt* k, double out[8]) {
         kkt_solve_times(k);
     }
     for (int i = 0; i < 8; ++i) out[i] = k->times[i];
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_kkt_kernel_times(pipsgpu_kkt* k, double out[4]) {
+    PIPSGPU_TRY
+    if (!k || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_kernel_times: null");
+    if (k->have_rhs) {
+        require_device(k->ctx);
+        CUDA_CHECK(cudaStreamSynchronize(k->ctx->stream));
+        kkt_solve_times(k);
+    }
+    for (int i = 0; i < 4; ++i) out[i] = k->ktimes[i];
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_pool_sizes(pipsgpu_ctx* ctx, int64_t out[8]) {
+    PIPSGPU_TRY
+    if (!ctx || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_ctx_pool_sizes: null");
+    out[0] = ctx->Ltot; out[1] = ctx->Ctot; out[2] = ctx->SLtot; out[3] = ctx->nfronts; out[4] = ctx->npos;
+    out[5] = ctx->nlevels; out[6] = ctx->nnzK; out[7] = ctx->nnzB;
     PIPSGPU_CATCH
 }
 

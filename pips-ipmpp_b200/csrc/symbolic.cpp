@@ -85,7 +85,9 @@ void match_rows(int n, int nx, int ny, const std::vector<int>& xadj, const std::
 void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jcol, const double* val, int nB,
                   int64_t nnzB, const int* brow, const int* bcol, const SymbolicOptions& opt_in, LeafSymbolic& S) {
     SymbolicOptions opt = opt_in;
-    if (const char* e = std::getenv("PIPSGPU_SUBTREE_WIDTH")) opt.subtree_width = std::atoi(e);   // tuning knob
+    if (const char* e = std::getenv("PIPSGPU_SUBTREE_WIDTH")) opt.subtree_width = std::atoi(e);   // tuning knobs
+    if (const char* e = std::getenv("PIPSGPU_RELAX_SMALL")) opt.relax_small = std::atof(e);
+    if (const char* e = std::getenv("PIPSGPU_RELAX_MID")) opt.relax_mid = std::atof(e);
     if (nx + ny + nz != n) throw std::runtime_error("analyze_leaf: nx+ny+nz != n");
     S = LeafSymbolic();
     S.n = n; S.nx = nx; S.ny = ny; S.nz = nz; S.nB = nB;
@@ -316,8 +318,8 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
         const double tot = 0.5 * nscol * (nscol + 1.0) + (double)nscol * up;
         const double zf = z / tot;
         if (nscol <= 4) return true;
-        if (nscol <= 16) return zf < 0.8;
-        if (nscol <= 48) return zf < 0.1;
+        if (nscol <= 16) return zf < opt.relax_small;
+        if (nscol <= 48) return zf < opt.relax_mid;
         return zf < 0.05;
     };
     for (int j = 0; j < n; ++j) {

@@ -52,6 +52,8 @@ struct SymbolicOptions {
     int max_width = 32;      // supernodes wider than this are split into chains
     int use_metis = 1;
     int relax = 1;
+    double relax_small = 0.8;  // admissible fraction of explicit zeros when merging into a supernode of <= 16 columns
+    double relax_mid = 0.1;    // ... of <= 48 columns
     int subtree_width = 32;  // bottom subtrees with at most this many columns are merged into one front (0 = off)
 };
 

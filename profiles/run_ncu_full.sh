@@ -1,8 +1,14 @@
 #!/bin/bash
-# ncu --set full captures of the top kernels of one bench step (C2, 1 GPU). Outputs under gpurun_out/.
+# ncu --set full captures of selected launches of one bench step (C2, 1 GPU); the reports are exported to CSV on the box
+# (raw metrics + source-level stall samples) and the .ncu-rep files are dropped when they would exceed the copy-back limit.
+# usage: run_ncu_full.sh <tag> <kernel-regex> <skip> <count>
 mkdir -p gpurun_out
+TAG=$1; RX=$2; SKIP=$3; CNT=$4
 B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:psolve -s 6 -c 2 -f -o gpurun_out/prof_psolve $B > gpurun_out/ncu_psolve.log 2>&1; echo "psolve rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"front_update_tiles|small_fronts|big_panel|pivot_kernel" -s 82 -c 82 -f -o gpurun_out/prof_factor $B > gpurun_out/ncu_factor.log 2>&1; echo "factor rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"dense_solve" -s 4 -c 1 -f -o gpurun_out/prof_dsolve $B > gpurun_out/ncu_dsolve.log 2>&1; echo "dsolve rc=$?"
-ls -la gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RX" -s $SKIP -c $CNT -f -o gpurun_out/prof_$TAG $B > gpurun_out/ncu_$TAG.log 2>&1; echo "$TAG rc=$?"
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_source.csv 2>/dev/null
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page details > gpurun_out/prof_${TAG}_details.txt 2>/dev/null
+SZ=$(stat -c %s gpurun_out/prof_$TAG.ncu-rep 2>/dev/null || echo 0)
+if [ "$SZ" -gt 12000000 ]; then rm -f gpurun_out/prof_$TAG.ncu-rep; fi
+du -sh gpurun_out
