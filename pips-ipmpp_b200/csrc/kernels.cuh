@@ -78,37 +78,51 @@ struct SolveArgs {
 
 // ---- streaming persistent solve (psolve.cu): one launch = K^-1 for every block of the GPU ----
 constexpr int PS_WARPS = 8;      // warps per CTA, one CTA per SM
-constexpr int PS_BUF = 1536;     // doubles per staging buffer (12 KB), two buffers per warp
+constexpr int PS_BUF = 1184;     // doubles per staging buffer (9.25 KB, holds 32 rows of a 32-wide front), two per warp
+constexpr int PS_HDR = 96;       // chunk header: three 32-wide rows of D^-1 coefficients
 constexpr int PS_XA = 128;       // max rows per chunk
-struct SolveFront {              // one per front, in sweep order (deepest tree level first)
-    int64_t blob;                // offset (doubles, even) of [L11 ; L21] row-major in the solve pool
+constexpr int PS_SMAX = 512;     // max columns of a subtree unit (its right-hand-side slice lives in shared memory)
+constexpr int PS_NOUT = 384;     // rows above a unit that are accumulated in shared memory (the rest: global atomics)
+constexpr int PS_WARP_DOUBLES = 2 * PS_BUF + PS_SMAX + PS_NOUT;
+struct SolveFront {              // one per front, fronts of a unit contiguous and in postorder
+    int64_t blob;                // offset (doubles, even) of the front's chunks in the solve pool
     int col0;                    // global position of the first pivot column
-    int rows_off;                // into rowg (first na entries = ancestor rows)
+    int rows_off;                // into rowg / slots (first na entries = ancestor rows)
     int w, na, ldr;              // ldr = w | 1 (odd leading dimension)
-    int parent;                  // sweep-order index of the parent front or -1
+    int parent;                  // unit of the parent front or -1 (informational)
     int nchild;
     int front;                   // global front id (FrontDesc index)
 };
+struct SolveUnit {               // a bottom subtree (<= PS_SMAX columns) or one front above the cut; one warp per unit
+    int first, nfronts;          // range of SolveFront
+    int pbeg, ncols;             // contiguous range of global positions eliminated by the unit
+    int out_rows_off, nout;      // rowg range of the root front's ancestor rows kept in shared memory (<= PS_NOUT)
+    int parent;                  // unit of the root front's parent or -1
+    int nchild;                  // number of child units
+};
 struct PStreamArgs {
     const SolveFront* sf;
-    int nfronts;
+    const SolveUnit* units;      // forward ticket order: subtree units (largest first), then top units deepest level first
+    int nunits;
     const double* SL;            // solve pool
     const int* rowg;
     const int* gidx;             // per position: index of that row in the caller's (unpermuted, concatenated) vectors
-    const int8_t* ptype;
-    const double* Did; const double* Die;
     const double* in;            // right-hand side, original order
     double* out;                 // solution, original order
     double* x;                   // work: permuted order
-    double* acc;                 // per position: updates pushed by descendants (zero between solves)
-    int* fcnt;                   // per front: completed children, cumulative over solves
-    int* bflag;                  // per front: 2*epoch+1 = forward sweep of the tree done (roots), 2*epoch+2 = backward step done
+    double* acc;                 // per position: updates pushed by descendant units (zero between solves)
+    int* ucnt;                   // per unit: completed child units, cumulative over solves
+    int* uflag;                  // per unit: 2*epoch+1 = forward sweep of the tree done (roots), 2*epoch+2 = backward step done
+    int* ticket;                 // [0] next ticket, [1] warps that have left (re-arms [0] for the next launch)
     int epoch;
     int out_mode;                // 0: out = K^-1 in, 1: out -= K^-1 in
 };
+__host__ __device__ int ps_rows_per_chunk(int ldr);
+__host__ __device__ int ps_chunk_doubles(int ldr);
 void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s);
-void launch_pack_solve(const SolveFront* sf, const int* slab_front, const int* slab_row0, int nslabs, const FrontDesc* fronts,
-                       const double* L, double* SL, cudaStream_t s);
+void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* chunk_idx, int nchunks, const FrontDesc* fronts,
+                       const double* L, const double* Did, const double* Die, const int8_t* ptype, const uint16_t* slots,
+                       double* SL, cudaStream_t s);
 void count_launch();
 
 // ---- leaf path ----

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -165,9 +166,11 @@ struct pipsgpu_ctx {
     DevBuf<int64_t> kmap, bmap, diagpos;
     // streaming persistent solve (psolve.cu): solve pool + per-front descriptors in sweep order
     DevBuf<SolveFront> sfront;
+    DevBuf<SolveUnit> sunits;
     DevBuf<double> SL, acc;
-    DevBuf<int> fcnt, bflag, slab_front, slab_row0;
-    int nslabs = 0;
+    DevBuf<int> ucnt, uflag, ticket, chunk_front, chunk_idx;
+    DevBuf<uint16_t> slots;
+    int nchunks = 0, nunits = 0, nsub_units = 0;
     int64_t SLtot = 0;
     int ps_epoch = 0, ps_epoch_max = 1 << 16;
     int sm_count = 148;
@@ -185,22 +188,25 @@ struct pipsgpu_ctx {
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
     void psolve(const double* in, double* out, int out_mode) {
-        if (nfronts <= 0) return;
+        if (nunits <= 0) return;
+        if (solve_by_level) { psolve_by_level(in, out, out_mode); return; }
         if (ps_epoch >= ps_epoch_max) {   // counters / flags are monotone in the epoch: re-arm long before they wrap
-            cudaMemsetAsync(fcnt.p, 0, sizeof(int) * (size_t)nfronts, stream);
-            cudaMemsetAsync(bflag.p, 0, sizeof(int) * (size_t)nfronts, stream);
+            cudaMemsetAsync(ucnt.p, 0, sizeof(int) * (size_t)nunits, stream);
+            cudaMemsetAsync(uflag.p, 0, sizeof(int) * (size_t)nunits, stream);
             ps_epoch = 0;
         }
         PStreamArgs a;
-        a.sf = sfront.p; a.nfronts = (int)nfronts; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p; a.ptype = ptype.p;
-        a.Did = Did.p; a.Die = Die.p; a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.fcnt = fcnt.p; a.bflag = bflag.p;
+        a.sf = sfront.p; a.units = sunits.p; a.nunits = nunits; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p;
+        a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.ucnt = ucnt.p; a.uflag = uflag.p; a.ticket = ticket.p;
         a.epoch = ps_epoch; a.out_mode = out_mode;
         launch_psolve_stream(a, sm_count, stream);
         ps_epoch += 1;
     }
+    void psolve_by_level(const double* in, double* out, int out_mode);   // diagnostic path, PIPSGPU_SOLVE=level
+    bool solve_by_level = false;
     // factor panels -> solve pool (after every numeric factorisation)
     void pack_solve() {
-        launch_pack_solve(sfront.p, slab_front.p, slab_row0.p, nslabs, fronts.p, L.p, SL.p, stream);
+        launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p, stream);
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
         SolveArgs a;
@@ -297,6 +303,23 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
         launch_front_update_tiles(fa, tb, tc, s);
     }
 }
+
+}  // namespace
+
+// Diagnostic only (PIPSGPU_SOLVE=level): the same K^-1 application through the per-level kernels that pipsgpu_leaf_solve
+// uses, to tell a defect of the streaming solve kernel from a defect of the factors on a GPU box.
+void pipsgpu_ctx::psolve_by_level(const double* in, double* out, int out_mode) {
+    launch_gather_perm(gidx.p, in, x.p, npos, 1, npos, stream);
+    SolveArgs sa = solve_args(x.p, npos, upd.p, std::max<int64_t>(updtot, 1));
+    run_leaf_solve(this, sa, 1, nullptr, 0, npos);
+    if (out_mode == 0) launch_scatter_perm(gidx.p, x.p, out, npos, 1, npos, stream);
+    else {
+        launch_scatter_perm(gidx.p, x.p, work.p, npos, 1, npos, stream);
+        launch_axpy(-1.0, work.p, out, npos, stream);
+    }
+}
+
+namespace {
 
 void fetch_leaf_stats(pipsgpu_ctx* ctx) {
     std::vector<int> h(4 * ctx->leaves.size());
@@ -400,6 +423,7 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     ctx->device = device;
     CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (const char* e = std::getenv("PIPSGPU_SOLVE")) ctx->solve_by_level = std::string(e) == "level";
     *out = ctx.release();
     PIPSGPU_CATCH
 }
@@ -793,36 +817,114 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->work.alloc((size_t)npos + 1);
     ctx->stats.alloc((size_t)4 * std::max(nl, 1));
     {
-        // sweep order of the streaming solve = level_fronts (deepest level first); blobs laid out in that order
-        std::vector<int> tinv((size_t)nfr, -1);
-        for (int64_t t = 0; t < nfr; ++t) tinv[(size_t)level_fronts[(size_t)t]] = (int)t;
-        std::vector<SolveFront> sf((size_t)nfr);
-        std::vector<int> slab_front, slab_row0;
-        int64_t off = 0;
-        int maxchild = 1;
-        for (int64_t t = 0; t < nfr; ++t) {
-            const FrontDesc& fd = fronts[(size_t)level_fronts[(size_t)t]];
-            SolveFront& f = sf[(size_t)t];
-            f.blob = off; f.col0 = fd.col0; f.rows_off = (int)fd.rows_off; f.w = fd.w; f.na = fd.na; f.ldr = fd.w | 1;
-            f.parent = fd.parent >= 0 ? tinv[(size_t)fd.parent] : -1;
-            f.nchild = fd.child_end - fd.child_begin;
-            maxchild = std::max(maxchild, f.nchild);
-            f.front = level_fronts[(size_t)t];
-            if (fd.rows_off > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "row index pool too large for one context");
-            const int rows = fd.w + fd.na;
-            off += ((int64_t)rows * f.ldr + 1) & ~int64_t(1);
-            for (int r0 = 0; r0 < rows; r0 += 32) { slab_front.push_back((int)t); slab_row0.push_back(r0); }
+        // ---- work units of the streaming solve (psolve.cu): bottom subtrees with <= PS_SMAX columns + single fronts above ----
+        // fronts of a leaf are numbered in postorder, so a subtree is a contiguous range of fronts and of positions
+        if (ps_rows_per_chunk(MAXW | 1) < MAXW) throw Error(PIPSGPU_ERR_INVALID, "PS_BUF too small: L11 must fit the first chunk");
+        std::vector<int> sub_nf((size_t)nfr, 1), sub_cols((size_t)nfr), sub_minf((size_t)nfr), sub_minc((size_t)nfr);
+        std::vector<int64_t> sub_wt((size_t)nfr);
+        for (int64_t f = 0; f < nfr; ++f) {
+            const FrontDesc& fd = fronts[(size_t)f];
+            sub_cols[(size_t)f] = fd.w; sub_minf[(size_t)f] = (int)f; sub_minc[(size_t)f] = fd.col0;
+            sub_wt[(size_t)f] = (int64_t)(fd.w + fd.na) * (fd.w | 1);
         }
+        for (int64_t f = 0; f < nfr; ++f) {      // children precede their parent
+            const int p = fronts[(size_t)f].parent;
+            if (p < 0) continue;
+            if (p <= f) throw Error(PIPSGPU_ERR_INVALID, "front tree is not in postorder");
+            sub_nf[(size_t)p] += sub_nf[(size_t)f];
+            sub_cols[(size_t)p] = std::min<int64_t>((int64_t)sub_cols[(size_t)p] + sub_cols[(size_t)f], 1 << 30);
+            sub_minf[(size_t)p] = std::min(sub_minf[(size_t)p], sub_minf[(size_t)f]);
+            sub_minc[(size_t)p] = std::min(sub_minc[(size_t)p], sub_minc[(size_t)f]);
+            sub_wt[(size_t)p] += sub_wt[(size_t)f];
+        }
+        auto eligible = [&](int64_t f) {
+            const FrontDesc& fd = fronts[(size_t)f];
+            return sub_cols[(size_t)f] <= PS_SMAX && sub_minf[(size_t)f] == (int)f - sub_nf[(size_t)f] + 1 &&
+                   fd.col0 + fd.w - sub_minc[(size_t)f] == sub_cols[(size_t)f];
+        };
+        struct U { int root, first_front, nfronts; int64_t wt; };
+        std::vector<U> subs, tops;
+        std::vector<int> unit_of_front((size_t)nfr, -1);
+        std::vector<char> is_top((size_t)nfr, 0);
+        for (int64_t f = nfr - 1; f >= 0; --f) {
+            if (unit_of_front[(size_t)f] != -1) continue;
+            if (eligible(f)) {
+                const int f0 = (int)f - sub_nf[(size_t)f] + 1;
+                for (int g = f0; g <= (int)f; ++g) unit_of_front[(size_t)g] = -2;      // member of a subtree unit (id below)
+                subs.push_back(U{(int)f, f0, sub_nf[(size_t)f], sub_wt[(size_t)f]});
+            } else {
+                unit_of_front[(size_t)f] = -3;
+                is_top[(size_t)f] = 1;
+            }
+        }
+        std::stable_sort(subs.begin(), subs.end(), [](const U& a, const U& b) { return a.wt > b.wt; });
+        for (int64_t t = 0; t < nfr; ++t) {      // level_fronts: deepest level first
+            const int f = level_fronts[(size_t)t];
+            if (is_top[(size_t)f]) tops.push_back(U{f, f, 1, 0});
+        }
+        const int nunits = (int)(subs.size() + tops.size());
+        std::vector<SolveUnit> units((size_t)nunits);
+        std::vector<SolveFront> sf((size_t)nfr);
+        std::vector<int> chunk_front, chunk_idx;
+        std::vector<uint16_t> slots((size_t)nrows, (uint16_t)0xFFFF);
+        int64_t off = 0;
+        int sfi = 0;
+        for (int u = 0; u < nunits; ++u) {
+            const U& uu = (u < (int)subs.size()) ? subs[(size_t)u] : tops[(size_t)u - subs.size()];
+            for (int g = uu.first_front; g < uu.first_front + uu.nfronts; ++g) unit_of_front[(size_t)g] = u;
+        }
+        int maxchild = 1;
+        for (int u = 0; u < nunits; ++u) {
+            const U& uu = (u < (int)subs.size()) ? subs[(size_t)u] : tops[(size_t)u - subs.size()];
+            const FrontDesc& rd = fronts[(size_t)uu.root];
+            SolveUnit& un = units[(size_t)u];
+            un.first = sfi; un.nfronts = uu.nfronts;
+            un.pbeg = sub_minc[(size_t)uu.root]; un.ncols = rd.col0 + rd.w - un.pbeg;
+            if (uu.nfronts == 1) { un.pbeg = rd.col0; un.ncols = rd.w; }
+            if (rd.rows_off > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "row index pool too large for one context");
+            un.out_rows_off = (int)rd.rows_off; un.nout = std::min(rd.na, PS_NOUT);
+            un.parent = rd.parent >= 0 ? unit_of_front[(size_t)rd.parent] : -1;
+            un.nchild = 0;
+            const int* orow = rowg.data() + rd.rows_off;      // ancestor rows of the unit's root front: ascending positions
+            for (int g = uu.first_front; g < uu.first_front + uu.nfronts; ++g) {
+                const FrontDesc& fd = fronts[(size_t)g];
+                SolveFront& f = sf[(size_t)sfi];
+                f.blob = off; f.col0 = fd.col0; f.rows_off = (int)fd.rows_off; f.w = fd.w; f.na = fd.na; f.ldr = fd.w | 1;
+                f.parent = un.parent; f.nchild = fd.child_end - fd.child_begin; f.front = g;
+                const int rows = fd.w + fd.na, R = ps_rows_per_chunk(f.ldr);
+                const int nch = (rows + R - 1) / R;
+                for (int c = 0; c < nch; ++c) { chunk_front.push_back(sfi); chunk_idx.push_back(c); }
+                off += (int64_t)nch * ps_chunk_doubles(f.ldr);
+                for (int t = 0; t < fd.na; ++t) {
+                    const int p = rowg[(size_t)fd.rows_off + t];
+                    uint16_t sl = 0xFFFF;
+                    if (p >= un.pbeg && p < un.pbeg + un.ncols) sl = (uint16_t)(p - un.pbeg);
+                    else {
+                        const int* it = std::lower_bound(orow, orow + rd.na, p);
+                        if (it != orow + rd.na && *it == p && (it - orow) < un.nout) sl = (uint16_t)(PS_SMAX + (it - orow));
+                    }
+                    slots[(size_t)fd.rows_off + t] = sl;
+                }
+                ++sfi;
+            }
+        }
+        for (int u = 0; u < nunits; ++u)
+            if (units[(size_t)u].parent >= 0) maxchild = std::max(maxchild, ++units[(size_t)units[(size_t)u].parent].nchild);
         ctx->SLtot = off;
+        ctx->nunits = nunits;
+        ctx->nsub_units = (int)subs.size();
         ctx->ps_epoch_max = (1 << 30) / maxchild - 2;   // the child counters are cumulative: nchild * epoch must not wrap
-        ctx->nslabs = (int)slab_front.size();
-        ctx->sfront.upload(sf, s); ctx->slab_front.upload(slab_front, s); ctx->slab_row0.upload(slab_row0, s);
+        ctx->nchunks = (int)chunk_front.size();
+        ctx->sfront.upload(sf, s); ctx->sunits.upload(units, s); ctx->chunk_front.upload(chunk_front, s);
+        ctx->chunk_idx.upload(chunk_idx, s); ctx->slots.upload(slots, s);
         ctx->SL.alloc((size_t)off + 2);
         ctx->acc.alloc((size_t)npos + 1);
-        ctx->fcnt.alloc((size_t)nfr + 1); ctx->bflag.alloc((size_t)nfr + 1);
+        ctx->ucnt.alloc((size_t)nunits + 1); ctx->uflag.alloc((size_t)nunits + 1); ctx->ticket.alloc(2);
         CUDA_CHECK(cudaMemsetAsync(ctx->acc.p, 0, sizeof(double) * ((size_t)npos + 1), s));
-        CUDA_CHECK(cudaMemsetAsync(ctx->fcnt.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
-        CUDA_CHECK(cudaMemsetAsync(ctx->bflag.p, 0, sizeof(int) * ((size_t)nfr + 1), s));
+        CUDA_CHECK(cudaMemsetAsync(ctx->ucnt.p, 0, sizeof(int) * ((size_t)nunits + 1), s));
+        CUDA_CHECK(cudaMemsetAsync(ctx->uflag.p, 0, sizeof(int) * ((size_t)nunits + 1), s));
+        CUDA_CHECK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(int) * 2, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));     // the host vectors above go out of scope
     }
     CUDA_CHECK(cudaMemsetAsync(ctx->Die.p, 0, sizeof(double) * ((size_t)npos + 1), s));
     CUDA_CHECK(cudaMemsetAsync(ctx->De.p, 0, sizeof(double) * ((size_t)npos + 1), s));

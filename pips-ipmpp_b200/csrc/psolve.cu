@@ -71,13 +71,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 // chunk geometry of a front (host + device): every chunk = [3*32 header doubles | R*ldr row doubles | R/4 slot doubles]
 __host__ __device__ int ps_rows_per_chunk(int ldr) {
-    int r = (4 * (PS_BUF - PS_HDR)) / (4 * ldr + 1);
+    int r = (4 * (PS_BUF - PS_HDR - 1)) / (4 * ldr + 1);
     r &= ~3;                       // slots: 4 uint16 per double
     return r < PS_XA ? r : PS_XA;
 }
 __host__ __device__ int ps_chunk_doubles(int ldr) {
     const int R = ps_rows_per_chunk(ldr);
-    return PS_HDR + R * ldr + R / 4;
+    return (PS_HDR + R * ldr + R / 4 + 1) & ~1;      // even: bulk copies need 16-byte addresses and sizes
 }
 
 // -----------------------------------------------------------------------------------------------------
@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
 
     // ---- issue side: cursor over (ticket, front, chunk) of the next bulk copy; runs at most two chunks ahead ----
     int i_t = draw();            // ticket being issued
-    int i_tnext = -1;            // ticket drawn ahead for the issue side (handed to the consume side in order)
     SolveUnit i_unit;
     SolveFront i_desc;
     int i_fr = 0, i_ch = 0, i_nch = 0;     // front position within the unit (processing order), chunk position, #chunks
@@ -216,12 +215,12 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                 issue_load_front();
             }
         }
+        __syncwarp();
     };
     // The consume side must see the same ticket sequence as the issue side: tickets are queued in a 4-entry ring.
     // (The issue side is at most 2 chunks, hence at most 2 units, ahead.)
-    int tq0 = i_t, tq1 = -1, tq2 = -1;       // tickets issued-but-not-consumed, in order
-    auto push_ticket = [&](int t) { if (tq1 < 0) tq1 = t; else tq2 = t; };
-    (void)i_tnext;
+    int tq0 = i_t, tq1 = -1, tq2 = -1, tq3 = -1;       // tickets drawn-but-not-consumed, in order
+    auto push_ticket = [&](int t) { if (tq1 < 0) tq1 = t; else if (tq2 < 0) tq2 = t; else tq3 = t; };
 
     issue_load_unit();
     {
@@ -420,7 +419,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
             }
         }
         __syncwarp();
-        tq0 = tq1; tq1 = tq2; tq2 = -1;
+        tq0 = tq1; tq1 = tq2; tq2 = tq3; tq3 = -1;
         if (tq0 < 0) break;      // cannot happen: the issue side always holds a ticket (possibly >= nt)
     }
     // the last warp to leave re-arms the ticket counter for the next launch
