@@ -215,6 +215,13 @@ int pipsgpu_symbolic_export(pipsgpu_symbolic* sym, int* perm, int8_t* ptype, int
                             int* sn_level, int64_t* Loff, int64_t* Coff, int64_t* kmap, int64_t* bmap,
                             int* child_ptr, int* child_idx);
 
+/* grouping of the big fronts for the deferred border x border Schur-complement updates (host-only inspection of what
+ * pipsgpu_ctx_commit builds; no counterpart in the reference, whose plugins keep their supernode scheduling private -
+ * PardisoSchurSolver.C:434-477 just receives the finished Schur complement). Call once with null arrays to get
+ * counts = {groups, members, positions}, then with arrays of those sizes (mem_ptr: groups+1, pos_ptr: members+1). */
+int pipsgpu_symbolic_border_groups(pipsgpu_symbolic* sym, int big_u, double frac, int64_t counts[3], int* root, int* N,
+                                   int* mem_ptr, int* mem_front, int64_t* pos_ptr, int* pos);
+
 #ifdef __cplusplus
 }
 #endif

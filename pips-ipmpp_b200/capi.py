@@ -100,6 +100,20 @@ class Symbolic:
         a.update(n=n, nB=s["nB"], ns=ns)
         return a
 
+    def border_groups(self, big_u, frac):
+        """grouping of the big fronts for the deferred border x border updates (pipsgpu_symbolic_border_groups)"""
+        cnt = np.zeros(3, dtype=np.int64)
+        null = C.c_void_p()
+        _check(lib().pipsgpu_symbolic_border_groups(self.h, C.c_int(big_u), C.c_double(frac), _ip(cnt), null, null, null,
+                                                    null, null, null))
+        ng, nm, npos = (int(v) for v in cnt)
+        g = dict(root=np.zeros(ng, np.int32), N=np.zeros(ng, np.int32), mem_ptr=np.zeros(ng + 1, np.int32),
+                 mem_front=np.zeros(nm, np.int32), pos_ptr=np.zeros(nm + 1, np.int64), pos=np.zeros(npos, np.int32))
+        _check(lib().pipsgpu_symbolic_border_groups(self.h, C.c_int(big_u), C.c_double(frac), _ip(cnt), _ip(g["root"]),
+                                                    _ip(g["N"]), _ip(g["mem_ptr"]), _ip(g["mem_front"]), _ip(g["pos_ptr"]),
+                                                    _ip(g["pos"])))
+        return g
+
     def __del__(self):
         try:
             if self.h:

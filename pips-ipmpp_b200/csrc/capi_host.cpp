@@ -113,4 +113,16 @@ int pipsgpu_symbolic_export(pipsgpu_symbolic* sym, int* perm, int8_t* ptype, int
     PIPSGPU_CATCH
 }
 
+int pipsgpu_symbolic_border_groups(pipsgpu_symbolic* sym, int big_u, double frac, int64_t counts[3], int* root, int* N,
+                                   int* mem_ptr, int* mem_front, int64_t* pos_ptr, int* pos) {
+    PIPSGPU_TRY
+    if (!sym || !counts) throw std::runtime_error("pipsgpu_symbolic_border_groups: null argument");
+    pipsgpu::BorderGroups G;
+    pipsgpu::build_border_groups(sym->S, big_u, frac, G);
+    counts[0] = (int64_t)G.root.size(); counts[1] = (int64_t)G.mem_front.size(); counts[2] = (int64_t)G.pos.size();
+    copy_out(root, G.root); copy_out(N, G.N); copy_out(mem_ptr, G.mem_ptr); copy_out(mem_front, G.mem_front);
+    copy_out(pos_ptr, G.pos_ptr); copy_out(pos, G.pos);
+    PIPSGPU_CATCH
+}
+
 }  // extern "C"

@@ -107,18 +107,24 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     double* did = s_did[warp];
     double* die = s_die[warp];
     int8_t* pt = s_pt[warp];
-    for (int k = 0; k < wp; ++k) {
-        Pl[lane * PLD + k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
-        Pw[lane * PLD + k] = 0.0;
-    }
-    // children's contributions to the pivot block: lane = row, inverse indices of the columns by shuffle
-    for (int c = fd.child_begin; c < fd.child_end; ++c) {
-        const ChildRef ch = child_ref(a, c);
-        const int ci = (lane < w) ? ch.inv[lane] : -1;
-        for (int k = 0; k < w; ++k) {
-            const int cj = __shfl_sync(full, ci, k);
-            if (cj >= 0 && ci >= 0 && lane >= k) Pl[lane * PLD + k] += ch.C[(size_t)cj * ch.u + ci];
+    // assembled pivot block, lane = row: own entries + the children's contributions. All global loads of one source are
+    // issued back to back into registers (one warp per front: the kernel is latency-bound).
+    {
+        double pv[MAXW];
+#pragma unroll
+        for (int k = 0; k < MAXW; ++k) pv[k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
+        for (int c = fd.child_begin; c < fd.child_end; ++c) {
+            const ChildRef ch = child_ref(a, c);
+            const int ci = (lane < w) ? ch.inv[lane] : -1;
+#pragma unroll
+            for (int k = 0; k < MAXW; ++k) {
+                const int cj = __shfl_sync(full, ci, k);
+                if (k < w && cj >= 0 && ci >= 0 && lane >= k) pv[k] += ch.C[(size_t)cj * ch.u + ci];
+            }
         }
+#pragma unroll
+        for (int k = 0; k < MAXW; ++k)
+            if (k < wp) { Pl[lane * PLD + k] = pv[k]; Pw[lane * PLD + k] = 0.0; }
     }
     pt[lane] = (lane < w) ? a.ptype[fd.col0 + lane] : (int8_t)0;
     did[lane] = 0.0;
@@ -213,81 +219,136 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     COUNT_LAUNCH();
 }
 
-// 32 rows [i0, i0+32) of the panel by one warp:  W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so
-// column tile y only needs A21(:, 0 .. 8y+7)), stored k-major in the scratch; then L21 = W21 D^-1 (block diagonal, 2x2
-// blocks couple neighbouring columns) row by row, written over A21.
-__device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
-                                            double* __restrict__ Wt, const double* __restrict__ X, int i0, int lane) {
-    const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
+// Per-front child table held across the lanes of a warp (lane c = child c, up to 32 children; later ones are re-read):
+// the pointers a consumer needs to gather from a child's contribution block, fetched once per front instead of once per
+// gather (two dependent global loads each time).
+struct ChildLane {
+    unsigned long long C, inv;
+    int u;
+};
+__device__ __forceinline__ ChildLane child_lane_load(const FactorArgs& a, const FrontDesc& fd, int lane) {
+    ChildLane cl;
+    cl.C = 0; cl.inv = 0; cl.u = 0;
+    const int c = fd.child_begin + lane;
+    if (c < fd.child_end) {
+        const FrontDesc& cd = a.fronts[a.child_list[c]];
+        cl.C = (unsigned long long)(a.C + cd.Coff);
+        cl.inv = (unsigned long long)(a.invmap + cd.inv_off);
+        cl.u = cd.na + cd.nb;
+    }
+    return cl;
+}
+__device__ __forceinline__ ChildRef child_get(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl, int c) {
+    if (c < 32) {
+        ChildRef r;
+        r.C = reinterpret_cast<const double*>(__shfl_sync(0xffffffffu, cl.C, c));
+        r.inv = reinterpret_cast<const int*>(__shfl_sync(0xffffffffu, cl.inv, c));
+        r.u = __shfl_sync(0xffffffffu, cl.u, c);
+        return r;
+    }
+    return child_ref(a, fd.child_begin + c);
+}
+
+constexpr int PCLD = 36;                     // leading dimension of the per-warp staging tile (conflict-free fragments)
+constexpr int PC_TILE = 32 * PCLD;           // doubles per warp
+
+// 32 rows [i0, i0+32) of the panel by one warp (WP = padded front width):
+//   1. lane = row: own entries + children's contributions gathered into registers (independent loads), staged in the
+//      warp's shared-memory tile;
+//   2. W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so column tile y only needs A21(:, 0 .. 8y+7));
+//      column tiles are processed from the last to the first so that W21 can overwrite A21 in the tile;
+//   3. lane = row: L21 = W21 D^-1 (block diagonal, 2x2 blocks couple neighbouring columns); L21 goes to the panel,
+//      W21 to the k-major scratch of the update kernels.
+template <int WP>
+__device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl,
+                                            double* __restrict__ F, double* __restrict__ Wt, const double* __restrict__ X,
+                                            double* __restrict__ As, int i0, int lane, double did_l, double die_l, int pt_l) {
+    const unsigned full = 0xffffffffu;
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
     const int lr = lane >> 2, lk = lane & 3;
     double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
-    // children's contributions to these 32 panel rows (in place: the panel is written by its owner only)
-    if (fd.child_end > fd.child_begin) {
-        const int i = i0 + lane;
-        for (int c = fd.child_begin; c < fd.child_end; ++c) {
-            const ChildRef ch = child_ref(a, c);
+    const int i = i0 + lane;
+    {
+        double av[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) av[k] = (k < w && i < u) ? A21[(size_t)k * m + i] : 0.0;
+        const int nch = fd.child_end - fd.child_begin;
+        for (int c = 0; c < nch; ++c) {
+            const ChildRef ch = child_get(a, fd, cl, c);
             const int ci = (i < u) ? ch.inv[w + i] : -1;
             const int cjl = (lane < w) ? ch.inv[lane] : -1;
-            for (int k = 0; k < w; ++k) {
-                const int cj = __shfl_sync(0xffffffffu, cjl, k);
-                if (cj >= 0 && ci >= 0) A21[(size_t)k * m + i] += ch.C[(size_t)cj * ch.u + ci];
+#pragma unroll
+            for (int k = 0; k < WP; ++k) {
+                const int cj = __shfl_sync(full, cjl, k);
+                if (cj >= 0 && ci >= 0) av[k] += ch.C[(size_t)cj * ch.u + ci];
             }
         }
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < WP; ++k) As[lane * PCLD + k] = av[k];
     }
-    for (int y = 0; y < wp / 8; ++y) {
+    __syncwarp();
+#pragma unroll
+    for (int y = WP / 8 - 1; y >= 0; --y) {
         double aw[4][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x) aw[x][0] = aw[x][1] = 0.0;
-        const int kend = (y + 1) * 8;
         const int n = y * 8 + lr;              // output column of this lane's B fragment
-        for (int k0 = 0; k0 < kend; k0 += 4) {
-            const int k = k0 + lk;
-            const double bx = X[(size_t)n * wp + k];
+        double bx[2 * (WP / 8)];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int i = i0 + x * 8 + lr;
-                const double af = (i < u && k < w) ? A21[(size_t)k * m + i] : 0.0;
-                dmma_m8n8k4(aw[x][0], aw[x][1], af, bx);
-            }
+        for (int q = 0; q < 2 * (y + 1); ++q) bx[q] = X[(size_t)n * WP + q * 4 + lk];
+#pragma unroll
+        for (int q = 0; q < 2 * (y + 1); ++q) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) dmma_m8n8k4(aw[x][0], aw[x][1], As[(x * 8 + lr) * PCLD + q * 4 + lk], bx[q]);
         }
+        __syncwarp();                          // every lane has read columns 8y .. 8y+7 of A21 before they become W21
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-            const int i = i0 + x * 8 + lr;
-            if (i >= u) continue;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) Wt[(size_t)(y * 8 + lk * 2 + e) * u + i] = aw[x][e];
+            As[(x * 8 + lr) * PCLD + y * 8 + lk * 2] = aw[x][0];
+            As[(x * 8 + lr) * PCLD + y * 8 + lk * 2 + 1] = aw[x][1];
         }
     }
     __syncwarp();
-    const int i = i0 + lane;
-    if (i < u) {
-        const int g0 = fd.col0;
-        for (int k = 0; k < w; ++k) {
-            const int t = a.ptype[g0 + k];
-            double l = Wt[(size_t)k * u + i] * a.Did[g0 + k];
-            if (t == 1) l = fma(Wt[(size_t)(k + 1) * u + i], a.Die[g0 + k], l);
-            else if (t == 2) l = fma(Wt[(size_t)(k - 1) * u + i], a.Die[g0 + k - 1], l);
-            A21[(size_t)k * m + i] = l;
+    {
+        double wv[WP];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) wv[k] = As[lane * PCLD + k];
+#pragma unroll
+        for (int k = 0; k < WP; ++k) {
+            const int t = __shfl_sync(full, pt_l, k);
+            const double d = __shfl_sync(full, did_l, k);
+            const double e = __shfl_sync(full, die_l, k);
+            const double ep = __shfl_sync(full, die_l, (k + 31) & 31);
+            double l = wv[k] * d;
+            if (t == 1) l = fma(k + 1 < WP ? wv[k + 1 < WP ? k + 1 : k] : 0.0, e, l);
+            else if (t == 2) l = fma(k > 0 ? wv[k > 0 ? k - 1 : 0] : 0.0, ep, l);
+            if (i < u) {
+                if (k < w) A21[(size_t)k * m + i] = l;
+                Wt[(size_t)k * u + i] = wv[k];
+            }
         }
     }
+    __syncwarp();                              // the tile is reused by the next chunk
+}
+
+// per-lane copies of D^-1 and the pivot types of a front's columns (lane k = column k)
+__device__ __forceinline__ void front_dinv_lane(const FactorArgs& a, const FrontDesc& fd, int lane, double& did_l,
+                                                double& die_l, int& pt_l) {
+    const bool in = lane < fd.w;
+    did_l = in ? a.Did[fd.col0 + lane] : 0.0;
+    die_l = in ? a.Die[fd.col0 + lane] : 0.0;
+    pt_l = in ? (int)a.ptype[fd.col0 + lane] : 0;
 }
 
 constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
 
-__global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fi = blockIdx.x * SF_WARPS + warp;
-    if (fi >= nfronts) return;
-    const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
-    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
-    if (u == 0) return;
-    double* F = a.L + fd.Loff;
-    double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
-    const double* X = a.XY + fd.XYoff;
-    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
-    __syncwarp();
-    // ---- update: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U ----
+// update of one small front:  U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U
+template <int WP>
+__device__ __forceinline__ void small_front_update(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl,
+                                                   const double* F, const double* Wt, int lane) {
+    // F and Wt were written by this warp in the panel phase: plain (coherent) loads, no __restrict__ / ld.global.nc
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
+    const int w4 = (w + 3) & ~3;
     double* Cs = a.C + fd.Coff;
     const int* rowg = a.rowg + fd.rows_off;
     const int lr = lane >> 2, lk = lane & 3;
@@ -300,45 +361,72 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            for (int k0 = 0; k0 < wp; k0 += 4) {
-                double af[4], bf[4];
-                const int k = k0 + lk;
+            // inverse indices of the first child: in flight while the tensor pipe works
+            int ci[4], cj[4][2];
+            ChildRef ch;
+            ch.C = nullptr; ch.inv = nullptr; ch.u = 0;
+            const bool pass = (bj * 32 < na) && nch > 0;
+            if (pass) {
+                ch = child_get(a, fd, cl, 0);
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     const int i = bi * 32 + x * 8 + lr;
-                    af[x] = (i < u && k < w) ? L21[(size_t)k * m + i] : 0.0;
+                    ci[x] = (i < u) ? ch.inv[w + i] : -1;
                 }
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int j = bj * 32 + y * 8 + lr;
-                    bf[y] = (j < u) ? Wt[(size_t)k * u + j] : 0.0;
+                for (int y = 0; y < 4; ++y)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = bj * 32 + y * 8 + lk * 2 + e;
+                        cj[y][e] = (j < na) ? ch.inv[w + j] : -1;
+                    }
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < WP; k0 += 4) {
+                if (k0 < w4) {
+                    double af[4], bf[4];
+                    const int k = k0 + lk;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = bi * 32 + x * 8 + lr;
+                        af[x] = (i < u && k < w) ? L21[(size_t)k * m + i] : 0.0;
+                    }
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const int j = bj * 32 + y * 8 + lr;
+                        bf[y] = (j < u) ? Wt[(size_t)k * u + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
                 }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
             }
             // acc <- -U + children's pass-through entries (ancestor columns only)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) { acc[x][y][0] = -acc[x][y][0]; acc[x][y][1] = -acc[x][y][1]; }
-            if (bj * 32 < na) {
+            if (pass) {
                 for (int c = 0; c < nch; ++c) {
-                    const ChildRef ch = child_ref(a, fd.child_begin + c);
-                    int ci[4], cj[4][2];
+                    // the next child's indices are requested before this child's values are consumed
+                    int ni[4], nj[4][2];
+                    ChildRef nx = ch;
+                    if (c + 1 < nch) {
+                        nx = child_get(a, fd, cl, c + 1);
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const int i = bi * 32 + x * 8 + lr;
-                        ci[x] = (i < u) ? ch.inv[w + i] : -1;
-                    }
-#pragma unroll
-                    for (int y = 0; y < 4; ++y)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int j = bj * 32 + y * 8 + lk * 2 + e;
-                            cj[y][e] = (j < na) ? ch.inv[w + j] : -1;
+                        for (int x = 0; x < 4; ++x) {
+                            const int i = bi * 32 + x * 8 + lr;
+                            ni[x] = (i < u) ? nx.inv[w + i] : -1;
                         }
+#pragma unroll
+                        for (int y = 0; y < 4; ++y)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int j = bj * 32 + y * 8 + lk * 2 + e;
+                                nj[y][e] = (j < na) ? nx.inv[w + j] : -1;
+                            }
+                    }
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -347,6 +435,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
                             for (int e = 0; e < 2; ++e)
                                 if (ci[x] >= 0 && cj[y][e] >= 0 && ci[x] >= cj[y][e])
                                     acc[x][y][e] += ch.C[(size_t)cj[y][e] * ch.u + ci[x]];
+                    if (c + 1 < nch) {
+                        ch = nx;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) ci[x] = ni[x];
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) { cj[y][0] = nj[y][0]; cj[y][1] = nj[y][1]; }
+                    }
                 }
             }
 #pragma unroll
@@ -368,6 +463,34 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
         }
     }
 }
+
+template <int WP>
+__device__ __forceinline__ void small_front_body(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ As, int lane) {
+    const int u = fd.na + fd.nb;
+    double* F = a.L + fd.Loff;
+    double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
+    const double* X = a.XY + fd.XYoff;
+    const ChildLane cl = child_lane_load(a, fd, lane);
+    double did_l, die_l;
+    int pt_l;
+    front_dinv_lane(a, fd, lane, did_l, die_l, pt_l);
+    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk<WP>(a, fd, cl, F, Wt, X, As, i0, lane, did_l, die_l, pt_l);
+    __syncwarp();
+    small_front_update<WP>(a, fd, cl, F, Wt, lane);
+}
+
+__global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
+    __shared__ double s_tile[SF_WARPS][PC_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SF_WARPS + warp;
+    if (fi >= nfronts) return;
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
+    if (fd.na + fd.nb == 0) return;
+    const int wp = padded_width(fd.w);
+    if (wp == 8) small_front_body<8>(a, fd, s_tile[warp], lane);
+    else if (wp == 16) small_front_body<16>(a, fd, s_tile[warp], lane);
+    else small_front_body<32>(a, fd, s_tile[warp], lane);
+}
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
     small_fronts_kernel<<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, 0, s>>>(a, begin, nfronts);
@@ -376,19 +499,33 @@ void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream
 
 // big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-__global__ void __launch_bounds__(BF_T) big_panel_kernel(FactorArgs a, int begin) {
-    const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
-    const int w = fd.w, u = fd.na + fd.nb;
+template <int WP>
+__device__ __forceinline__ void big_panel_body(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ As, int warp, int lane) {
+    const int u = fd.na + fd.nb;
     double* F = a.L + fd.Loff;
     double* Wt = a.W + fd.Woff;
     const double* X = a.XY + fd.XYoff;
+    const ChildLane cl = child_lane_load(a, fd, lane);
+    double did_l, die_l;
+    int pt_l;
+    front_dinv_lane(a, fd, lane, did_l, die_l, pt_l);
+    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk<WP>(a, fd, cl, F, Wt, X, As, i0, lane, did_l, die_l, pt_l);
+}
+__global__ void __launch_bounds__(BF_T, 2) big_panel_kernel(FactorArgs a, int begin) {
+    extern __shared__ double bp_smem[];
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    (void)w;
-    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
+    double* As = bp_smem + warp * PC_TILE;
+    const int wp = padded_width(fd.w);
+    if (wp == 8) big_panel_body<8>(a, fd, As, warp, lane);
+    else if (wp == 16) big_panel_body<16>(a, fd, As, warp, lane);
+    else big_panel_body<32>(a, fd, As, warp, lane);
 }
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    big_panel_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
+    constexpr int smem = (BF_T / 32) * PC_TILE * (int)sizeof(double);
+    cudaFuncSetAttribute(big_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    big_panel_kernel<<<nfronts, BF_T, smem, s>>>(a, begin);
     COUNT_LAUNCH();
 }
 
@@ -411,13 +548,10 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
     const int i0 = td.bi * TILE, j0 = td.bj * TILE;
     const int tid = threadIdx.x;
     // A tile: L rows i0.. (column-major panel: coalesced along rows), B tile: W rows j0.. (row-major scratch)
-    for (int idx = tid; idx < TILE * 32; idx += 128) {
+    for (int idx = tid; idx < TILE * wp; idx += 128) {
         const int k = idx >> 6, r = idx & 63;
         As[r * TLD + k] = (k < w && i0 + r < u) ? F[(size_t)k * m + w + i0 + r] : 0.0;
-    }
-    for (int idx = tid; idx < TILE * 32; idx += 128) {
-        const int k = idx >> 6, r = idx & 63;
-        Bs[r * TLD + k] = (k < wp && j0 + r < u) ? Wscr[(size_t)k * u + j0 + r] : 0.0;
+        Bs[r * TLD + k] = (j0 + r < u) ? Wscr[(size_t)k * u + j0 + r] : 0.0;
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -428,7 +562,8 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
     for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-    for (int k0 = 0; k0 < wp; k0 += 4) {
+    const int w4 = (w + 3) & ~3;
+    for (int k0 = 0; k0 < w4; k0 += 4) {
         double af[4], bf[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) af[x] = As[(wr + x * 8 + lr) * TLD + k0 + lk];
@@ -482,13 +617,109 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
                 if (gj > gi) continue;
                 const double v = acc[x][y][e];
                 if (gj < na) Cs[(size_t)gj * u + gi] = v;
-                else if (a.SC) atomicAdd(&a.SC[scrow + rowg[gj]], v);
+                else if (a.SC && !td.grouped) atomicAdd(&a.SC[scrow + rowg[gj]], v);
             }
     }
 }
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s) {
     if (ntiles <= 0) return;
     front_update_tiles_kernel<<<(unsigned)ntiles, 128, 0, s>>>(a, tile_begin);
+    COUNT_LAUNCH();
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Deferred border x border updates: one CTA per 64x64 tile (lower) of a group's N x N index space. For every member
+// front f of the group the tile receives  L_B,f(rows of tile bi) * (L_B,f D_f)(rows of tile bj)^T ; rows of f are
+// scattered to their positions in the root's border row list while staging (absent rows are zero), W = L D is
+// recomputed from L and the block-diagonal D on the fly. One flush (red.global.add.f64) per tile and group instead of
+// one per tile and front: the per-front flush was bound by the RED issue rate (~1.3 cycles per lane and SM).
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
+    __shared__ double As[TILE * TLD];
+    __shared__ double Bs[TILE * TLD];
+    const GTile td = a.gtiles[gtile_begin + blockIdx.x];
+    const GroupDesc g = a.groups[td.group];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int r = tid & 63, kq = tid >> 6;     // staging: thread = (tile row r, column parity kq)
+    double acc[4][4][2];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
+    const int64_t inv_stride = (int64_t)g.nblk * GROUP_TILE;
+    const int* inv_i = a.ginv + g.inv_base + (int64_t)td.bi * GROUP_TILE + r;
+    const int* inv_j = a.ginv + g.inv_base + (int64_t)td.bj * GROUP_TILE + r;
+    GroupMember mb = a.gmembers[g.mem_begin];
+    int ti = inv_i[0], tj = inv_j[0];
+    for (int mi = g.mem_begin; mi < g.mem_end; ++mi) {
+        // the next member's descriptor and row maps are requested before this member's panel is staged
+        GroupMember nmb = mb;
+        int nti = -1, ntj = -1;
+        if (mi + 1 < g.mem_end) {
+            nmb = a.gmembers[mi + 1];
+            nti = inv_i[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
+            ntj = inv_j[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
+        }
+        // barrier: the previous member's MMA has read As/Bs; vote: does this member have rows in both tile ranges?
+        const int any = __syncthreads_or((ti >= 0 ? 1 : 0) | (tj >= 0 ? 2 : 0));
+        if (any == 3) {
+            const int w = mb.w, m = mb.m, g0 = mb.col0;
+            const int w4 = (w + 3) & ~3;
+            const double* Lb = a.L + mb.Lb_off;
+            for (int k = kq; k < w4; k += 2) {
+                double av = 0.0, bv = 0.0;
+                if (k < w) {
+                    if (ti >= 0) av = Lb[(size_t)k * m + ti];
+                    if (tj >= 0) {
+                        const int pt = a.ptype[g0 + k];
+                        bv = Lb[(size_t)k * m + tj] * a.Dd[g0 + k];
+                        if (pt == 1 && k + 1 < w) bv = fma(Lb[(size_t)(k + 1) * m + tj], a.De[g0 + k], bv);
+                        else if (pt == 2 && k > 0) bv = fma(Lb[(size_t)(k - 1) * m + tj], a.De[g0 + k - 1], bv);
+                    }
+                }
+                As[r * TLD + k] = av;
+                Bs[r * TLD + k] = bv;
+            }
+            __syncthreads();
+            for (int k0 = 0; k0 < w4; k0 += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) af[x] = As[(wr + x * 8 + lr) * TLD + k0 + lk];
+#pragma unroll
+                for (int y = 0; y < 4; ++y) bf[y] = Bs[(wc + y * 8 + lr) * TLD + k0 + lk];
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+            }
+        }
+        mb = nmb; ti = nti; tj = ntj;
+    }
+    const FrontDesc& rd = a.fronts[g.root];
+    const int* rowb = a.rowg + rd.rows_off + rd.na;            // Schur-complement index of every border row of the root
+    const int i0 = td.bi * GROUP_TILE, j0 = td.bj * GROUP_TILE;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int gi = i0 + wr + x * 8 + lr;
+        if (gi >= g.N) continue;
+        const int64_t scrow = (int64_t)rowb[gi] * a.ldsc;
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = j0 + wc + y * 8 + lk * 2 + e;
+                if (gj > gi) continue;
+                const double v = acc[x][y][e];
+                if (v != 0.0) atomicAdd(&a.SC[scrow + rowb[gj]], -v);
+            }
+    }
+}
+void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
+    if (ngtiles <= 0 || !a.SC) return;
+    border_group_kernel<<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
     COUNT_LAUNCH();
 }
 
@@ -924,35 +1155,62 @@ void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* W
 
 // forward / block-diagonal / backward solve with the dense factors  P A P^T = L D L^T, one CTA per right-hand side.
 // perm[i] = original index at pivot position i; ptype marks 2x2 pivots (Bunch-Kaufman path), Dinv_e their coupling.
+// The vector lives in shared memory; per block column the 32x32 diagonal block (one entry per thread) and the first
+// DS_PRE panel rows of every warp are loaded BEFORE the barrier that the substitution of warp 0 waits on, so that one
+// block step costs one global-memory round trip (the first version re-read the factor inside the 32-step
+// substitution: 1600 dependent loads, 0.55 ms per solve at n_S = 800).
 constexpr int DS_T = 1024;
+constexpr int DS_PRE = 8;
 __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restrict__ A, int ld, int n,
                                                            const int* __restrict__ perm, const int8_t* __restrict__ ptype,
                                                            const double* __restrict__ Dinv, const double* __restrict__ Dinv_e,
-                                                           double* xall, int64_t xstride, double* wall) {
-    __shared__ double xs[DENSE_NB];
-    __shared__ double red[DS_T / 32][DENSE_NB + 1];
+                                                           double* xall, int64_t xstride) {
+    extern __shared__ double ds_smem[];
+    double* x = ds_smem;                               // n (padded to even)
+    double (*Ld)[DENSE_NB + 1] = reinterpret_cast<double (*)[DENSE_NB + 1]>(ds_smem + ((n + 1) & ~1));
+    double (*red)[DENSE_NB + 1] = Ld + DENSE_NB;       // DS_T/32 partial sums per column
+    double* xs = &red[DS_T / 32][0];
     double* xo = xall + (int64_t)blockIdx.x * xstride;
-    double* x = wall + (int64_t)blockIdx.x * n;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     const int nwarps = DS_T / 32;
     for (int i = tid; i < n; i += DS_T) x[i] = xo[perm[i]];
-    __syncthreads();
     // ---- forward: L y = b ----
     for (int kb = 0; kb < n; kb += DENSE_NB) {
         const int bw = min(DENSE_NB, n - kb);
+        {   // thread (warp, lane) stages entry (row warp, column lane) of the diagonal block
+            const bool in = warp < bw && lane < warp;
+            Ld[warp][lane] = in ? A[(int64_t)(kb + warp) * ld + kb + lane] : 0.0;
+        }
+        double pre[DS_PRE];
+        const int r0 = kb + bw + warp;
+#pragma unroll
+        for (int q = 0; q < DS_PRE; ++q) {
+            const int r = r0 + q * nwarps;
+            pre[q] = (r < n && lane < bw) ? A[(int64_t)r * ld + kb + lane] : 0.0;
+        }
+        __syncthreads();
         if (warp == 0) {
             double t = (lane < bw) ? x[kb + lane] : 0.0;
             for (int k = 0; k < bw; ++k) {
                 const double xk = __shfl_sync(full, t, k);
-                if (lane > k && lane < bw) t -= A[(int64_t)(kb + lane) * ld + kb + k] * xk;
+                t = fma(-Ld[lane][k], xk, t);          // Ld is zero on and above the diagonal
             }
             if (lane < bw) x[kb + lane] = t;
             xs[lane] = (lane < bw) ? t : 0.0;
         }
         __syncthreads();
-        for (int r = kb + bw + warp; r < n; r += nwarps) {
-            double v = (lane < bw) ? A[(int64_t)r * ld + kb + lane] * xs[lane] : 0.0;
+        const double xl = xs[lane];
+#pragma unroll
+        for (int q = 0; q < DS_PRE; ++q) {
+            const int r = r0 + q * nwarps;
+            double v = pre[q] * xl;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            if (lane == 0 && r < n) x[r] -= v;
+        }
+        for (int r = r0 + DS_PRE * nwarps; r < n; r += nwarps) {
+            double v = (lane < bw) ? A[(int64_t)r * ld + kb + lane] * xl : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
             if (lane == 0) x[r] -= v;
@@ -975,6 +1233,10 @@ __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restr
     for (int b = nblk - 1; b >= 0; --b) {
         const int kb = b * DENSE_NB;
         const int bw = min(DENSE_NB, n - kb);
+        {
+            const bool in = warp < bw && lane < warp;
+            Ld[warp][lane] = in ? A[(int64_t)(kb + warp) * ld + kb + lane] : 0.0;
+        }
         double acc = 0.0;
         for (int r = kb + bw + warp; r < n; r += nwarps)
             if (lane < bw) acc = fma(A[(int64_t)r * ld + kb + lane], x[r], acc);
@@ -982,11 +1244,12 @@ __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restr
         __syncthreads();
         if (warp == 0) {
             double s = 0.0;
+#pragma unroll 8
             for (int q = 0; q < nwarps; ++q) s += red[q][lane];
             double t = (lane < bw) ? x[kb + lane] - s : 0.0;
             for (int k = bw - 1; k >= 0; --k) {
                 const double xk = __shfl_sync(full, t, k);
-                if (lane < k) t -= A[(int64_t)(kb + k) * ld + kb + lane] * xk;
+                t = fma(-Ld[k][lane], xk, t);          // L(kb+k, kb+lane), zero unless lane < k
             }
             if (lane < bw) x[kb + lane] = t;
         }
@@ -994,10 +1257,16 @@ __global__ void __launch_bounds__(DS_T) dense_solve_kernel(const double* __restr
     }
     for (int i = tid; i < n; i += DS_T) xo[perm[i]] = x[i];
 }
+static size_t dense_solve_smem(int n) {
+    return sizeof(double) * ((size_t)((n + 1) & ~1) + (size_t)(DENSE_NB + DS_T / 32 + 1) * (DENSE_NB + 1));
+}
 void launch_dense_solve(const double* A, int ld, int n, const int* perm, const int8_t* ptype, const double* Dinv,
                         const double* Dinv_e, double* x, int nrhs, int64_t xstride, double* work, cudaStream_t s) {
     if (n <= 0 || nrhs <= 0) return;
-    dense_solve_kernel<<<nrhs, DS_T, 0, s>>>(A, ld, n, perm, ptype, Dinv, Dinv_e, x, xstride, work);
+    (void)work;
+    const size_t smem = dense_solve_smem(n);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dense_solve_kernel<<<nrhs, DS_T, smem, s>>>(A, ld, n, perm, ptype, Dinv, Dinv_e, x, xstride);
     COUNT_LAUNCH();
 }
 

@@ -11,7 +11,22 @@ constexpr int DENSE_NB = 32;     // block size of the dense root LDL^T
 constexpr int BIG_U = 128;       // fronts with at least this many off-diagonal rows update through the tiled DMMA kernel
 constexpr int TILE = 64;         // output tile of the tiled update
 
-struct TileDesc { int front, bi, bj, pad; };
+struct TileDesc { int front, bi, bj, grouped; };   // grouped: the border x border part of this front is left to its group
+
+// ---- deferred border x border updates (border_group_kernel) ----
+// A group is a connected piece of a block's front tree whose members' border row sets are nested in the group root's
+// (border rows are never eliminated, so border(child) is a subset of border(parent)). Its share of
+// SC -= Bord^T K^-1 Bord  is one SYRK over the concatenated border panels of the members in the root's index space,
+// accumulated in registers and flushed once per 64x64 tile instead of once per front.
+constexpr int GROUP_TILE = 64;
+struct GroupMember { int64_t Lb_off; int m, w, col0, front; };   // border rows of the member's panel: Lb(t,k) = L[Lb_off + k*m + t]
+struct GroupDesc {
+    int64_t inv_base;   // ginv[inv_base + (member*nblk + b)*64 + r] = member's border row at root position 64b+r, or -1
+    int mem_begin, mem_end;
+    int N, nblk;        // N = border rows of the root front, nblk = ceil(N / 64)
+    int root, pad;
+};
+struct GTile { int group, bi, bj, pad; };
 
 // One front (supernode) of one scenario block. All offsets index context-wide pools.
 struct FrontDesc {
@@ -60,6 +75,10 @@ struct FactorArgs {
     int ldsc;
     int* stats;                  // per leaf: {positive, negative, zero, perturbed}
     const TileDesc* tiles;       // update tiles of the big fronts, grouped by level
+    const GroupDesc* groups;
+    const GroupMember* gmembers;
+    const int* ginv;
+    const GTile* gtiles;
 };
 
 struct SolveArgs {
@@ -132,6 +151,7 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s); 
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);      // fronts fl_fronts[begin..)
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
+void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s);
 void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_fwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s);

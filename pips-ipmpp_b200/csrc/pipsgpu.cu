@@ -109,6 +109,7 @@ struct pipsgpu_leaf {
     bool border_set = false;
     // symbolic
     LeafSymbolic S;
+    BorderGroups G;                  // grouping of the big fronts (consumed by pipsgpu_ctx_commit)
     bool analyzed = false;
     double knorm = 1.0;
     // placement in the context pools (valid after commit)
@@ -118,6 +119,7 @@ struct pipsgpu_leaf {
     std::vector<int> level_begin, level_count;   // per global level: sub-range of level_fronts owned by this leaf
     std::vector<int> fl_begin, fl_count;         // per (global level, small|big): sub-range of fl_fronts owned by this leaf
     std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
+    int64_t gtile_begin = 0, gtile_count = 0;    // sub-range of the border-group tiles of this leaf
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double flops = 0;
     int inertia[3] = {0, 0, 0};
@@ -154,6 +156,14 @@ struct pipsgpu_ctx {
     std::vector<int> level_ptr;     // nlevels*NCLS+1 into level_fronts; group g = level_order*NCLS + width class, deepest level first
     std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
     DevBuf<TileDesc> tiles;
+    // deferred border x border updates (kernels.cuh: GroupDesc)
+    DevBuf<GroupDesc> groups;
+    DevBuf<GroupMember> gmembers;
+    DevBuf<int> ginv;
+    DevBuf<GTile> gtiles;
+    int64_t ngtiles = 0;
+    bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
+    double group_frac = 0.6;        // a front joins its parent's group if it has at least this share of the root's border rows
     DevBuf<double> XY;
     int64_t XYtot = 0;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
@@ -184,6 +194,7 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gtiles = gtiles.p;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -252,6 +263,7 @@ void analyze_one(pipsgpu_leaf* lf) {
         for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p)
             if (lf->jcol[p] != i) kn = std::max(kn, std::fabs(lf->val[p]));
     lf->knorm = std::max(kn, 1.0);
+    build_border_groups(lf->S, BIG_U, lf->ctx ? lf->ctx->group_frac : 0.6, lf->G);
     lf->analyzed = true;
 }
 
@@ -301,6 +313,11 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
         int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
         if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
         launch_front_update_tiles(fa, tb, tc, s);
+    }
+    // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement)
+    if (sc) {
+        if (only) launch_border_groups(fa, only->gtile_begin, only->gtile_count, s);
+        else launch_border_groups(fa, 0, ctx->ngtiles, s);
     }
 }
 
@@ -424,6 +441,8 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (const char* e = std::getenv("PIPSGPU_SOLVE")) ctx->solve_by_level = std::string(e) == "level";
+    if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
     *out = ctx.release();
     PIPSGPU_CATCH
 }
@@ -767,19 +786,69 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             }
         }
     }
-    // ---- update tiles of the big fronts, grouped by (level, leaf) ----
+    // ---- border groups: which big fronts leave their border x border update to a group SYRK (kernels.cuh) ----
+    // (grouping per leaf: build_border_groups in symbolic.cpp, run with the symbolic analysis on the host threads)
+    std::vector<GroupDesc> groups;
+    std::vector<GroupMember> gmembers;
+    std::vector<int> ginv;
+    std::vector<GTile> gtiles;
+    std::vector<char> grouped((size_t)nfr, 0);
+    if (ctx->grouping) {
+        for (auto* lf : ctx->leaves) {
+            const BorderGroups& G = lf->G;
+            const int ng = (int)G.root.size();
+            for (int s2 = 0; s2 < lf->S.ns; ++s2) grouped[(size_t)lf->front_base + s2] = G.grouped[(size_t)s2];
+            // heavy groups first: their tiles loop over the most members
+            std::vector<int> order((size_t)ng);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+                return G.mem_ptr[(size_t)x + 1] - G.mem_ptr[(size_t)x] > G.mem_ptr[(size_t)y + 1] - G.mem_ptr[(size_t)y];
+            });
+            lf->gtile_begin = (int64_t)gtiles.size();
+            for (int oi : order) {
+                GroupDesc gd;
+                gd.N = G.N[(size_t)oi]; gd.nblk = (gd.N + GROUP_TILE - 1) / GROUP_TILE;
+                gd.root = lf->front_base + G.root[(size_t)oi]; gd.pad = 0;
+                gd.mem_begin = (int)gmembers.size(); gd.inv_base = (int64_t)ginv.size();
+                for (int q = G.mem_ptr[(size_t)oi]; q < G.mem_ptr[(size_t)oi + 1]; ++q) {
+                    const int f = lf->front_base + G.mem_front[(size_t)q];
+                    const FrontDesc& fd = fronts[(size_t)f];
+                    GroupMember mb;
+                    mb.Lb_off = fd.Loff + fd.w + fd.na; mb.m = fd.w + fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f;
+                    gmembers.push_back(mb);
+                    const size_t base = ginv.size();
+                    ginv.resize(base + (size_t)gd.nblk * GROUP_TILE, -1);
+                    const int* pf = G.pos.data() + G.pos_ptr[(size_t)q];
+                    if (G.pos_ptr[(size_t)q + 1] - G.pos_ptr[(size_t)q] != fd.nb) throw Error(PIPSGPU_ERR_INVALID, "border group: position map size mismatch");
+                    for (int t = 0; t < fd.nb; ++t) ginv[base + (size_t)pf[t]] = t;
+                }
+                gd.mem_end = (int)gmembers.size();
+                const int gi = (int)groups.size();
+                groups.push_back(gd);
+                for (int bi = 0; bi < gd.nblk; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) gtiles.push_back(GTile{gi, bi, bj, 0});
+            }
+            lf->gtile_count = (int64_t)gtiles.size() - lf->gtile_begin;
+            lf->G = BorderGroups();
+        }
+    }
+    ctx->ngtiles = (int64_t)gtiles.size();
+    // ---- update tiles of the big fronts, grouped by (level, leaf); grouped fronts only keep the ancestor columns ----
     std::vector<TileDesc> tiles;
     {
         for (auto* lf : ctx->leaves) { lf->tile_begin.assign(nlev, 0); lf->tile_count.assign(nlev, 0); }
-        auto ntiles_of = [](const FrontDesc& fd) -> int64_t {
+        auto ntiles_of = [&](int64_t f) -> int64_t {
+            const FrontDesc& fd = fronts[(size_t)f];
             const int u = fd.na + fd.nb;
             if (u < BIG_U) return 0;
             const int64_t nt = (u + TILE - 1) / TILE;
-            return nt * (nt + 1) / 2;
+            if (!grouped[(size_t)f]) return nt * (nt + 1) / 2;
+            const int64_t nj = (fd.na + TILE - 1) / TILE;          // tile columns that hold ancestor columns
+            return nj * nt - nj * (nj - 1) / 2;
         };
         for (auto* lf : ctx->leaves)
             for (int s2 = 0; s2 < lf->S.ns; ++s2)
-                lf->tile_count[nlev - 1 - lf->S.sn_level[s2]] += ntiles_of(fronts[(size_t)lf->front_base + s2]);
+                lf->tile_count[nlev - 1 - lf->S.sn_level[s2]] += ntiles_of(lf->front_base + s2);
         ctx->tile_ptr.assign(nlev + 1, 0);
         for (int l = 0; l < nlev; ++l) {
             int64_t run = ctx->tile_ptr[l];
@@ -790,14 +859,21 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         for (auto* lf : ctx->leaves) {
             std::vector<int64_t> fill(lf->tile_begin);
             for (int s2 = 0; s2 < lf->S.ns; ++s2) {
-                const FrontDesc& fd = fronts[(size_t)lf->front_base + s2];
+                const int f = lf->front_base + s2;
+                const FrontDesc& fd = fronts[(size_t)f];
                 const int u = fd.na + fd.nb;
                 if (u < BIG_U) continue;
                 const int ol = nlev - 1 - lf->S.sn_level[s2];
                 const int nt = (u + TILE - 1) / TILE;
+                const int g = grouped[(size_t)f];
                 for (int bi = 0; bi < nt; ++bi)
-                    for (int bj = 0; bj <= bi; ++bj) tiles[(size_t)fill[ol]++] = TileDesc{lf->front_base + s2, bi, bj, 0};
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        if (g && bj * TILE >= fd.na) continue;
+                        tiles[(size_t)fill[ol]++] = TileDesc{f, bi, bj, g};
+                    }
             }
+            for (int l = 0; l < nlev; ++l)
+                if (fill[l] != lf->tile_begin[l] + lf->tile_count[l]) throw Error(PIPSGPU_ERR_INVALID, "update tile count mismatch");
         }
     }
 
@@ -809,6 +885,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
+    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gtiles.upload(gtiles, s);
     ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);

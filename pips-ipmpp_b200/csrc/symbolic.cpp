@@ -480,4 +480,53 @@ void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jco
     }
 }
 
+void build_border_groups(const LeafSymbolic& S, int big_u, double frac, BorderGroups& out) {
+    const int ns = S.ns;
+    out = BorderGroups();
+    out.grouped.assign((size_t)ns, 0);
+    std::vector<int> grp_of((size_t)ns, -1);
+    std::vector<std::vector<int>> pos((size_t)ns);
+    std::vector<std::vector<int>> mem;
+    // fronts are numbered in postorder: walking backwards visits parents before their children
+    for (int f = ns - 1; f >= 0; --f) {
+        const int na = S.sn_na[f], nb = S.sn_nb[f];
+        if (na + nb < big_u || nb == 0) continue;
+        const int p = S.sn_parent[f];
+        if (p >= 0 && p <= f) throw std::runtime_error("build_border_groups: front tree is not in postorder");
+        std::vector<int>& pf = pos[(size_t)f];
+        pf.resize((size_t)nb);
+        const int g = p >= 0 ? grp_of[(size_t)p] : -1;
+        if (g >= 0 && (double)nb >= frac * out.N[(size_t)g]) {
+            const int wp = S.sn_col[p + 1] - S.sn_col[p], nap = S.sn_na[p], nbp = S.sn_nb[p];
+            const std::vector<int>& pp = pos[(size_t)p];
+            const int* rel = S.relidx.data() + S.sn_rowptr[f] + na;
+            for (int t = 0; t < nb; ++t) {
+                const int li = rel[t] - wp - nap;
+                if (li < 0 || li >= nbp) throw std::runtime_error("build_border_groups: border row of a front is not a border row of its parent");
+                pf[(size_t)t] = pp[(size_t)li];
+                if (t > 0 && pf[(size_t)t] <= pf[(size_t)t - 1]) throw std::runtime_error("build_border_groups: border rows are not ascending");
+            }
+            grp_of[(size_t)f] = g;
+            mem[(size_t)g].push_back(f);
+        } else {
+            for (int t = 0; t < nb; ++t) pf[(size_t)t] = t;
+            grp_of[(size_t)f] = (int)out.root.size();
+            out.root.push_back(f);
+            out.N.push_back(nb);
+            mem.push_back(std::vector<int>{f});
+        }
+        out.grouped[(size_t)f] = 1;
+    }
+    out.mem_ptr.assign(1, 0);
+    out.pos_ptr.assign(1, 0);
+    for (size_t g = 0; g < mem.size(); ++g) {
+        for (int f : mem[g]) {
+            out.mem_front.push_back(f);
+            out.pos.insert(out.pos.end(), pos[(size_t)f].begin(), pos[(size_t)f].end());
+            out.pos_ptr.push_back((int64_t)out.pos.size());
+        }
+        out.mem_ptr.push_back((int)out.mem_front.size());
+    }
+}
+
 }  // namespace pipsgpu

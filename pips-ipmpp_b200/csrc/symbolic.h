@@ -62,4 +62,19 @@ struct SymbolicOptions {
 void analyze_leaf(int n, int nx, int ny, int nz, const int* krow, const int* jcol, const double* val, int nB,
                   int64_t nnzB, const int* brow, const int* bcol, const SymbolicOptions& opt, LeafSymbolic& out);
 
+// Grouping of the big fronts (>= big_u off-diagonal rows, at least one border row) for the deferred border x border
+// updates (kernels.cuh: GroupDesc). Border rows are never eliminated, so border(child) is a subset of border(parent):
+// a front joins its parent's group if the parent is grouped and the front has at least frac * (border rows of the
+// group root) border rows, otherwise it opens a group of its own. pos maps every border row of a member to the index
+// of the same border row in the root's list (strictly ascending).
+struct BorderGroups {
+    std::vector<int> root, N;          // per group: root front, its number of border rows
+    std::vector<int> mem_ptr;          // ngroups+1 into mem_front
+    std::vector<int> mem_front;        // members of each group, root first, then descendants (parents before children)
+    std::vector<int64_t> pos_ptr;      // per member (+1): into pos
+    std::vector<int> pos;
+    std::vector<char> grouped;         // per front
+};
+void build_border_groups(const LeafSymbolic& S, int big_u, double frac, BorderGroups& out);
+
 }  // namespace pipsgpu

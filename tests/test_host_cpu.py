@@ -161,6 +161,52 @@ def test_symbolic_analysis_invariants(pkg, cfg, max_width):
         assert sym.sizes["nnzL"] == int(np.tril(S).sum())
 
 
+@pytest.mark.parametrize("cfg,big_u,frac", [("T2", 4, 0.6), ("T3", 8, 0.5), ("T3", 16, 0.9), ("T3", 2, 0.05)])
+def test_border_groups_are_nested_and_equivalent(pkg, cfg, big_u, frac):
+    """the grouping behind border_group_kernel: every big front with border rows sits in exactly one group, a group is a
+    connected piece of the tree below its root, positions address the same border index in the root's row list, and
+    accumulating sum_f L_B,f D_f L_B,f^T through the group positions (what the kernel does, 64-row tiles included)
+    equals accumulating it front by front through the border indices"""
+    lp = pkg.problem.synthetic(cfg)
+    sym, (krow, jcol, val, nB, brow, bcol) = _symbolic(pkg, lp, 0)
+    a = sym.export()
+    g = sym.border_groups(big_u, frac)
+    n, ns = a["n"], a["ns"]
+    rp, rows, na, nb, par = a["sn_rowptr"], a["rowidx"], a["sn_na"], a["sn_nb"], a["sn_parent"]
+    w = np.diff(a["sn_col"])
+    want = {f for f in range(ns) if na[f] + nb[f] >= big_u and nb[f] > 0}
+    assert sorted(g["mem_front"].tolist()) == sorted(want) and len(want) > 0
+    rng = np.random.default_rng(5)
+    direct = np.zeros((nB, nB))
+    grouped = np.zeros((nB, nB))
+    for gi in range(len(g["root"])):
+        root, N = int(g["root"][gi]), int(g["N"][gi])
+        mem = g["mem_front"][g["mem_ptr"][gi]:g["mem_ptr"][gi + 1]]
+        assert mem[0] == root and N == nb[root]
+        rootb = rows[rp[root] + na[root]:rp[root + 1]] - n           # border index of every root row
+        inside = set(int(f) for f in mem)
+        nblk = (N + 63) // 64
+        acc = np.zeros((nblk * 64, nblk * 64))
+        for q, f in zip(range(g["mem_ptr"][gi], g["mem_ptr"][gi + 1]), mem):
+            pos = g["pos"][g["pos_ptr"][q]:g["pos_ptr"][q + 1]]
+            fb = rows[rp[f] + na[f]:rp[f + 1]] - n
+            assert len(pos) == nb[f] and np.all(np.diff(pos) > 0)
+            assert np.array_equal(rootb[pos], fb)
+            if f != root:
+                assert int(par[f]) in inside and nb[f] >= frac * N
+            LB = rng.standard_normal((nb[f], w[f]))
+            D = rng.standard_normal((w[f], w[f])); D = D + D.T
+            U = LB @ D @ LB.T
+            direct[np.ix_(fb, fb)] += U
+            # the kernel's staging: per 64-row block an inverse map position -> member row, absent rows are zero
+            inv = -np.ones(nblk * 64, int); inv[pos] = np.arange(nb[f])
+            A = np.where(inv[:, None] >= 0, LB[np.maximum(inv, 0)], 0.0)
+            acc += A @ D @ A.T
+        assert np.all(acc[N:, :] == 0) and np.all(acc[:, N:] == 0)
+        grouped[np.ix_(rootb, rootb)] += acc[:N, :N]
+    assert np.allclose(grouped, direct, rtol=1e-12, atol=1e-12)
+
+
 def test_symbolic_is_deterministic_and_counts_flops(pkg):
     lp = pkg.problem.synthetic("T2")
     s1, _ = _symbolic(pkg, lp, 1)
