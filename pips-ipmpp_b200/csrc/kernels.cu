@@ -219,136 +219,81 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     COUNT_LAUNCH();
 }
 
-// Per-front child table held across the lanes of a warp (lane c = child c, up to 32 children; later ones are re-read):
-// the pointers a consumer needs to gather from a child's contribution block, fetched once per front instead of once per
-// gather (two dependent global loads each time).
-struct ChildLane {
-    unsigned long long C, inv;
-    int u;
-};
-__device__ __forceinline__ ChildLane child_lane_load(const FactorArgs& a, const FrontDesc& fd, int lane) {
-    ChildLane cl;
-    cl.C = 0; cl.inv = 0; cl.u = 0;
-    const int c = fd.child_begin + lane;
-    if (c < fd.child_end) {
-        const FrontDesc& cd = a.fronts[a.child_list[c]];
-        cl.C = (unsigned long long)(a.C + cd.Coff);
-        cl.inv = (unsigned long long)(a.invmap + cd.inv_off);
-        cl.u = cd.na + cd.nb;
-    }
-    return cl;
-}
-__device__ __forceinline__ ChildRef child_get(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl, int c) {
-    if (c < 32) {
-        ChildRef r;
-        r.C = reinterpret_cast<const double*>(__shfl_sync(0xffffffffu, cl.C, c));
-        r.inv = reinterpret_cast<const int*>(__shfl_sync(0xffffffffu, cl.inv, c));
-        r.u = __shfl_sync(0xffffffffu, cl.u, c);
-        return r;
-    }
-    return child_ref(a, fd.child_begin + c);
-}
-
-constexpr int PCLD = 36;                     // leading dimension of the per-warp staging tile (conflict-free fragments)
-constexpr int PC_TILE = 32 * PCLD;           // doubles per warp
-
-// 32 rows [i0, i0+32) of the panel by one warp (WP = padded front width):
-//   1. lane = row: own entries + children's contributions gathered into registers (independent loads), staged in the
-//      warp's shared-memory tile;
-//   2. W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so column tile y only needs A21(:, 0 .. 8y+7));
-//      column tiles are processed from the last to the first so that W21 can overwrite A21 in the tile;
-//   3. lane = row: L21 = W21 D^-1 (block diagonal, 2x2 blocks couple neighbouring columns); L21 goes to the panel,
-//      W21 to the k-major scratch of the update kernels.
-template <int WP>
-__device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl,
-                                            double* __restrict__ F, double* __restrict__ Wt, const double* __restrict__ X,
-                                            double* __restrict__ As, int i0, int lane, double did_l, double die_l, int pt_l) {
-    const unsigned full = 0xffffffffu;
-    const int w = fd.w, u = fd.na + fd.nb, m = w + u;
+// 32 rows [i0, i0+32) of the panel by one warp:  W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so
+// column tile y only needs A21(:, 0 .. 8y+7)), stored k-major in the scratch; then L21 = W21 D^-1 (block diagonal, 2x2
+// blocks couple neighbouring columns) row by row, written over A21.
+__device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
+                                            double* __restrict__ Wt, const double* __restrict__ X, int i0, int lane) {
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
     const int lr = lane >> 2, lk = lane & 3;
     double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
-    const int i = i0 + lane;
-    {
-        double av[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) av[k] = (k < w && i < u) ? A21[(size_t)k * m + i] : 0.0;
-        const int nch = fd.child_end - fd.child_begin;
-        for (int c = 0; c < nch; ++c) {
-            const ChildRef ch = child_get(a, fd, cl, c);
+    // children's contributions to these 32 panel rows (in place: the panel is written by its owner only)
+    if (fd.child_end > fd.child_begin) {
+        const int i = i0 + lane;
+        for (int c = fd.child_begin; c < fd.child_end; ++c) {
+            const ChildRef ch = child_ref(a, c);
             const int ci = (i < u) ? ch.inv[w + i] : -1;
             const int cjl = (lane < w) ? ch.inv[lane] : -1;
-#pragma unroll
-            for (int k = 0; k < WP; ++k) {
-                const int cj = __shfl_sync(full, cjl, k);
-                if (cj >= 0 && ci >= 0) av[k] += ch.C[(size_t)cj * ch.u + ci];
+            for (int k = 0; k < w; ++k) {
+                const int cj = __shfl_sync(0xffffffffu, cjl, k);
+                if (cj >= 0 && ci >= 0) A21[(size_t)k * m + i] += ch.C[(size_t)cj * ch.u + ci];
             }
         }
-#pragma unroll
-        for (int k = 0; k < WP; ++k) As[lane * PCLD + k] = av[k];
+        __syncwarp();
     }
-    __syncwarp();
-#pragma unroll
-    for (int y = WP / 8 - 1; y >= 0; --y) {
+    for (int y = 0; y < wp / 8; ++y) {
         double aw[4][2];
 #pragma unroll
         for (int x = 0; x < 4; ++x) aw[x][0] = aw[x][1] = 0.0;
+        const int kend = (y + 1) * 8;
         const int n = y * 8 + lr;              // output column of this lane's B fragment
-        double bx[2 * (WP / 8)];
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            const int k = k0 + lk;
+            const double bx = X[(size_t)n * wp + k];
 #pragma unroll
-        for (int q = 0; q < 2 * (y + 1); ++q) bx[q] = X[(size_t)n * WP + q * 4 + lk];
-#pragma unroll
-        for (int q = 0; q < 2 * (y + 1); ++q) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) dmma_m8n8k4(aw[x][0], aw[x][1], As[(x * 8 + lr) * PCLD + q * 4 + lk], bx[q]);
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x * 8 + lr;
+                const double af = (i < u && k < w) ? A21[(size_t)k * m + i] : 0.0;
+                dmma_m8n8k4(aw[x][0], aw[x][1], af, bx);
+            }
         }
-        __syncwarp();                          // every lane has read columns 8y .. 8y+7 of A21 before they become W21
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-            As[(x * 8 + lr) * PCLD + y * 8 + lk * 2] = aw[x][0];
-            As[(x * 8 + lr) * PCLD + y * 8 + lk * 2 + 1] = aw[x][1];
+            const int i = i0 + x * 8 + lr;
+            if (i >= u) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Wt[(size_t)(y * 8 + lk * 2 + e) * u + i] = aw[x][e];
         }
     }
     __syncwarp();
-    {
-        double wv[WP];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) wv[k] = As[lane * PCLD + k];
-#pragma unroll
-        for (int k = 0; k < WP; ++k) {
-            const int t = __shfl_sync(full, pt_l, k);
-            const double d = __shfl_sync(full, did_l, k);
-            const double e = __shfl_sync(full, die_l, k);
-            const double ep = __shfl_sync(full, die_l, (k + 31) & 31);
-            double l = wv[k] * d;
-            if (t == 1) l = fma(k + 1 < WP ? wv[k + 1 < WP ? k + 1 : k] : 0.0, e, l);
-            else if (t == 2) l = fma(k > 0 ? wv[k > 0 ? k - 1 : 0] : 0.0, ep, l);
-            if (i < u) {
-                if (k < w) A21[(size_t)k * m + i] = l;
-                Wt[(size_t)k * u + i] = wv[k];
-            }
+    const int i = i0 + lane;
+    if (i < u) {
+        const int g0 = fd.col0;
+        for (int k = 0; k < w; ++k) {
+            const int t = a.ptype[g0 + k];
+            double l = Wt[(size_t)k * u + i] * a.Did[g0 + k];
+            if (t == 1) l = fma(Wt[(size_t)(k + 1) * u + i], a.Die[g0 + k], l);
+            else if (t == 2) l = fma(Wt[(size_t)(k - 1) * u + i], a.Die[g0 + k - 1], l);
+            A21[(size_t)k * m + i] = l;
         }
     }
-    __syncwarp();                              // the tile is reused by the next chunk
-}
-
-// per-lane copies of D^-1 and the pivot types of a front's columns (lane k = column k)
-__device__ __forceinline__ void front_dinv_lane(const FactorArgs& a, const FrontDesc& fd, int lane, double& did_l,
-                                                double& die_l, int& pt_l) {
-    const bool in = lane < fd.w;
-    did_l = in ? a.Did[fd.col0 + lane] : 0.0;
-    die_l = in ? a.Die[fd.col0 + lane] : 0.0;
-    pt_l = in ? (int)a.ptype[fd.col0 + lane] : 0;
 }
 
 constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
 
-// update of one small front:  U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U
-template <int WP>
-__device__ __forceinline__ void small_front_update(const FactorArgs& a, const FrontDesc& fd, const ChildLane& cl,
-                                                   const double* F, const double* Wt, int lane) {
-    // F and Wt were written by this warp in the panel phase: plain (coherent) loads, no __restrict__ / ld.global.nc
-    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
-    const int w4 = (w + 3) & ~3;
+__global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * SF_WARPS + warp;
+    if (fi >= nfronts) return;
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
+    const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
+    if (u == 0) return;
+    double* F = a.L + fd.Loff;
+    double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
+    const double* X = a.XY + fd.XYoff;
+    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
+    __syncwarp();
+    // ---- update: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U ----
     double* Cs = a.C + fd.Coff;
     const int* rowg = a.rowg + fd.rows_off;
     const int lr = lane >> 2, lk = lane & 3;
@@ -361,72 +306,45 @@ __device__ __forceinline__ void small_front_update(const FactorArgs& a, const Fr
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-            // inverse indices of the first child: in flight while the tensor pipe works
-            int ci[4], cj[4][2];
-            ChildRef ch;
-            ch.C = nullptr; ch.inv = nullptr; ch.u = 0;
-            const bool pass = (bj * 32 < na) && nch > 0;
-            if (pass) {
-                ch = child_get(a, fd, cl, 0);
+            for (int k0 = 0; k0 < wp; k0 += 4) {
+                double af[4], bf[4];
+                const int k = k0 + lk;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     const int i = bi * 32 + x * 8 + lr;
-                    ci[x] = (i < u) ? ch.inv[w + i] : -1;
+                    af[x] = (i < u && k < w) ? L21[(size_t)k * m + i] : 0.0;
                 }
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = bj * 32 + y * 8 + lk * 2 + e;
-                        cj[y][e] = (j < na) ? ch.inv[w + j] : -1;
-                    }
-            }
-#pragma unroll
-            for (int k0 = 0; k0 < WP; k0 += 4) {
-                if (k0 < w4) {
-                    double af[4], bf[4];
-                    const int k = k0 + lk;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const int i = bi * 32 + x * 8 + lr;
-                        af[x] = (i < u && k < w) ? L21[(size_t)k * m + i] : 0.0;
-                    }
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int j = bj * 32 + y * 8 + lr;
-                        bf[y] = (j < u) ? Wt[(size_t)k * u + j] : 0.0;
-                    }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+                for (int y = 0; y < 4; ++y) {
+                    const int j = bj * 32 + y * 8 + lr;
+                    bf[y] = (j < u) ? Wt[(size_t)k * u + j] : 0.0;
                 }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
             }
             // acc <- -U + children's pass-through entries (ancestor columns only)
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y) { acc[x][y][0] = -acc[x][y][0]; acc[x][y][1] = -acc[x][y][1]; }
-            if (pass) {
+            if (bj * 32 < na) {
                 for (int c = 0; c < nch; ++c) {
-                    // the next child's indices are requested before this child's values are consumed
-                    int ni[4], nj[4][2];
-                    ChildRef nx = ch;
-                    if (c + 1 < nch) {
-                        nx = child_get(a, fd, cl, c + 1);
+                    const ChildRef ch = child_ref(a, fd.child_begin + c);
+                    int ci[4], cj[4][2];
 #pragma unroll
-                        for (int x = 0; x < 4; ++x) {
-                            const int i = bi * 32 + x * 8 + lr;
-                            ni[x] = (i < u) ? nx.inv[w + i] : -1;
-                        }
-#pragma unroll
-                        for (int y = 0; y < 4; ++y)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int j = bj * 32 + y * 8 + lk * 2 + e;
-                                nj[y][e] = (j < na) ? nx.inv[w + j] : -1;
-                            }
+                    for (int x = 0; x < 4; ++x) {
+                        const int i = bi * 32 + x * 8 + lr;
+                        ci[x] = (i < u) ? ch.inv[w + i] : -1;
                     }
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = bj * 32 + y * 8 + lk * 2 + e;
+                            cj[y][e] = (j < na) ? ch.inv[w + j] : -1;
+                        }
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -435,13 +353,6 @@ __device__ __forceinline__ void small_front_update(const FactorArgs& a, const Fr
                             for (int e = 0; e < 2; ++e)
                                 if (ci[x] >= 0 && cj[y][e] >= 0 && ci[x] >= cj[y][e])
                                     acc[x][y][e] += ch.C[(size_t)cj[y][e] * ch.u + ci[x]];
-                    if (c + 1 < nch) {
-                        ch = nx;
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) ci[x] = ni[x];
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) { cj[y][0] = nj[y][0]; cj[y][1] = nj[y][1]; }
-                    }
                 }
             }
 #pragma unroll
@@ -463,34 +374,6 @@ __device__ __forceinline__ void small_front_update(const FactorArgs& a, const Fr
         }
     }
 }
-
-template <int WP>
-__device__ __forceinline__ void small_front_body(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ As, int lane) {
-    const int u = fd.na + fd.nb;
-    double* F = a.L + fd.Loff;
-    double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
-    const double* X = a.XY + fd.XYoff;
-    const ChildLane cl = child_lane_load(a, fd, lane);
-    double did_l, die_l;
-    int pt_l;
-    front_dinv_lane(a, fd, lane, did_l, die_l, pt_l);
-    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk<WP>(a, fd, cl, F, Wt, X, As, i0, lane, did_l, die_l, pt_l);
-    __syncwarp();
-    small_front_update<WP>(a, fd, cl, F, Wt, lane);
-}
-
-__global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
-    __shared__ double s_tile[SF_WARPS][PC_TILE];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int fi = blockIdx.x * SF_WARPS + warp;
-    if (fi >= nfronts) return;
-    const FrontDesc fd = a.fronts[a.fl_fronts[begin + fi]];
-    if (fd.na + fd.nb == 0) return;
-    const int wp = padded_width(fd.w);
-    if (wp == 8) small_front_body<8>(a, fd, s_tile[warp], lane);
-    else if (wp == 16) small_front_body<16>(a, fd, s_tile[warp], lane);
-    else small_front_body<32>(a, fd, s_tile[warp], lane);
-}
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
     small_fronts_kernel<<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, 0, s>>>(a, begin, nfronts);
@@ -499,33 +382,19 @@ void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream
 
 // big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-template <int WP>
-__device__ __forceinline__ void big_panel_body(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ As, int warp, int lane) {
-    const int u = fd.na + fd.nb;
+__global__ void __launch_bounds__(BF_T) big_panel_kernel(FactorArgs a, int begin) {
+    const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
+    const int w = fd.w, u = fd.na + fd.nb;
     double* F = a.L + fd.Loff;
     double* Wt = a.W + fd.Woff;
     const double* X = a.XY + fd.XYoff;
-    const ChildLane cl = child_lane_load(a, fd, lane);
-    double did_l, die_l;
-    int pt_l;
-    front_dinv_lane(a, fd, lane, did_l, die_l, pt_l);
-    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk<WP>(a, fd, cl, F, Wt, X, As, i0, lane, did_l, die_l, pt_l);
-}
-__global__ void __launch_bounds__(BF_T, 2) big_panel_kernel(FactorArgs a, int begin) {
-    extern __shared__ double bp_smem[];
-    const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* As = bp_smem + warp * PC_TILE;
-    const int wp = padded_width(fd.w);
-    if (wp == 8) big_panel_body<8>(a, fd, As, warp, lane);
-    else if (wp == 16) big_panel_body<16>(a, fd, As, warp, lane);
-    else big_panel_body<32>(a, fd, As, warp, lane);
+    (void)w;
+    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
 }
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    constexpr int smem = (BF_T / 32) * PC_TILE * (int)sizeof(double);
-    cudaFuncSetAttribute(big_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    big_panel_kernel<<<nfronts, BF_T, smem, s>>>(a, begin);
+    big_panel_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
     COUNT_LAUNCH();
 }
 
@@ -663,9 +532,11 @@ __global__ void __launch_bounds__(128) border_group_kernel(FactorArgs a, int64_t
             nti = inv_i[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
             ntj = inv_j[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
         }
-        // barrier: the previous member's MMA has read As/Bs; vote: does this member have rows in both tile ranges?
-        const int any = __syncthreads_or((ti >= 0 ? 1 : 0) | (tj >= 0 ? 2 : 0));
-        if (any == 3) {
+        // barrier: the previous member's MMA has read As/Bs; votes: does this member have rows in both tile ranges?
+        // (__syncthreads_or returns a predicate, not the bitwise OR of its arguments: one vote per range)
+        const int any_i = __syncthreads_or(ti >= 0);
+        const int any_j = __syncthreads_or(tj >= 0);
+        if (any_i && any_j) {
             const int w = mb.w, m = mb.m, g0 = mb.col0;
             const int w4 = (w + 3) & ~3;
             const double* Lb = a.L + mb.Lb_off;

@@ -138,6 +138,9 @@ struct PStreamArgs {
 };
 __host__ __device__ int ps_rows_per_chunk(int ldr);
 __host__ __device__ int ps_chunk_doubles(int ldr);
+__host__ __device__ int ps_chunk_rows(int ldr, int rows, int c);
+__host__ __device__ int ps_chunk_doubles_rows(int ldr, int cr);
+__host__ __device__ int64_t ps_front_doubles(int ldr, int rows);
 void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s);
 void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* chunk_idx, int nchunks, const FrontDesc* fronts,
                        const double* L, const double* Did, const double* Die, const int8_t* ptype, const uint16_t* slots,

@@ -971,7 +971,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const int rows = fd.w + fd.na, R = ps_rows_per_chunk(f.ldr);
                 const int nch = (rows + R - 1) / R;
                 for (int c = 0; c < nch; ++c) { chunk_front.push_back(sfi); chunk_idx.push_back(c); }
-                off += (int64_t)nch * ps_chunk_doubles(f.ldr);
+                off += ps_front_doubles(f.ldr, rows);
                 for (int t = 0; t < fd.na; ++t) {
                     const int p = rowg[(size_t)fd.rows_off + t];
                     uint16_t sl = 0xFFFF;

@@ -79,6 +79,20 @@ __host__ __device__ int ps_chunk_doubles(int ldr) {
     const int R = ps_rows_per_chunk(ldr);
     return (PS_HDR + R * ldr + R / 4 + 1) & ~1;      // even: bulk copies need 16-byte addresses and sizes
 }
+// Rows stored in chunk c of a front with `rows` rows: every chunk but the last holds R rows and occupies
+// ps_chunk_doubles(ldr) doubles (so chunk c starts at c * ps_chunk_doubles); the last one is cut to its own rows
+// (rounded up to the 4 slots of one double) - most fronts are a single short chunk.
+__host__ __device__ int ps_chunk_rows(int ldr, int rows, int c) {
+    const int R = ps_rows_per_chunk(ldr);
+    const int rem = rows - c * R;
+    return rem < R ? ((rem + 3) & ~3) : R;
+}
+__host__ __device__ int ps_chunk_doubles_rows(int ldr, int cr) { return (PS_HDR + cr * ldr + cr / 4 + 1) & ~1; }
+__host__ __device__ int64_t ps_front_doubles(int ldr, int rows) {
+    const int R = ps_rows_per_chunk(ldr);
+    const int nch = (rows + R - 1) / R;
+    return (int64_t)(nch - 1) * ps_chunk_doubles(ldr) + ps_chunk_doubles_rows(ldr, ps_chunk_rows(ldr, rows, nch - 1));
+}
 
 // -----------------------------------------------------------------------------------------------------
 // pack: panel (column-major, ld = m, rows [pivot | ancestors | border]) -> chunks of the solve pool. One warp per chunk.
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
     const int c = chunk_idx[q];
     const FrontDesc fd = fronts[f.front];
     const int w = f.w, rows = f.w + f.na, m = fd.w + fd.na + fd.nb, ldr = f.ldr;
-    const int R = ps_rows_per_chunk(ldr);
+    const int R = ps_rows_per_chunk(ldr), CR = ps_chunk_rows(ldr, rows, c);
     const int r0 = c * R, r1 = min(rows, r0 + R);
     double* dst = SL + f.blob + (size_t)c * ps_chunk_doubles(ldr);
     // header: z = dd*y + dn*y_next + dp*y_prev  (1x1 and 2x2 pivots without a type switch in the solve)
@@ -130,8 +144,8 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
         }
     }
     // shared-memory slot of every L21 row of this chunk
-    uint16_t* sd = reinterpret_cast<uint16_t*>(rowsdst + (size_t)R * ldr);
-    for (int i = r0 + lane; i < r0 + R; i += 32)
+    uint16_t* sd = reinterpret_cast<uint16_t*>(rowsdst + (size_t)CR * ldr);
+    for (int i = r0 + lane; i < r0 + CR; i += 32)
         sd[i - r0] = (i >= w && i < r1) ? slots[f.rows_off + (i - w)] : (uint16_t)0xFFFF;
 }
 
@@ -201,7 +215,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
         const int c = fwd ? i_ch : i_nch - 1 - i_ch;      // backward: last rows first, the L11 chunk last
         if (lane == 0) {
             const int cd = ps_chunk_doubles(i_desc.ldr);
-            const uint32_t bytes = (uint32_t)cd * 8u;
+            const uint32_t bytes = (uint32_t)ps_chunk_doubles_rows(i_desc.ldr, ps_chunk_rows(i_desc.ldr, i_desc.w + i_desc.na, c)) * 8u;
             s_desc[warp][slot] = i_desc;
             mbar_expect_tx(&bar[slot], bytes);
             bulk_g2s(buf0 + (size_t)slot * PS_BUF, a.SL + i_desc.blob + (int64_t)c * cd, bytes, &bar[slot]);
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                     const int r0 = c * R, r1 = min(rows, r0 + R);
                     const double* H = buf0 + (size_t)slot * PS_BUF;
                     const double* B = H + PS_HDR;
-                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)R * ldr);
+                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows(ldr, rows, c) * ldr);
                     if (c > 0) mbar_wait(&bar[slot], slot ? phase1 : phase0);
                     if (slot) phase1 ^= 1; else phase0 ^= 1;
                     int rb = r0;
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                     const int rb = max(r0, w);
                     const double* H = buf0 + (size_t)slot * PS_BUF;
                     const double* B = H + PS_HDR;
-                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)R * ldr);
+                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows(ldr, rows, c) * ldr);
                     if (cc > 0) mbar_wait(&bar[slot], slot ? phase1 : phase0);
                     if (slot) phase1 ^= 1; else phase0 ^= 1;
                     // x of the ancestor rows of this chunk
