@@ -164,6 +164,12 @@ struct pipsgpu_ctx {
     int64_t ngtiles = 0;
     bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
     double group_frac = 0.6;        // a front joins its parent's group if it has at least this share of the root's border rows
+    int big_u = BIG_U;              // PIPSGPU_BIG_U: fronts with at least this many off-diagonal rows take the CTA-parallel path
+    // side stream: the small fronts of a level run next to the big-front panel / tile kernels of the same level, and the
+    // border-group SYRKs next to pack_solve (PIPSGPU_OVERLAP=0 keeps everything on one stream)
+    bool overlap = true;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf<double> XY;
     int64_t XYtot = 0;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
@@ -263,7 +269,7 @@ void analyze_one(pipsgpu_leaf* lf) {
         for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p)
             if (lf->jcol[p] != i) kn = std::max(kn, std::fabs(lf->val[p]));
     lf->knorm = std::max(kn, 1.0);
-    build_border_groups(lf->S, BIG_U, lf->ctx ? lf->ctx->group_frac : 0.6, lf->G);
+    build_border_groups(lf->S, lf->ctx ? lf->ctx->big_u : BIG_U, lf->ctx ? lf->ctx->group_frac : 0.6, lf->G);
     lf->analyzed = true;
 }
 
@@ -293,8 +299,12 @@ void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_lea
     }
 }
 
-void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
+// All levels of the numeric factorisation (deepest first), then the deferred border-group updates and the solve-pool
+// pack. e_pack0 / e_pack1 (optional) bracket the pack kernel on the main stream.
+void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cudaEvent_t e_pack0 = nullptr,
+                       cudaEvent_t e_pack1 = nullptr) {
     cudaStream_t s = ctx->stream;
+    cudaStream_t s2 = ctx->overlap ? ctx->stream2 : nullptr;
     FactorArgs fa = ctx->factor_args(sc);
     for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
         if (only) {
@@ -303,21 +313,46 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only) {
             const int begin = ctx->level_ptr[lv * NCLS];
             launch_pivot(fa, begin, ctx->level_ptr[(lv + 1) * NCLS] - begin, s);
         }
+        int begin[2], count[2];
         for (int kind = 0; kind < 2; ++kind) {
             const int g = lv * 2 + kind;
-            int begin = ctx->fl_ptr[g], count = ctx->fl_ptr[g + 1] - ctx->fl_ptr[g];
-            if (only) { begin = only->fl_begin[g]; count = only->fl_count[g]; }
-            if (kind == 0) launch_small_fronts(fa, begin, count, s);
-            else launch_big_panel(fa, begin, count, s);
+            begin[kind] = ctx->fl_ptr[g]; count[kind] = ctx->fl_ptr[g + 1] - ctx->fl_ptr[g];
+            if (only) { begin[kind] = only->fl_begin[g]; count[kind] = only->fl_count[g]; }
         }
         int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
         if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
-        launch_front_update_tiles(fa, tb, tc, s);
+        // small and big fronts of one level are independent of each other (disjoint panels, scratch and contribution
+        // blocks): the latency-bound one-warp-per-front kernel runs next to the CTA-parallel panel + tile kernels
+        const bool fork = s2 && count[0] > 0 && count[1] > 0;
+        cudaStream_t sb = fork ? s2 : s;
+        if (fork) {
+            CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
+            CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+        }
+        launch_small_fronts(fa, begin[0], count[0], s);
+        launch_big_panel(fa, begin[1], count[1], sb);
+        launch_front_update_tiles(fa, tb, tc, sb);
+        if (fork) {
+            CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
+            CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        }
     }
-    // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement)
-    if (sc) {
-        if (only) launch_border_groups(fa, only->gtile_begin, only->gtile_count, s);
-        else launch_border_groups(fa, 0, ctx->ngtiles, s);
+    // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement):
+    // read-only on the factor panels, like the pack kernel next to which they run
+    int64_t gb = 0, gc = ctx->ngtiles;
+    if (only) { gb = only->gtile_begin; gc = only->gtile_count; }
+    const bool fork = s2 && sc && gc > 0;
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+    }
+    if (sc) launch_border_groups(fa, gb, gc, fork ? s2 : s);
+    if (e_pack0) CUDA_CHECK(cudaEventRecord(e_pack0, s));
+    ctx->pack_solve();
+    if (e_pack1) CUDA_CHECK(cudaEventRecord(e_pack1, s));
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
+        CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     }
 }
 
@@ -443,6 +478,11 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_SOLVE")) ctx->solve_by_level = std::string(e) == "level";
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
+    if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
+    if (const char* e = std::getenv("PIPSGPU_OVERLAP")) ctx->overlap = std::string(e) != "0";
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     *out = ctx.release();
     PIPSGPU_CATCH
 }
@@ -456,6 +496,9 @@ int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx) {
     for (auto* lf : ctx->leaves) delete lf;
     if (ctx->h_dvals) cudaFreeHost(ctx->h_dvals);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
     PIPSGPU_CATCH
 }
@@ -768,7 +811,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     // ---- factorisation launch lists: fronts grouped by (level, small|big), by leaf inside a group ----
     std::vector<int> fl_fronts((size_t)nfr);
     {
-        auto kind_of = [&](const FrontDesc& fd) { return (fd.na + fd.nb >= BIG_U) ? 1 : 0; };
+        auto kind_of = [&](const FrontDesc& fd) { return (fd.na + fd.nb >= ctx->big_u) ? 1 : 0; };
         std::vector<int> cnt2(nlev * 2 + 1, 0);
         for (auto* lf : ctx->leaves)
             for (int s2 = 0; s2 < lf->S.ns; ++s2)
@@ -840,7 +883,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         auto ntiles_of = [&](int64_t f) -> int64_t {
             const FrontDesc& fd = fronts[(size_t)f];
             const int u = fd.na + fd.nb;
-            if (u < BIG_U) return 0;
+            if (u < ctx->big_u) return 0;
             const int64_t nt = (u + TILE - 1) / TILE;
             if (!grouped[(size_t)f]) return nt * (nt + 1) / 2;
             const int64_t nj = (fd.na + TILE - 1) / TILE;          // tile columns that hold ancestor columns
@@ -862,7 +905,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const int f = lf->front_base + s2;
                 const FrontDesc& fd = fronts[(size_t)f];
                 const int u = fd.na + fd.nb;
-                if (u < BIG_U) continue;
+                if (u < ctx->big_u) continue;
                 const int ol = nlev - 1 - lf->S.sn_level[s2];
                 const int nt = (u + TILE - 1) / TILE;
                 const int g = grouped[(size_t)f];
@@ -1078,7 +1121,6 @@ int pipsgpu_leaf_factorize(pipsgpu_leaf* lf, int inertia[3]) {
     require_device(ctx);
     factor_prepare(ctx, lf);
     run_factor_levels(ctx, nullptr, lf);
-    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     lf->factorized = true;
     if (inertia) { inertia[0] = lf->inertia[0]; inertia[1] = lf->inertia[1]; inertia[2] = lf->inertia[2]; }
@@ -1091,7 +1133,6 @@ int pipsgpu_ctx_factorize_leaves(pipsgpu_ctx* ctx, pipsgpu_sc* sc) {
     if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_ctx_factorize_leaves: context not committed");
     factor_prepare(ctx, nullptr);
     run_factor_levels(ctx, sc, nullptr);
-    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     for (auto* lf : ctx->leaves) lf->factorized = true;
     PIPSGPU_CATCH
@@ -1105,7 +1146,6 @@ int pipsgpu_leaf_add_schur(pipsgpu_leaf* lf, pipsgpu_sc* sc) {
     // the Schur term is a by-product of the elimination: redo this leaf's numeric phase with the SC attached
     factor_prepare(ctx, lf);
     run_factor_levels(ctx, sc, lf);
-    ctx->pack_solve();
     fetch_leaf_stats(ctx);
     lf->factorized = true;
     PIPSGPU_CATCH
@@ -1405,10 +1445,7 @@ static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[
     launch_set_diag(ctx->diagpos.p, ctx->dvals.p, ctx->npos, ctx->Kval.p, s);
     factor_prepare(ctx, nullptr);
     CUDA_CHECK(cudaEventRecord(k->ev[1], s));
-    run_factor_levels(ctx, sc, nullptr);
-    CUDA_CHECK(cudaEventRecord(k->ev[12], s));
-    ctx->pack_solve();
-    CUDA_CHECK(cudaEventRecord(k->ev[13], s));
+    run_factor_levels(ctx, sc, nullptr, k->ev[12], k->ev[13]);
     CUDA_CHECK(cudaEventRecord(k->ev[2], s));
     // ---- reduceKKT ----
     sc_allreduce_impl(sc);
