@@ -537,22 +537,25 @@ __global__ void __launch_bounds__(128) border_group_kernel(FactorArgs a, int64_t
         const int any_i = __syncthreads_or(ti >= 0);
         const int any_j = __syncthreads_or(tj >= 0);
         if (any_i && any_j) {
-            const int w = mb.w, m = mb.m, g0 = mb.col0;
+            const int w = mb.w, m = mb.m, u = mb.u;
             const int w4 = (w + 3) & ~3;
             const double* Lb = a.L + mb.Lb_off;
-            for (int k = kq; k < w4; k += 2) {
-                double av = 0.0, bv = 0.0;
-                if (k < w) {
-                    if (ti >= 0) av = Lb[(size_t)k * m + ti];
-                    if (tj >= 0) {
-                        const int pt = a.ptype[g0 + k];
-                        bv = Lb[(size_t)k * m + tj] * a.Dd[g0 + k];
-                        if (pt == 1 && k + 1 < w) bv = fma(Lb[(size_t)(k + 1) * m + tj], a.De[g0 + k], bv);
-                        else if (pt == 2 && k > 0) bv = fma(Lb[(size_t)(k - 1) * m + tj], a.De[g0 + k - 1], bv);
-                    }
+            const double* Wb = a.W + mb.Wb_off;
+            // all loads of a batch of 8 columns are issued before the first one is consumed (the staging is one global
+            // round trip per batch; W = L D comes from the member's persistent panel scratch)
+            for (int kb = 0; kb < w4; kb += 16) {
+                double av[8], bv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = kb + kq + 2 * q;
+                    av[q] = (k < w && ti >= 0) ? Lb[(size_t)k * m + ti] : 0.0;
+                    bv[q] = (k < w && tj >= 0) ? Wb[(size_t)k * u + tj] : 0.0;
                 }
-                As[r * TLD + k] = av;
-                Bs[r * TLD + k] = bv;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = kb + kq + 2 * q;
+                    if (k < w4) { As[r * TLD + k] = av[q]; Bs[r * TLD + k] = bv[q]; }
+                }
             }
             __syncthreads();
             for (int k0 = 0; k0 < w4; k0 += 4) {

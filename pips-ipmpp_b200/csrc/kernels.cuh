@@ -19,7 +19,10 @@ struct TileDesc { int front, bi, bj, grouped; };   // grouped: the border x bord
 // SC -= Bord^T K^-1 Bord  is one SYRK over the concatenated border panels of the members in the root's index space,
 // accumulated in registers and flushed once per 64x64 tile instead of once per front.
 constexpr int GROUP_TILE = 64;
-struct GroupMember { int64_t Lb_off; int m, w, col0, front; };   // border rows of the member's panel: Lb(t,k) = L[Lb_off + k*m + t]
+struct GroupMember {             // border rows of a member: Lb(t,k) = L[Lb_off + k*m + t],  (L_B D)(t,k) = W[Wb_off + k*u + t]
+    int64_t Lb_off, Wb_off;      // Wb_off: the member's W21 scratch is persistent (not the per-level one), see pipsgpu_ctx_commit
+    int m, u, w, col0, front, pad;
+};
 struct GroupDesc {
     int64_t inv_base;   // ginv[inv_base + (member*nblk + b)*64 + r] = member's border row at root position 64b+r, or -1
     int mem_begin, mem_end;
@@ -108,8 +111,8 @@ struct SolveFront {              // one per front, fronts of a unit contiguous a
     int col0;                    // global position of the first pivot column
     int rows_off;                // into rowg / slots (first na entries = ancestor rows)
     int w, na, ldr;              // ldr = w | 1 (odd leading dimension)
-    int parent;                  // unit of the parent front or -1 (informational)
-    int nchild;
+    int R;                       // rows per full chunk = ps_rows_per_chunk(ldr)   (kept here: the kernel must not divide)
+    int nch;                     // number of chunks = ceil((w + na) / R)
     int front;                   // global front id (FrontDesc index)
 };
 struct SolveUnit {               // a bottom subtree (<= PS_SMAX columns) or one front above the cut; one warp per unit

@@ -857,7 +857,14 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                     const int f = lf->front_base + G.mem_front[(size_t)q];
                     const FrontDesc& fd = fronts[(size_t)f];
                     GroupMember mb;
-                    mb.Lb_off = fd.Loff + fd.w + fd.na; mb.m = fd.w + fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f;
+                    // the member's W21 = L21 D scratch moves from the per-level area to a persistent one: the group SYRK
+                    // runs after the last level and reads (L_B D) from there instead of rebuilding it from L and D
+                    FrontDesc& fdm = fronts[(size_t)f];
+                    fdm.Woff = ctx->Wtot;
+                    const int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
+                    ctx->Wtot += (wsz + 1) & ~int64_t(1);
+                    mb.Lb_off = fd.Loff + fd.w + fd.na; mb.Wb_off = fdm.Woff + fd.na;
+                    mb.m = fd.w + fd.na + fd.nb; mb.u = fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f; mb.pad = 0;
                     gmembers.push_back(mb);
                     const size_t base = ginv.size();
                     ginv.resize(base + (size_t)gd.nblk * GROUP_TILE, -1);
@@ -1010,9 +1017,10 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const FrontDesc& fd = fronts[(size_t)g];
                 SolveFront& f = sf[(size_t)sfi];
                 f.blob = off; f.col0 = fd.col0; f.rows_off = (int)fd.rows_off; f.w = fd.w; f.na = fd.na; f.ldr = fd.w | 1;
-                f.parent = un.parent; f.nchild = fd.child_end - fd.child_begin; f.front = g;
+                f.front = g;
                 const int rows = fd.w + fd.na, R = ps_rows_per_chunk(f.ldr);
                 const int nch = (rows + R - 1) / R;
+                f.R = R; f.nch = nch;
                 for (int c = 0; c < nch; ++c) { chunk_front.push_back(sfi); chunk_idx.push_back(c); }
                 off += ps_front_doubles(f.ldr, rows);
                 for (int t = 0; t < fd.na; ++t) {

@@ -88,6 +88,11 @@ __host__ __device__ int ps_chunk_rows(int ldr, int rows, int c) {
     return rem < R ? ((rem + 3) & ~3) : R;
 }
 __host__ __device__ int ps_chunk_doubles_rows(int ldr, int cr) { return (PS_HDR + cr * ldr + cr / 4 + 1) & ~1; }
+// the same with R known (SolveFront::R): no integer division on the device
+__device__ __forceinline__ int ps_chunk_rows_R(int R, int rows, int c) {
+    const int rem = rows - c * R;
+    return rem < R ? ((rem + 3) & ~3) : R;
+}
 __host__ __device__ int64_t ps_front_doubles(int ldr, int rows) {
     const int R = ps_rows_per_chunk(ldr);
     const int nch = (rows + R - 1) / R;
@@ -111,9 +116,9 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
     const int c = chunk_idx[q];
     const FrontDesc fd = fronts[f.front];
     const int w = f.w, rows = f.w + f.na, m = fd.w + fd.na + fd.nb, ldr = f.ldr;
-    const int R = ps_rows_per_chunk(ldr), CR = ps_chunk_rows(ldr, rows, c);
+    const int R = f.R, CR = ps_chunk_rows_R(R, rows, c);
     const int r0 = c * R, r1 = min(rows, r0 + R);
-    double* dst = SL + f.blob + (size_t)c * ps_chunk_doubles(ldr);
+    double* dst = SL + f.blob + (size_t)c * ps_chunk_doubles_rows(ldr, R);
     // header: z = dd*y + dn*y_next + dp*y_prev  (1x1 and 2x2 pivots without a type switch in the solve)
     if (c == 0) {
         const int p = fd.col0 + lane;
@@ -192,14 +197,23 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
     // ---- issue side: cursor over (ticket, front, chunk) of the next bulk copy; runs at most two chunks ahead ----
     int i_t = draw();            // ticket being issued
     SolveUnit i_unit;
-    SolveFront i_desc;
+    SolveFront i_desc, n_desc;
+    int n_fi = -1;               // front index held in n_desc, or -1
     int i_fr = 0, i_ch = 0, i_nch = 0;     // front position within the unit (processing order), chunk position, #chunks
     auto issue_load_front = [&]() {
         const bool fwd = i_t < nu;
         const int fi = fwd ? i_unit.first + i_fr : i_unit.first + i_unit.nfronts - 1 - i_fr;
-        i_desc = a.sf[fi];
-        const int R = ps_rows_per_chunk(i_desc.ldr);
-        i_nch = (i_desc.w + i_desc.na + R - 1) / R;
+        // the descriptor of the following front of the unit was requested one front ago (n_desc): its load latency
+        // hides behind the processing of a whole front
+        if (n_fi == fi) i_desc = n_desc;
+        else i_desc = a.sf[fi];
+        if (i_fr + 1 < i_unit.nfronts) {
+            n_fi = fwd ? fi + 1 : fi - 1;
+            n_desc = a.sf[n_fi];
+        } else {
+            n_fi = -1;
+        }
+        i_nch = i_desc.nch;
         i_ch = 0;
     };
     auto issue_load_unit = [&]() {
@@ -214,8 +228,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
         const bool fwd = i_t < nu;
         const int c = fwd ? i_ch : i_nch - 1 - i_ch;      // backward: last rows first, the L11 chunk last
         if (lane == 0) {
-            const int cd = ps_chunk_doubles(i_desc.ldr);
-            const uint32_t bytes = (uint32_t)ps_chunk_doubles_rows(i_desc.ldr, ps_chunk_rows(i_desc.ldr, i_desc.w + i_desc.na, c)) * 8u;
+            const int cd = ps_chunk_doubles_rows(i_desc.ldr, i_desc.R);
+            const uint32_t bytes = (uint32_t)ps_chunk_doubles_rows(i_desc.ldr, ps_chunk_rows_R(i_desc.R, i_desc.w + i_desc.na, c)) * 8u;
             s_desc[warp][slot] = i_desc;
             mbar_expect_tx(&bar[slot], bytes);
             bulk_g2s(buf0 + (size_t)slot * PS_BUF, a.SL + i_desc.blob + (int64_t)c * cd, bytes, &bar[slot]);
@@ -294,8 +308,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
             mbar_wait(&bar[slot], slot ? phase1 : phase0);
             const SolveFront f = s_desc[warp][slot];
             const int w = f.w, na = f.na, ldr = f.ldr, rows = w + na;
-            const int R = ps_rows_per_chunk(ldr);
-            const int nc = (rows + R - 1) / R;
+            const int R = f.R;
+            const int nc = f.nch;
             const int crel = f.col0 - pbeg;
             const int* __restrict__ rowg = a.rowg + f.rows_off;
             if (fwd) {
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                     const int r0 = c * R, r1 = min(rows, r0 + R);
                     const double* H = buf0 + (size_t)slot * PS_BUF;
                     const double* B = H + PS_HDR;
-                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows(ldr, rows, c) * ldr);
+                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows_R(R, rows, c) * ldr);
                     if (c > 0) mbar_wait(&bar[slot], slot ? phase1 : phase0);
                     if (slot) phase1 ^= 1; else phase0 ^= 1;
                     int rb = r0;
@@ -364,7 +378,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                     const int rb = max(r0, w);
                     const double* H = buf0 + (size_t)slot * PS_BUF;
                     const double* B = H + PS_HDR;
-                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows(ldr, rows, c) * ldr);
+                    const uint16_t* SLT = reinterpret_cast<const uint16_t*>(B + (size_t)ps_chunk_rows_R(R, rows, c) * ldr);
                     if (cc > 0) mbar_wait(&bar[slot], slot ? phase1 : phase0);
                     if (slot) phase1 ^= 1; else phase0 ^= 1;
                     // x of the ancestor rows of this chunk
