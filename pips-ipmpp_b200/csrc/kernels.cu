@@ -219,62 +219,99 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     COUNT_LAUNCH();
 }
 
-// 32 rows [i0, i0+32) of the panel by one warp:  W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so
-// column tile y only needs A21(:, 0 .. 8y+7)), stored k-major in the scratch; then L21 = W21 D^-1 (block diagonal, 2x2
-// blocks couple neighbouring columns) row by row, written over A21.
+// 32 rows [i0, i0+32) of the panel by one warp:
+//   1. lane = row: the children's contributions are added to the panel in place (the panel is written by its owner only),
+//      8 columns per batch so that the gathers of a batch are independent loads (one round trip per batch, not per column);
+//   2. W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so column tile y only needs A21(:, 0 .. 8y+7));
+//      the A fragments of a k-step feed every column tile that needs them, W21 goes k-major to the scratch;
+//   3. lane = row: L21 = W21 D^-1 (block diagonal, 2x2 blocks couple neighbouring columns), written over A21.
+// The loops stay rolled over the runtime width: a fully unrolled, width-templated version of this code was 188 KB of
+// SASS and ran 2.2x slower on instruction fetch alone (profiles/README.md).
 __device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
                                             double* __restrict__ Wt, const double* __restrict__ X, int i0, int lane) {
+    const unsigned full = 0xffffffffu;
     const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
     const int lr = lane >> 2, lk = lane & 3;
     double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
-    // children's contributions to these 32 panel rows (in place: the panel is written by its owner only)
+    const int i = i0 + lane;
     if (fd.child_end > fd.child_begin) {
-        const int i = i0 + lane;
         for (int c = fd.child_begin; c < fd.child_end; ++c) {
             const ChildRef ch = child_ref(a, c);
             const int ci = (i < u) ? ch.inv[w + i] : -1;
             const int cjl = (lane < w) ? ch.inv[lane] : -1;
-            for (int k = 0; k < w; ++k) {
-                const int cj = __shfl_sync(0xffffffffu, cjl, k);
-                if (cj >= 0 && ci >= 0) A21[(size_t)k * m + i] += ch.C[(size_t)cj * ch.u + ci];
+            for (int kb = 0; kb < w; kb += 8) {
+                double v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int cj = __shfl_sync(full, cjl, kb + q);      // kb + q <= 31; lanes >= w hold -1
+                    v[q] = (cj >= 0 && ci >= 0) ? ch.C[(size_t)cj * ch.u + ci] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (v[q] != 0.0) A21[(size_t)(kb + q) * m + i] += v[q];
             }
         }
         __syncwarp();
     }
-    for (int y = 0; y < wp / 8; ++y) {
-        double aw[4][2];
+    {
+        double aw[4][4][2];                    // [column tile y][row tile x]
 #pragma unroll
-        for (int x = 0; x < 4; ++x) aw[x][0] = aw[x][1] = 0.0;
-        const int kend = (y + 1) * 8;
-        const int n = y * 8 + lr;              // output column of this lane's B fragment
-        for (int k0 = 0; k0 < kend; k0 += 4) {
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) aw[y][x][0] = aw[y][x][1] = 0.0;
+        const int ny = wp >> 3;
+        for (int k0 = 0; k0 < wp; k0 += 4) {
             const int k = k0 + lk;
-            const double bx = X[(size_t)n * wp + k];
+            double af[4];
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                const int i = i0 + x * 8 + lr;
-                const double af = (i < u && k < w) ? A21[(size_t)k * m + i] : 0.0;
-                dmma_m8n8k4(aw[x][0], aw[x][1], af, bx);
+                const int r = i0 + x * 8 + lr;
+                af[x] = (r < u && k < w) ? A21[(size_t)k * m + r] : 0.0;
+            }
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                if (y < ny && k0 < (y + 1) * 8) {
+                    const double bx = X[(size_t)(y * 8 + lr) * wp + k];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) dmma_m8n8k4(aw[y][x][0], aw[y][x][1], af[x], bx);
+                }
             }
         }
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int i = i0 + x * 8 + lr;
-            if (i >= u) continue;
+        for (int y = 0; y < 4; ++y) {
+            if (y < ny) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) Wt[(size_t)(y * 8 + lk * 2 + e) * u + i] = aw[x][e];
+                for (int x = 0; x < 4; ++x) {
+                    const int r = i0 + x * 8 + lr;
+                    if (r < u) {
+                        Wt[(size_t)(y * 8 + lk * 2) * u + r] = aw[y][x][0];
+                        Wt[(size_t)(y * 8 + lk * 2 + 1) * u + r] = aw[y][x][1];
+                    }
+                }
+            }
         }
     }
     __syncwarp();
-    const int i = i0 + lane;
     if (i < u) {
         const int g0 = fd.col0;
-        for (int k = 0; k < w; ++k) {
-            const int t = a.ptype[g0 + k];
-            double l = Wt[(size_t)k * u + i] * a.Did[g0 + k];
-            if (t == 1) l = fma(Wt[(size_t)(k + 1) * u + i], a.Die[g0 + k], l);
-            else if (t == 2) l = fma(Wt[(size_t)(k - 1) * u + i], a.Die[g0 + k - 1], l);
-            A21[(size_t)k * m + i] = l;
+        for (int kb = 0; kb < w; kb += 8) {
+            double wv[10];                     // W21(i, kb-1 .. kb+8): the 2x2 pivots couple neighbouring columns
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+                const int k = kb - 1 + q;
+                wv[q] = (k >= 0 && k < w) ? Wt[(size_t)k * u + i] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = kb + q;
+                if (k < w) {
+                    const int t = a.ptype[g0 + k];
+                    double l = wv[q + 1] * a.Did[g0 + k];
+                    if (t == 1) l = fma(wv[q + 2], a.Die[g0 + k], l);
+                    else if (t == 2) l = fma(wv[q], a.Die[g0 + k - 1], l);
+                    A21[(size_t)k * m + i] = l;
+                }
+            }
         }
     }
 }
@@ -382,7 +419,7 @@ void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream
 
 // big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-__global__ void __launch_bounds__(BF_T) big_panel_kernel(FactorArgs a, int begin) {
+__global__ void __launch_bounds__(BF_T, 3) big_panel_kernel(FactorArgs a, int begin) {
     const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
     const int w = fd.w, u = fd.na + fd.nb;
     double* F = a.L + fd.Loff;
@@ -404,10 +441,13 @@ void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t 
 // C(i,j) -= U(i,j) for ancestor columns j < na, Schur complement -= U(i,j) for border x border (red.global.add.f64).
 // Operands are staged in shared memory (stride 36 doubles: conflict-free m8n8k4 fragment loads).
 // -----------------------------------------------------------------------------------------------------
-constexpr int TLD = 36;
+// Staging layout: k-major, As[k * KLD + r] with KLD = 68: consecutive tile rows of one column are consecutive words
+// (conflict-free stores, coalesced with the column-major panel), and an m8n8k4 fragment load (4 columns x 8 rows per
+// half-warp pair) hits 8*lk + 2*lr: all 32 banks once. (Row-major with stride 36 had 8-way conflicts on the stores.)
+constexpr int KLD = 68;
 __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, int64_t tile_begin) {
-    __shared__ double As[TILE * TLD];
-    __shared__ double Bs[TILE * TLD];
+    __shared__ double As[MAXW * KLD];
+    __shared__ double Bs[MAXW * KLD];
     const TileDesc td = a.tiles[tile_begin + blockIdx.x];
     const FrontDesc fd = a.fronts[td.front];
     const int w = fd.w, na = fd.na, u = fd.na + fd.nb, m = w + u;
@@ -416,11 +456,22 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
     const double* Wscr = a.W + fd.Woff;
     const int i0 = td.bi * TILE, j0 = td.bj * TILE;
     const int tid = threadIdx.x;
+    // the first child's descriptor and inverse indices (three dependent global loads) travel while the operands are
+    // staged and multiplied
+    const bool gather = j0 < na && fd.child_begin < fd.child_end;
+    ChildRef ch0;
+    ch0.C = nullptr; ch0.inv = nullptr; ch0.u = 0;
+    int pre_inv = -1;
+    if (gather) {
+        ch0 = child_ref(a, fd.child_begin);
+        if (tid < TILE) pre_inv = (i0 + tid < u) ? ch0.inv[w + i0 + tid] : -1;
+        else pre_inv = (j0 + tid - TILE < na) ? ch0.inv[w + j0 + tid - TILE] : -1;
+    }
     // A tile: L rows i0.. (column-major panel: coalesced along rows), B tile: W rows j0.. (row-major scratch)
     for (int idx = tid; idx < TILE * wp; idx += 128) {
         const int k = idx >> 6, r = idx & 63;
-        As[r * TLD + k] = (k < w && i0 + r < u) ? F[(size_t)k * m + w + i0 + r] : 0.0;
-        Bs[r * TLD + k] = (j0 + r < u) ? Wscr[(size_t)k * u + j0 + r] : 0.0;
+        As[k * KLD + r] = (k < w && i0 + r < u) ? F[(size_t)k * m + w + i0 + r] : 0.0;
+        Bs[k * KLD + r] = (j0 + r < u) ? Wscr[(size_t)k * u + j0 + r] : 0.0;
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -435,9 +486,9 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
     for (int k0 = 0; k0 < w4; k0 += 4) {
         double af[4], bf[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) af[x] = As[(wr + x * 8 + lr) * TLD + k0 + lk];
+        for (int x = 0; x < 4; ++x) af[x] = As[(k0 + lk) * KLD + wr + x * 8 + lr];
 #pragma unroll
-        for (int y = 0; y < 4; ++y) bf[y] = Bs[(wc + y * 8 + lr) * TLD + k0 + lk];
+        for (int y = 0; y < 4; ++y) bf[y] = Bs[(k0 + lk) * KLD + wc + y * 8 + lr];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -450,14 +501,19 @@ __global__ void __launch_bounds__(128) front_update_tiles_kernel(FactorArgs a, i
 #pragma unroll
         for (int y = 0; y < 4; ++y) { acc[x][y][0] = -acc[x][y][0]; acc[x][y][1] = -acc[x][y][1]; }
     // children's pass-through entries of this tile (ancestor columns only): inverse indices staged in shared memory
-    if (j0 < na) {
+    if (gather) {
         int* s_ci = reinterpret_cast<int*>(As);        // operands are dead: reuse the staging buffers
         int* s_cj = s_ci + TILE;
         for (int c = fd.child_begin; c < fd.child_end; ++c) {
-            const ChildRef ch = child_ref(a, c);
+            const ChildRef ch = (c == fd.child_begin) ? ch0 : child_ref(a, c);
+            int v = pre_inv;
+            if (c != fd.child_begin) {
+                if (tid < TILE) v = (i0 + tid < u) ? ch.inv[w + i0 + tid] : -1;
+                else v = (j0 + tid - TILE < na) ? ch.inv[w + j0 + tid - TILE] : -1;
+            }
             __syncthreads();
-            if (tid < TILE) s_ci[tid] = (i0 + tid < u) ? ch.inv[w + i0 + tid] : -1;
-            else s_cj[tid - TILE] = (j0 + tid - TILE < na) ? ch.inv[w + j0 + tid - TILE] : -1;
+            if (tid < TILE) s_ci[tid] = v;
+            else s_cj[tid - TILE] = v;
             __syncthreads();
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
@@ -503,9 +559,9 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
 // recomputed from L and the block-diagonal D on the fly. One flush (red.global.add.f64) per tile and group instead of
 // one per tile and front: the per-front flush was bound by the RED issue rate (~1.3 cycles per lane and SM).
 // -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
-    __shared__ double As[TILE * TLD];
-    __shared__ double Bs[TILE * TLD];
+__global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
+    __shared__ double As[MAXW * KLD];
+    __shared__ double Bs[MAXW * KLD];
     const GTile td = a.gtiles[gtile_begin + blockIdx.x];
     const GroupDesc g = a.groups[td.group];
     const int tid = threadIdx.x;
@@ -521,56 +577,67 @@ __global__ void __launch_bounds__(128) border_group_kernel(FactorArgs a, int64_t
     const int64_t inv_stride = (int64_t)g.nblk * GROUP_TILE;
     const int* inv_i = a.ginv + g.inv_base + (int64_t)td.bi * GROUP_TILE + r;
     const int* inv_j = a.ginv + g.inv_base + (int64_t)td.bj * GROUP_TILE + r;
-    GroupMember mb = a.gmembers[g.mem_begin];
-    int ti = inv_i[0], tj = inv_j[0];
-    for (int mi = g.mem_begin; mi < g.mem_end; ++mi) {
-        // the next member's descriptor and row maps are requested before this member's panel is staged
+    // gflags[(inv_base / 64) + member * nblk + b] != 0: the member has border rows in block b of the root's index space.
+    // Members without rows in both tile ranges are skipped without touching a barrier.
+    const int8_t* flag_i = a.gflags + g.inv_base / GROUP_TILE + td.bi;
+    const int8_t* flag_j = a.gflags + g.inv_base / GROUP_TILE + td.bj;
+    const int nmem = g.mem_end - g.mem_begin;
+    int q = 0;
+    while (q < nmem && !(flag_i[(int64_t)q * g.nblk] && flag_j[(int64_t)q * g.nblk])) ++q;
+    GroupMember mb;
+    int ti = -1, tj = -1;
+    if (q < nmem) {
+        mb = a.gmembers[g.mem_begin + q];
+        ti = inv_i[(int64_t)q * inv_stride];
+        tj = inv_j[(int64_t)q * inv_stride];
+    }
+    bool first = true;
+    while (q < nmem) {
+        // the next contributing member's descriptor and row maps are requested before this member's panel is staged
+        int qn = q + 1;
+        while (qn < nmem && !(flag_i[(int64_t)qn * g.nblk] && flag_j[(int64_t)qn * g.nblk])) ++qn;
         GroupMember nmb = mb;
         int nti = -1, ntj = -1;
-        if (mi + 1 < g.mem_end) {
-            nmb = a.gmembers[mi + 1];
-            nti = inv_i[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
-            ntj = inv_j[(int64_t)(mi + 1 - g.mem_begin) * inv_stride];
+        if (qn < nmem) {
+            nmb = a.gmembers[g.mem_begin + qn];
+            nti = inv_i[(int64_t)qn * inv_stride];
+            ntj = inv_j[(int64_t)qn * inv_stride];
         }
-        // barrier: the previous member's MMA has read As/Bs; votes: does this member have rows in both tile ranges?
-        // (__syncthreads_or returns a predicate, not the bitwise OR of its arguments: one vote per range)
-        const int any_i = __syncthreads_or(ti >= 0);
-        const int any_j = __syncthreads_or(tj >= 0);
-        if (any_i && any_j) {
-            const int w = mb.w, m = mb.m, u = mb.u;
-            const int w4 = (w + 3) & ~3;
-            const double* Lb = a.L + mb.Lb_off;
-            const double* Wb = a.W + mb.Wb_off;
-            // all loads of a batch of 8 columns are issued before the first one is consumed (the staging is one global
-            // round trip per batch; W = L D comes from the member's persistent panel scratch)
-            for (int kb = 0; kb < w4; kb += 16) {
-                double av[8], bv[8];
+        const int w = mb.w, m = mb.m, u = mb.u;
+        const int w4 = (w + 3) & ~3;
+        const double* Lb = a.L + mb.Lb_off;
+        const double* Wb = a.W + mb.Wb_off;
+        // all loads of a batch of 8 columns are issued before the first one is consumed (the staging is one global
+        // round trip per batch; W = L D comes from the member's persistent panel scratch)
+        for (int kb = 0; kb < w4; kb += 16) {
+            double av[8], bv[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k = kb + kq + 2 * q;
-                    av[q] = (k < w && ti >= 0) ? Lb[(size_t)k * m + ti] : 0.0;
-                    bv[q] = (k < w && tj >= 0) ? Wb[(size_t)k * u + tj] : 0.0;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k = kb + kq + 2 * q;
-                    if (k < w4) { As[r * TLD + k] = av[q]; Bs[r * TLD + k] = bv[q]; }
-                }
+            for (int qq = 0; qq < 8; ++qq) {
+                const int k = kb + kq + 2 * qq;
+                av[qq] = (k < w && ti >= 0) ? Lb[(size_t)k * m + ti] : 0.0;
+                bv[qq] = (k < w && tj >= 0) ? Wb[(size_t)k * u + tj] : 0.0;
             }
-            __syncthreads();
-            for (int k0 = 0; k0 < w4; k0 += 4) {
-                double af[4], bf[4];
+            if (kb == 0 && !first) __syncthreads();      // the previous member's MMA has read As / Bs
 #pragma unroll
-                for (int x = 0; x < 4; ++x) af[x] = As[(wr + x * 8 + lr) * TLD + k0 + lk];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) bf[y] = Bs[(wc + y * 8 + lr) * TLD + k0 + lk];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+            for (int qq = 0; qq < 8; ++qq) {
+                const int k = kb + kq + 2 * qq;
+                if (k < w4) { As[k * KLD + r] = av[qq]; Bs[k * KLD + r] = bv[qq]; }
             }
         }
-        mb = nmb; ti = nti; tj = ntj;
+        first = false;
+        __syncthreads();
+        for (int k0 = 0; k0 < w4; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) af[x] = As[(k0 + lk) * KLD + wr + x * 8 + lr];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) bf[y] = Bs[(k0 + lk) * KLD + wc + y * 8 + lr];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+        }
+        mb = nmb; ti = nti; tj = ntj; q = qn;
     }
     const FrontDesc& rd = a.fronts[g.root];
     const int* rowb = a.rowg + rd.rows_off + rd.na;            // Schur-complement index of every border row of the root

@@ -8,7 +8,7 @@ namespace pipsgpu {
 
 constexpr int MAXW = 32;         // maximum front width (pivot columns); symbolic analysis splits wider supernodes
 constexpr int DENSE_NB = 32;     // block size of the dense root LDL^T
-constexpr int BIG_U = 128;       // fronts with at least this many off-diagonal rows update through the tiled DMMA kernel
+constexpr int BIG_U = 64;        // default big-front threshold (PIPSGPU_BIG_U): fronts with at least this many off-diagonal rows take the CTA-parallel path
 constexpr int TILE = 64;         // output tile of the tiled update
 
 struct TileDesc { int front, bi, bj, grouped; };   // grouped: the border x border part of this front is left to its group
@@ -81,6 +81,7 @@ struct FactorArgs {
     const GroupDesc* groups;
     const GroupMember* gmembers;
     const int* ginv;
+    const int8_t* gflags;        // per (group member, 64-row block of the root's border index space): has rows there
     const GTile* gtiles;
 };
 

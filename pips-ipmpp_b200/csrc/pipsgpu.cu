@@ -160,6 +160,7 @@ struct pipsgpu_ctx {
     DevBuf<GroupDesc> groups;
     DevBuf<GroupMember> gmembers;
     DevBuf<int> ginv;
+    DevBuf<int8_t> gflags;
     DevBuf<GTile> gtiles;
     int64_t ngtiles = 0;
     bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
@@ -200,7 +201,7 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
-        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gtiles = gtiles.p;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -834,6 +835,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     std::vector<GroupDesc> groups;
     std::vector<GroupMember> gmembers;
     std::vector<int> ginv;
+    std::vector<int8_t> gflags;
     std::vector<GTile> gtiles;
     std::vector<char> grouped((size_t)nfr, 0);
     if (ctx->grouping) {
@@ -871,6 +873,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                     const int* pf = G.pos.data() + G.pos_ptr[(size_t)q];
                     if (G.pos_ptr[(size_t)q + 1] - G.pos_ptr[(size_t)q] != fd.nb) throw Error(PIPSGPU_ERR_INVALID, "border group: position map size mismatch");
                     for (int t = 0; t < fd.nb; ++t) ginv[base + (size_t)pf[t]] = t;
+                    gflags.resize(base / GROUP_TILE + (size_t)gd.nblk, 0);
+                    for (int t = 0; t < fd.nb; ++t) gflags[base / GROUP_TILE + (size_t)pf[t] / GROUP_TILE] = 1;
                 }
                 gd.mem_end = (int)gmembers.size();
                 const int gi = (int)groups.size();
@@ -935,7 +939,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
-    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gtiles.upload(gtiles, s);
+    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gflags.upload(gflags, s); ctx->gtiles.upload(gtiles, s);
     ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
