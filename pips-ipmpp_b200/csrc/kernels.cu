@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     // ---- L11 to the panel (unit diagonal) ----
     for (int k = 0; k < w; ++k)
         if (lane < w && lane >= k) F[(size_t)k * m + lane] = (lane == k) ? 1.0 : Pl[lane * PLD + k];
-    if (fd.na + fd.nb == 0) return;
     // ---- X = L11^-1 (lane = column c of X, forward substitution; overwrites W11) ----
     for (int i = 0; i < wp; ++i) {
         double acc = 0.0;
@@ -219,40 +218,108 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     COUNT_LAUNCH();
 }
 
-// 32 rows [i0, i0+32) of the panel by one warp:
-//   1. lane = row: the children's contributions are added to the panel in place (the panel is written by its owner only),
-//      8 columns per batch so that the gathers of a batch are independent loads (one round trip per batch, not per column);
-//   2. W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so column tile y only needs A21(:, 0 .. 8y+7));
-//      the A fragments of a k-step feed every column tile that needs them, W21 goes k-major to the scratch;
-//   3. lane = row: L21 = W21 D^-1 (block diagonal, 2x2 blocks couple neighbouring columns), written over A21.
-// The loops stay rolled over the runtime width: a fully unrolled, width-templated version of this code was 188 KB of
-// SASS and ran 2.2x slower on instruction fetch alone (profiles/README.md).
+// 32 rows [i0, i0+32) of the panel by one warp:  W21 = A21 X^T on the tensor pipe (X = L11^-1 is lower triangular, so
+// column tile y only needs A21(:, 0 .. 8y+7)), stored k-major in the scratch; then L21 = W21 D^-1 (block diagonal, 2x2
+// blocks couple neighbouring columns) row by row, written over A21.
 __device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
                                             double* __restrict__ Wt, const double* __restrict__ X, int i0, int lane) {
+    const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
+    const int lr = lane >> 2, lk = lane & 3;
+    double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
+    // children's contributions to these 32 panel rows (in place: the panel is written by its owner only)
+    if (fd.child_end > fd.child_begin) {
+        const int i = i0 + lane;
+        for (int c = fd.child_begin; c < fd.child_end; ++c) {
+            const ChildRef ch = child_ref(a, c);
+            const int ci = (i < u) ? ch.inv[w + i] : -1;
+            const int cjl = (lane < w) ? ch.inv[lane] : -1;
+            for (int k = 0; k < w; ++k) {
+                const int cj = __shfl_sync(0xffffffffu, cjl, k);
+                if (cj >= 0 && ci >= 0) A21[(size_t)k * m + i] += ch.C[(size_t)cj * ch.u + ci];
+            }
+        }
+        __syncwarp();
+    }
+    for (int y = 0; y < wp / 8; ++y) {
+        double aw[4][2];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) aw[x][0] = aw[x][1] = 0.0;
+        const int kend = (y + 1) * 8;
+        const int n = y * 8 + lr;              // output column of this lane's B fragment
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            const int k = k0 + lk;
+            const double bx = X[(size_t)n * wp + k];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = i0 + x * 8 + lr;
+                const double af = (i < u && k < w) ? A21[(size_t)k * m + i] : 0.0;
+                dmma_m8n8k4(aw[x][0], aw[x][1], af, bx);
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            const int i = i0 + x * 8 + lr;
+            if (i >= u) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Wt[(size_t)(y * 8 + lk * 2 + e) * u + i] = aw[x][e];
+        }
+    }
+    __syncwarp();
+    const int i = i0 + lane;
+    if (i < u) {
+        const int g0 = fd.col0;
+        for (int k = 0; k < w; ++k) {
+            const int t = a.ptype[g0 + k];
+            double l = Wt[(size_t)k * u + i] * a.Did[g0 + k];
+            if (t == 1) l = fma(Wt[(size_t)(k + 1) * u + i], a.Die[g0 + k], l);
+            else if (t == 2) l = fma(Wt[(size_t)(k - 1) * u + i], a.Die[g0 + k - 1], l);
+            A21[(size_t)k * m + i] = l;
+        }
+    }
+}
+
+// The same 32 panel rows with the chunk staged in shared memory (PIPSGPU_PANEL=staged): the in-place version above walks
+// global memory five times per entry (own read-modify-write per child, A fragments, W21 store, W21 reload, L21 store) and
+// is bound by that traffic on the big fronts; here every entry is read once and L21 / W21 are written once.
+//   tile T[k * PKL + r] (k-major, 32 columns x 36): lane = row accesses and m8n8k4 fragment loads are both conflict-free.
+// Loops stay rolled over the runtime width (batches of 8 columns): a fully unrolled, width-templated version of this
+// code was 188 KB of SASS and lost 2.2x on instruction fetch (profiles/README.md).
+constexpr int PKL = 36;
+constexpr int PT_TILE = MAXW * PKL;          // doubles per warp
+__device__ __forceinline__ void panel_chunk_staged(const FactorArgs& a, const FrontDesc& fd, double* __restrict__ F,
+                                                   double* __restrict__ Wt, const double* __restrict__ X,
+                                                   double* __restrict__ T, int i0, int lane) {
     const unsigned full = 0xffffffffu;
     const int w = fd.w, u = fd.na + fd.nb, m = w + u, wp = padded_width(w);
     const int lr = lane >> 2, lk = lane & 3;
     double* A21 = F + w;                       // A21(i,k) = A21[k*m + i]
     const int i = i0 + lane;
-    if (fd.child_end > fd.child_begin) {
-        for (int c = fd.child_begin; c < fd.child_end; ++c) {
-            const ChildRef ch = child_ref(a, c);
-            const int ci = (i < u) ? ch.inv[w + i] : -1;
-            const int cjl = (lane < w) ? ch.inv[lane] : -1;
-            for (int kb = 0; kb < w; kb += 8) {
-                double v[8];
+    // 1. lane = row: own entries (zero padded to wp columns), then the children's contributions, into the tile
+    for (int kb = 0; kb < wp; kb += 8) {
+        double v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int cj = __shfl_sync(full, cjl, kb + q);      // kb + q <= 31; lanes >= w hold -1
-                    v[q] = (cj >= 0 && ci >= 0) ? ch.C[(size_t)cj * ch.u + ci] : 0.0;
-                }
+        for (int q = 0; q < 8; ++q) v[q] = (kb + q < w && i < u) ? A21[(size_t)(kb + q) * m + i] : 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (v[q] != 0.0) A21[(size_t)(kb + q) * m + i] += v[q];
-            }
-        }
-        __syncwarp();
+        for (int q = 0; q < 8; ++q) T[(kb + q) * PKL + lane] = v[q];
     }
+    for (int c = fd.child_begin; c < fd.child_end; ++c) {
+        const ChildRef ch = child_ref(a, c);
+        const int ci = (i < u) ? ch.inv[w + i] : -1;
+        const int cjl = (lane < w) ? ch.inv[lane] : -1;
+        for (int kb = 0; kb < w; kb += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int cj = __shfl_sync(full, cjl, kb + q);      // kb + q <= 31; lanes >= w hold -1
+                v[q] = (cj >= 0 && ci >= 0) ? ch.C[(size_t)cj * ch.u + ci] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (v[q] != 0.0) T[(kb + q) * PKL + lane] += v[q];
+        }
+    }
+    __syncwarp();
+    // 2. W21 = A21 X^T on the tensor pipe: the A fragments of a k-step feed every column tile that needs them
     {
         double aw[4][4][2];                    // [column tile y][row tile x]
 #pragma unroll
@@ -261,64 +328,58 @@ __device__ __forceinline__ void panel_chunk(const FactorArgs& a, const FrontDesc
             for (int x = 0; x < 4; ++x) aw[y][x][0] = aw[y][x][1] = 0.0;
         const int ny = wp >> 3;
         for (int k0 = 0; k0 < wp; k0 += 4) {
-            const int k = k0 + lk;
             double af[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int r = i0 + x * 8 + lr;
-                af[x] = (r < u && k < w) ? A21[(size_t)k * m + r] : 0.0;
-            }
+            for (int x = 0; x < 4; ++x) af[x] = T[(k0 + lk) * PKL + x * 8 + lr];
 #pragma unroll
             for (int y = 0; y < 4; ++y) {
                 if (y < ny && k0 < (y + 1) * 8) {
-                    const double bx = X[(size_t)(y * 8 + lr) * wp + k];
+                    const double bx = X[(size_t)(y * 8 + lr) * wp + k0 + lk];
 #pragma unroll
                     for (int x = 0; x < 4; ++x) dmma_m8n8k4(aw[y][x][0], aw[y][x][1], af[x], bx);
                 }
             }
         }
+        __syncwarp();                          // every lane has read its A fragments: W21 may overwrite the tile
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
             if (y < ny) {
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
-                    const int r = i0 + x * 8 + lr;
-                    if (r < u) {
-                        Wt[(size_t)(y * 8 + lk * 2) * u + r] = aw[y][x][0];
-                        Wt[(size_t)(y * 8 + lk * 2 + 1) * u + r] = aw[y][x][1];
-                    }
+                    T[(y * 8 + lk * 2) * PKL + x * 8 + lr] = aw[y][x][0];
+                    T[(y * 8 + lk * 2 + 1) * PKL + x * 8 + lr] = aw[y][x][1];
                 }
             }
         }
     }
     __syncwarp();
+    // 3. lane = row: L21 = W21 D^-1 to the panel, W21 (zero padded to wp columns) to the scratch of the update kernels
     if (i < u) {
         const int g0 = fd.col0;
-        for (int kb = 0; kb < w; kb += 8) {
-            double wv[10];                     // W21(i, kb-1 .. kb+8): the 2x2 pivots couple neighbouring columns
-#pragma unroll
-            for (int q = 0; q < 10; ++q) {
-                const int k = kb - 1 + q;
-                wv[q] = (k >= 0 && k < w) ? Wt[(size_t)k * u + i] : 0.0;
-            }
+        for (int kb = 0; kb < wp; kb += 8) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int k = kb + q;
+                const double wk = T[k * PKL + lane];
+                Wt[(size_t)k * u + i] = wk;
                 if (k < w) {
                     const int t = a.ptype[g0 + k];
-                    double l = wv[q + 1] * a.Did[g0 + k];
-                    if (t == 1) l = fma(wv[q + 2], a.Die[g0 + k], l);
-                    else if (t == 2) l = fma(wv[q], a.Die[g0 + k - 1], l);
+                    double l = wk * a.Did[g0 + k];
+                    if (t == 1) l = fma(T[(k + 1) * PKL + lane], a.Die[g0 + k], l);
+                    else if (t == 2) l = fma(T[(k - 1) * PKL + lane], a.Die[g0 + k - 1], l);
                     A21[(size_t)k * m + i] = l;
                 }
             }
         }
     }
+    __syncwarp();                              // the tile is reused by the next chunk
 }
 
 constexpr int SF_WARPS = 4;   // small fronts per CTA (one warp each)
 
+template <bool STAGED>
 __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorArgs a, int begin, int nfronts) {
+    extern __shared__ double sf_smem[];        // STAGED: one panel tile per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * SF_WARPS + warp;
     if (fi >= nfronts) return;
@@ -328,7 +389,10 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
     double* F = a.L + fd.Loff;
     double* Wt = a.W + fd.Woff;                // W21(j,k) = Wt[k*u + j]
     const double* X = a.XY + fd.XYoff;
-    for (int i0 = 0; i0 < u; i0 += 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
+    for (int i0 = 0; i0 < u; i0 += 32) {
+        if (STAGED) panel_chunk_staged(a, fd, F, Wt, X, sf_smem + warp * PT_TILE, i0, lane);
+        else panel_chunk(a, fd, F, Wt, X, i0, lane);
+    }
     __syncwarp();
     // ---- update: U = L21 * W21^T in 32x32 blocks (16 m8n8k4 tiles per warp); C = children's pass-through - U ----
     double* Cs = a.C + fd.Coff;
@@ -413,25 +477,42 @@ __global__ void __launch_bounds__(SF_WARPS * 32, 4) small_fronts_kernel(FactorAr
 }
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    small_fronts_kernel<<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, 0, s>>>(a, begin, nfronts);
+    if (a.panel_staged)
+        small_fronts_kernel<true><<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, SF_WARPS * PT_TILE * sizeof(double), s>>>(a, begin, nfronts);
+    else
+        small_fronts_kernel<false><<<cdiv(nfronts, SF_WARPS), SF_WARPS * 32, 0, s>>>(a, begin, nfronts);
     COUNT_LAUNCH();
 }
 
 // big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-__global__ void __launch_bounds__(BF_T, 3) big_panel_kernel(FactorArgs a, int begin) {
+template <bool STAGED>
+__global__ void __launch_bounds__(BF_T, STAGED ? 2 : 4) big_panel_kernel(FactorArgs a, int begin) {
+    extern __shared__ double bp_smem[];        // STAGED: one panel tile per warp
     const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
-    const int w = fd.w, u = fd.na + fd.nb;
+    const int u = fd.na + fd.nb;
     double* F = a.L + fd.Loff;
     double* Wt = a.W + fd.Woff;
     const double* X = a.XY + fd.XYoff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    (void)w;
-    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) panel_chunk(a, fd, F, Wt, X, i0, lane);
+    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) {
+        if (STAGED) panel_chunk_staged(a, fd, F, Wt, X, bp_smem + warp * PT_TILE, i0, lane);
+        else panel_chunk(a, fd, F, Wt, X, i0, lane);
+    }
 }
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
-    big_panel_kernel<<<nfronts, BF_T, 0, s>>>(a, begin);
+    if (a.panel_staged) {
+        constexpr int smem = (BF_T / 32) * PT_TILE * (int)sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(big_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        big_panel_kernel<true><<<nfronts, BF_T, smem, s>>>(a, begin);
+    } else {
+        big_panel_kernel<false><<<nfronts, BF_T, 0, s>>>(a, begin);
+    }
     COUNT_LAUNCH();
 }
 
@@ -559,7 +640,17 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
 // recomputed from L and the block-diagonal D on the fly. One flush (red.global.add.f64) per tile and group instead of
 // one per tile and front: the per-front flush was bound by the RED issue rate (~1.3 cycles per lane and SM).
 // -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
+// one staging batch of a member: columns k0, k0+2, .., k0+14 of tile rows ti (L_B) and tj (L_B D)
+#define GROUP_LOAD_BATCH(Lb_, Wb_, m_, u_, w_, ti_, tj_, k0_, av_, bv_)                       \
+    _Pragma("unroll") for (int qq = 0; qq < 8; ++qq) {                                        \
+        const int k_ = (k0_) + 2 * qq;                                                        \
+        av_[qq] = (k_ < (w_) && (ti_) >= 0) ? (Lb_)[(size_t)k_ * (m_) + (ti_)] : 0.0;         \
+        bv_[qq] = (k_ < (w_) && (tj_) >= 0) ? (Wb_)[(size_t)k_ * (u_) + (tj_)] : 0.0;         \
+    }
+// PIPE (PIPSGPU_GROUP_PIPE=1): the first batch of the NEXT contributing member is loaded into registers before the MMA of
+// the current one, so the global round trip of the staging overlaps the tensor work and the barriers.
+template <bool PIPE>
+__global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
     __shared__ double As[MAXW * KLD];
     __shared__ double Bs[MAXW * KLD];
     const GTile td = a.gtiles[gtile_begin + blockIdx.x];
@@ -592,6 +683,12 @@ __global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int6
         tj = inv_j[(int64_t)q * inv_stride];
     }
     bool first = true;
+    double pav[8], pbv[8];
+    if (PIPE && q < nmem) {
+        const double* Lb0 = a.L + mb.Lb_off;
+        const double* Wb0 = a.W + mb.Wb_off;
+        GROUP_LOAD_BATCH(Lb0, Wb0, mb.m, mb.u, mb.w, ti, tj, kq, pav, pbv)
+    }
     while (q < nmem) {
         // the next contributing member's descriptor and row maps are requested before this member's panel is staged
         int qn = q + 1;
@@ -611,11 +708,11 @@ __global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int6
         // round trip per batch; W = L D comes from the member's persistent panel scratch)
         for (int kb = 0; kb < w4; kb += 16) {
             double av[8], bv[8];
+            if (PIPE && kb == 0) {
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) {
-                const int k = kb + kq + 2 * qq;
-                av[qq] = (k < w && ti >= 0) ? Lb[(size_t)k * m + ti] : 0.0;
-                bv[qq] = (k < w && tj >= 0) ? Wb[(size_t)k * u + tj] : 0.0;
+                for (int qq = 0; qq < 8; ++qq) { av[qq] = pav[qq]; bv[qq] = pbv[qq]; }
+            } else {
+                GROUP_LOAD_BATCH(Lb, Wb, m, u, w, ti, tj, kb + kq, av, bv)
             }
             if (kb == 0 && !first) __syncthreads();      // the previous member's MMA has read As / Bs
 #pragma unroll
@@ -626,6 +723,11 @@ __global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int6
         }
         first = false;
         __syncthreads();
+        if (PIPE && qn < nmem) {
+            const double* Lbn = a.L + nmb.Lb_off;
+            const double* Wbn = a.W + nmb.Wb_off;
+            GROUP_LOAD_BATCH(Lbn, Wbn, nmb.m, nmb.u, nmb.w, nti, ntj, kq, pav, pbv)
+        }
         for (int k0 = 0; k0 < w4; k0 += 4) {
             double af[4], bf[4];
 #pragma unroll
@@ -660,7 +762,8 @@ __global__ void __launch_bounds__(128, 4) border_group_kernel(FactorArgs a, int6
 }
 void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
     if (ngtiles <= 0 || !a.SC) return;
-    border_group_kernel<<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    if (a.group_pipe) border_group_kernel<true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    else border_group_kernel<false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
     COUNT_LAUNCH();
 }
 

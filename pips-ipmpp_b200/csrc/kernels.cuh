@@ -81,6 +81,8 @@ struct FactorArgs {
     const GroupDesc* groups;
     const GroupMember* gmembers;
     const int* ginv;
+    int group_pipe;              // PIPSGPU_GROUP_PIPE=1: software-pipelined member staging in border_group_kernel
+    int panel_staged;            // PIPSGPU_PANEL=staged: panel chunks staged in shared memory (kernels.cu: panel_chunk_staged)
     const int8_t* gflags;        // per (group member, 64-row block of the root's border index space): has rows there
     const GTile* gtiles;
 };
@@ -139,6 +141,7 @@ struct PStreamArgs {
     int* ticket;                 // [0] next ticket, [1] warps that have left (re-arms [0] for the next launch)
     int epoch;
     int out_mode;                // 0: out = K^-1 in, 1: out -= K^-1 in
+    int xform;                   // 1: the pool's pivot-block rows hold X = L11^-1 (unit lower) instead of L11
 };
 __host__ __device__ int ps_rows_per_chunk(int ldr);
 __host__ __device__ int ps_chunk_doubles(int ldr);
@@ -148,7 +151,7 @@ __host__ __device__ int64_t ps_front_doubles(int ldr, int rows);
 void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s);
 void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* chunk_idx, int nchunks, const FrontDesc* fronts,
                        const double* L, const double* Did, const double* Die, const int8_t* ptype, const uint16_t* slots,
-                       double* SL, cudaStream_t s);
+                       double* SL, const double* XY, cudaStream_t s);   // XY != null: pivot-block rows = X = L11^-1
 void count_launch();
 
 // ---- leaf path ----

@@ -169,6 +169,11 @@ struct pipsgpu_ctx {
     // side stream: the small fronts of a level run next to the big-front panel / tile kernels of the same level, and the
     // border-group SYRKs next to pack_solve (PIPSGPU_OVERLAP=0 keeps everything on one stream)
     bool overlap = true;
+    // PIPSGPU_XFORM=1: the solve pool carries X = L11^-1 instead of L11, the streaming solve applies the pivot blocks as
+    // two small matrix-vector products (no serial substitution chain); X scratch is then persistent per front
+    bool xform = false;
+    bool panel_staged = false;      // PIPSGPU_PANEL=staged
+    bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf<double> XY;
@@ -201,7 +206,7 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
-        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -216,7 +221,7 @@ struct pipsgpu_ctx {
         PStreamArgs a;
         a.sf = sfront.p; a.units = sunits.p; a.nunits = nunits; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p;
         a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.ucnt = ucnt.p; a.uflag = uflag.p; a.ticket = ticket.p;
-        a.epoch = ps_epoch; a.out_mode = out_mode;
+        a.epoch = ps_epoch; a.out_mode = out_mode; a.xform = xform ? 1 : 0;
         launch_psolve_stream(a, sm_count, stream);
         ps_epoch += 1;
     }
@@ -224,7 +229,8 @@ struct pipsgpu_ctx {
     bool solve_by_level = false;
     // factor panels -> solve pool (after every numeric factorisation)
     void pack_solve() {
-        launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p, stream);
+        launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p,
+                          xform ? XY.p : nullptr, stream);
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
         SolveArgs a;
@@ -481,6 +487,9 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
     if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
     if (const char* e = std::getenv("PIPSGPU_OVERLAP")) ctx->overlap = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_XFORM")) ctx->xform = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_PANEL")) ctx->panel_staged = std::string(e) == "staged";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_PIPE")) ctx->group_pipe = std::string(e) != "0";
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -746,8 +755,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
-            fd.XYoff = xyfill[ol];
-            xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
+            if (ctx->xform) {      // persistent: pack_solve reads X after the last level
+                fd.XYoff = ctx->XYtot;
+                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w);
+            } else {
+                fd.XYoff = xyfill[ol];
+                xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
+            }
         }
         for (size_t t = 0; t < S.rowidx.size(); ++t) {
             const int r = S.rowidx[t];
@@ -807,8 +821,10 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
-    ctx->XYtot = 0;
-    for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
+    if (!ctx->xform) {
+        ctx->XYtot = 0;
+        for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
+    }
     // ---- factorisation launch lists: fronts grouped by (level, small|big), by leaf inside a group ----
     std::vector<int> fl_fronts((size_t)nfr);
     {

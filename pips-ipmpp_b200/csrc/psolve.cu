@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
                                                          const FrontDesc* __restrict__ fronts, const double* __restrict__ L,
                                                          const double* __restrict__ Did, const double* __restrict__ Die,
                                                          const int8_t* __restrict__ ptype, const uint16_t* __restrict__ slots,
-                                                         double* __restrict__ SL) {
+                                                         double* __restrict__ SL, const double* __restrict__ XY) {
     __shared__ double tile[4][32 * 33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + warp;
@@ -144,7 +144,11 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
         for (int idx = lane; idx < total; idx += 32) {
             const int r = idx / ldr, k = idx - r * ldr;
             double v = (k < w) ? T[r * 33 + k] : 0.0;
-            if (s0 + r < w && k > s0 + r) v = 0.0;      // strict upper part of L11 (the unit diagonal is stored as 1)
+            if (s0 + r < w) {
+                const int pr = s0 + r;                  // pivot-block row: L11 (or X = L11^-1), unit diagonal, zeros above
+                if (k > pr) v = 0.0;
+                else if (XY && k < pr) v = XY[fd.XYoff + (size_t)pr * padded_width(w) + k];
+            }
             d2[idx] = v;
         }
     }
@@ -156,9 +160,9 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
 
 void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* chunk_idx, int nchunks, const FrontDesc* fronts,
                        const double* L, const double* Did, const double* Die, const int8_t* ptype, const uint16_t* slots,
-                       double* SL, cudaStream_t s) {
+                       double* SL, const double* XY, cudaStream_t s) {
     if (nchunks <= 0) return;
-    pack_solve_kernel<<<(nchunks + 3) / 4, 128, 0, s>>>(sf, chunk_front, chunk_idx, nchunks, fronts, L, Did, Die, ptype, slots, SL);
+    pack_solve_kernel<<<(nchunks + 3) / 4, 128, 0, s>>>(sf, chunk_front, chunk_idx, nchunks, fronts, L, Did, Die, ptype, slots, SL, XY);
     count_launch();
 }
 
@@ -324,9 +328,25 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                     int rb = r0;
                     if (c == 0) {
                         // y = L11^-1 y : lane i owns row i
-                        for (int k = 0; k < w; ++k) {
-                            const double yk = __shfl_sync(full, y, k);
-                            if (lane > k && lane < w) y = fma(-B[lane * ldr + k], yk, y);
+                        if (a.xform) {
+                            // the pool holds X = L11^-1: one small matrix-vector product, no substitution chain
+                            sy[lane] = y;
+                            __syncwarp();
+                            const double* xr = B + lane * ldr;      // lanes >= w read rows below the pivot block: discarded
+                            double t0 = 0.0, t1 = 0.0;
+                            int k = 0;
+                            for (; k + 2 <= w; k += 2) {
+                                t0 = fma(xr[k], sy[k], t0);
+                                t1 = fma(xr[k + 1], sy[k + 1], t1);
+                            }
+                            if (k < w) t0 = fma(xr[k], sy[k], t0);
+                            __syncwarp();
+                            y = (lane < w) ? t0 + t1 : 0.0;
+                        } else {
+                            for (int k = 0; k < w; ++k) {
+                                const double yk = __shfl_sync(full, y, k);
+                                if (lane > k && lane < w) y = fma(-B[lane * ldr + k], yk, y);
+                            }
                         }
                         sy[lane] = y;
                         // x = D^-1 y (1x1 and 2x2 pivots; pairs never straddle a front)
@@ -402,9 +422,24 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                         tt -= s;
                         if (lane >= w) tt = 0.0;
                         // x = L11^-T t : lane j owns column j
-                        for (int kk = w - 1; kk > 0; --kk) {
-                            const double xk = __shfl_sync(full, tt, kk);
-                            if (lane < kk) tt = fma(-B[kk * ldr + lane], xk, tt);
+                        if (a.xform) {
+                            // x_j = sum_k X(k,j) t_k (rows of X have zeros right of the diagonal); lanes >= w: discarded
+                            sy[lane] = tt;
+                            __syncwarp();
+                            double t0 = 0.0, t1 = 0.0;
+                            int kk = 0;
+                            for (; kk + 2 <= w; kk += 2) {
+                                t0 = fma(B[kk * ldr + lane], sy[kk], t0);
+                                t1 = fma(B[(kk + 1) * ldr + lane], sy[kk + 1], t1);
+                            }
+                            if (kk < w) t0 = fma(B[kk * ldr + lane], sy[kk], t0);
+                            __syncwarp();
+                            tt = (lane < w) ? t0 + t1 : 0.0;
+                        } else {
+                            for (int kk = w - 1; kk > 0; --kk) {
+                                const double xk = __shfl_sync(full, tt, kk);
+                                if (lane < kk) tt = fma(-B[kk * ldr + lane], xk, tt);
+                            }
                         }
                         if (lane < w) xs[crel + lane] = tt;
                     }
