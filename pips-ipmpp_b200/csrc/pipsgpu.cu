@@ -171,7 +171,7 @@ struct pipsgpu_ctx {
     bool overlap = true;
     // PIPSGPU_XFORM=1: the solve pool carries X = L11^-1 instead of L11, the streaming solve applies the pivot blocks as
     // two small matrix-vector products (no serial substitution chain); X scratch is then persistent per front
-    bool xform = false;
+    bool xform = true;
     bool panel_staged = false;      // PIPSGPU_PANEL=staged
     bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
     cudaStream_t stream2 = nullptr;
