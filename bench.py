@@ -26,6 +26,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own log (version banner, NCCL_DEBUG=INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402

@@ -137,18 +137,23 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
     for (int s0 = r0; s0 < r1; s0 += 32) {
         const int nr = min(32, r1 - s0);
         __syncwarp();
-        for (int k = 0; k < w; ++k) T[lane * 33 + k] = (lane < nr) ? F[(size_t)k * m + s0 + lane] : 0.0;
+        // pivot-block rows (only in the first slab of chunk 0) take X = L11^-1 below the diagonal when XY is given;
+        // lane = row, the loads of one row are independent of each other
+        const int pr = s0 + lane;
+        const bool xrow = XY != nullptr && pr < w;
+        const double* Xr = XY ? XY + fd.XYoff + (size_t)(xrow ? pr : 0) * padded_width(w) : nullptr;
+        for (int k = 0; k < w; ++k) {
+            double v = 0.0;
+            if (lane < nr) v = (xrow && k < pr) ? Xr[k] : F[(size_t)k * m + s0 + lane];
+            T[lane * 33 + k] = v;
+        }
         __syncwarp();
         double* d2 = rowsdst + (size_t)(s0 - r0) * ldr;
         const int total = nr * ldr;
         for (int idx = lane; idx < total; idx += 32) {
             const int r = idx / ldr, k = idx - r * ldr;
             double v = (k < w) ? T[r * 33 + k] : 0.0;
-            if (s0 + r < w) {
-                const int pr = s0 + r;                  // pivot-block row: L11 (or X = L11^-1), unit diagonal, zeros above
-                if (k > pr) v = 0.0;
-                else if (XY && k < pr) v = XY[fd.XYoff + (size_t)pr * padded_width(w) + k];
-            }
+            if (s0 + r < w && k > s0 + r) v = 0.0;      // pivot-block row (L11 or X): unit diagonal, zeros above it
             d2[idx] = v;
         }
     }
