@@ -137,15 +137,17 @@ __global__ void __launch_bounds__(128) pack_solve_kernel(const SolveFront* __res
     for (int s0 = r0; s0 < r1; s0 += 32) {
         const int nr = min(32, r1 - s0);
         __syncwarp();
-        // pivot-block rows (only in the first slab of chunk 0) take X = L11^-1 below the diagonal when XY is given;
-        // lane = row, the loads of one row are independent of each other
-        const int pr = s0 + lane;
-        const bool xrow = XY != nullptr && pr < w;
-        const double* Xr = XY ? XY + fd.XYoff + (size_t)(xrow ? pr : 0) * padded_width(w) : nullptr;
-        for (int k = 0; k < w; ++k) {
-            double v = 0.0;
-            if (lane < nr) v = (xrow && k < pr) ? Xr[k] : F[(size_t)k * m + s0 + lane];
-            T[lane * 33 + k] = v;
+        for (int k = 0; k < w; ++k) T[lane * 33 + k] = (lane < nr) ? F[(size_t)k * m + s0 + lane] : 0.0;
+        if (XY != nullptr && s0 == 0) {
+            // pivot-block rows (first slab of chunk 0): X = L11^-1 replaces L11 below the diagonal. X is a contiguous
+            // wp x wp row-major block: read it coalesced and scatter it into the tile.
+            const int wp = padded_width(w), sh = (wp == 8) ? 3 : (wp == 16 ? 4 : 5);
+            const double* Xf = XY + fd.XYoff;
+            __syncwarp();
+            for (int idx = lane; idx < w * wp; idx += 32) {
+                const int xr = idx >> sh, xk = idx & (wp - 1);
+                if (xk < xr) T[xr * 33 + xk] = Xf[idx];
+            }
         }
         __syncwarp();
         double* d2 = rowsdst + (size_t)(s0 - r0) * ldr;
