@@ -339,8 +339,17 @@ def main():
                  "stage1_only_GBps": cnt["B1"] / t_leaf / 1e9,
                  "stored_factor_GBps": 8.0 * (pools["L"] + 2 * pools["C"]) / t_leaf / 1e9,
                  "credited_F1_F2_tflops": (cnt["F1"] + cnt["F2"]) / t_leaf / 1e12}
-    roofline = roof_solve if roof_solve["share_of_step"] >= roof_leaf["share_of_step"] else roof_leaf
-    roofline_other = roof_leaf if roofline is roof_solve else roof_solve
+    # the single dominant KERNEL of the step is the streaming solve (16 launches); the leaf stage is a set of ~100 launches
+    # of five kernels and is reported next to it
+    roofline, roofline_other = roof_solve, roof_leaf
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")) as f:
+            tr = json.load(f)["psolve_stream_kernel"]
+        if args.config == "C2" and (hi - lo) == 64:      # the capture was taken on this workload
+            roof_solve["traffic"] = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+            roof_solve["traffic_source"] = "profiles/r1/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception:
+        pass
     t_root = stage_ms["root_ldlt"] * 1e-3
     schur_tflops = (cnt["F2"] + cnt["F3"]) / (t_leaf + t_root) / 1e12
     nbytes = 8
