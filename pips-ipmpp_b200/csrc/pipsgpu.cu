@@ -80,16 +80,6 @@ struct CsrDev {
     }
 };
 
-struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    void init() {
-        if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    }
-    ~Timer() {
-        if (a) { cudaEventDestroy(a); cudaEventDestroy(b); }
-    }
-};
-
 }  // namespace
 
 // ============================================================================================================

@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
 
     // ---- issue side: cursor over (ticket, front, chunk) of the next bulk copy; runs at most two chunks ahead ----
     int i_t = draw();            // ticket being issued
-    SolveUnit i_unit;
-    SolveFront i_desc, n_desc;
+    SolveUnit i_unit = {};
+    SolveFront i_desc = {}, n_desc = {};
     int n_fi = -1;               // front index held in n_desc, or -1
     int i_fr = 0, i_ch = 0, i_nch = 0;     // front position within the unit (processing order), chunk position, #chunks
     auto issue_load_front = [&]() {
