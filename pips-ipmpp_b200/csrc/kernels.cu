@@ -486,8 +486,9 @@ void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream
 
 // big fronts: one CTA per front, every warp takes 32-row chunks of the panel
 constexpr int BF_T = 256;
-template <bool STAGED>
-__global__ void __launch_bounds__(BF_T, STAGED ? 2 : 4) big_panel_kernel(FactorArgs a, int begin) {
+template <bool STAGED, int THREADS>
+__global__ void __launch_bounds__(THREADS, STAGED ? (THREADS == 256 ? 2 : 4) : (THREADS == 256 ? 4 : 8))
+big_panel_kernel(FactorArgs a, int begin) {
     extern __shared__ double bp_smem[];        // STAGED: one panel tile per warp
     const FrontDesc fd = a.fronts[a.fl_fronts[begin + blockIdx.x]];
     const int u = fd.na + fd.nb;
@@ -495,23 +496,26 @@ __global__ void __launch_bounds__(BF_T, STAGED ? 2 : 4) big_panel_kernel(FactorA
     double* Wt = a.W + fd.Woff;
     const double* X = a.XY + fd.XYoff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i0 = warp * 32; i0 < u; i0 += (BF_T / 32) * 32) {
+    for (int i0 = warp * 32; i0 < u; i0 += THREADS) {
         if (STAGED) panel_chunk_staged(a, fd, F, Wt, X, bp_smem + warp * PT_TILE, i0, lane);
         else panel_chunk(a, fd, F, Wt, X, i0, lane);
     }
 }
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
+    const bool small_cta = a.bp_threads == 128;      // PIPSGPU_BP_THREADS=128
     if (a.panel_staged) {
-        constexpr int smem = (BF_T / 32) * PT_TILE * (int)sizeof(double);
+        const int smem = ((small_cta ? 128 : BF_T) / 32) * PT_TILE * (int)sizeof(double);
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(big_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(big_panel_kernel<true, BF_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BF_T / 32) * PT_TILE * (int)sizeof(double));
             attr_set = true;
         }
-        big_panel_kernel<true><<<nfronts, BF_T, smem, s>>>(a, begin);
+        if (small_cta) big_panel_kernel<true, 128><<<nfronts, 128, smem, s>>>(a, begin);
+        else big_panel_kernel<true, BF_T><<<nfronts, BF_T, smem, s>>>(a, begin);
     } else {
-        big_panel_kernel<false><<<nfronts, BF_T, 0, s>>>(a, begin);
+        if (small_cta) big_panel_kernel<false, 128><<<nfronts, 128, 0, s>>>(a, begin);
+        else big_panel_kernel<false, BF_T><<<nfronts, BF_T, 0, s>>>(a, begin);
     }
     COUNT_LAUNCH();
 }
@@ -649,7 +653,9 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
     }
 // PIPE (PIPSGPU_GROUP_PIPE=1): the first batch of the NEXT contributing member is loaded into registers before the MMA of
 // the current one, so the global round trip of the staging overlaps the tensor work and the barriers.
-template <bool PIPE>
+// LISTS (PIPSGPU_GROUP_LISTS=1): the contributing members of the tile come from a host-built list instead of a scan of the
+// per-member block flags.
+template <bool PIPE, bool LISTS>
 __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
     __shared__ double As[MAXW * KLD];
     __shared__ double Bs[MAXW * KLD];
@@ -672,15 +678,23 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
     // Members without rows in both tile ranges are skipped without touching a barrier.
     const int8_t* flag_i = a.gflags + g.inv_base / GROUP_TILE + td.bi;
     const int8_t* flag_j = a.gflags + g.inv_base / GROUP_TILE + td.bj;
-    const int nmem = g.mem_end - g.mem_begin;
-    int q = 0;
-    while (q < nmem && !(flag_i[(int64_t)q * g.nblk] && flag_j[(int64_t)q * g.nblk])) ++q;
+    // cursor over the contributing members: an index into the tile's list (LISTS) or a member index (flag scan)
+    const int* list = LISTS ? a.gt_list + a.gt_ptr[gtile_begin + blockIdx.x] : nullptr;
+    const int nmem = LISTS ? (int)(a.gt_ptr[gtile_begin + blockIdx.x + 1] - a.gt_ptr[gtile_begin + blockIdx.x])
+                           : g.mem_end - g.mem_begin;
+    auto skip = [&](int c) {
+        if (!LISTS)
+            while (c < nmem && !(flag_i[(int64_t)c * g.nblk] && flag_j[(int64_t)c * g.nblk])) ++c;
+        return c;
+    };
+    int q = skip(0);
     GroupMember mb;
     int ti = -1, tj = -1;
     if (q < nmem) {
-        mb = a.gmembers[g.mem_begin + q];
-        ti = inv_i[(int64_t)q * inv_stride];
-        tj = inv_j[(int64_t)q * inv_stride];
+        const int qm = LISTS ? list[q] : q;
+        mb = a.gmembers[g.mem_begin + qm];
+        ti = inv_i[(int64_t)qm * inv_stride];
+        tj = inv_j[(int64_t)qm * inv_stride];
     }
     bool first = true;
     double pav[8], pbv[8];
@@ -691,14 +705,14 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
     }
     while (q < nmem) {
         // the next contributing member's descriptor and row maps are requested before this member's panel is staged
-        int qn = q + 1;
-        while (qn < nmem && !(flag_i[(int64_t)qn * g.nblk] && flag_j[(int64_t)qn * g.nblk])) ++qn;
+        const int qn = skip(q + 1);
         GroupMember nmb = mb;
         int nti = -1, ntj = -1;
         if (qn < nmem) {
-            nmb = a.gmembers[g.mem_begin + qn];
-            nti = inv_i[(int64_t)qn * inv_stride];
-            ntj = inv_j[(int64_t)qn * inv_stride];
+            const int qm = LISTS ? list[qn] : qn;
+            nmb = a.gmembers[g.mem_begin + qm];
+            nti = inv_i[(int64_t)qm * inv_stride];
+            ntj = inv_j[(int64_t)qm * inv_stride];
         }
         const int w = mb.w, m = mb.m, u = mb.u;
         const int w4 = (w + 3) & ~3;
@@ -762,8 +776,13 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
 }
 void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
     if (ngtiles <= 0 || !a.SC) return;
-    if (a.group_pipe) border_group_kernel<true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-    else border_group_kernel<false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    if (a.group_lists) {
+        if (a.group_pipe) border_group_kernel<true, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+        else border_group_kernel<false, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    } else {
+        if (a.group_pipe) border_group_kernel<true, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+        else border_group_kernel<false, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    }
     COUNT_LAUNCH();
 }
 

@@ -151,6 +151,10 @@ struct pipsgpu_ctx {
     DevBuf<GroupMember> gmembers;
     DevBuf<int> ginv;
     DevBuf<int8_t> gflags;
+    DevBuf<int64_t> gt_ptr;         // per group tile: range of gt_list = the members that have rows in both of its blocks
+    DevBuf<int> gt_list;
+    bool group_lists = false;       // PIPSGPU_GROUP_LISTS=1: the group kernel walks gt_list instead of scanning gflags
+    int bp_threads = 256;           // PIPSGPU_BP_THREADS=128: smaller CTAs for the big-front panels
     DevBuf<GTile> gtiles;
     int64_t ngtiles = 0;
     bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
@@ -197,6 +201,7 @@ struct pipsgpu_ctx {
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
+        a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -480,6 +485,8 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_XFORM")) ctx->xform = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_PANEL")) ctx->panel_staged = std::string(e) == "staged";
     if (const char* e = std::getenv("PIPSGPU_GROUP_PIPE")) ctx->group_pipe = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_LISTS")) ctx->group_lists = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_BP_THREADS")) ctx->bp_threads = (std::atoi(e) == 128) ? 128 : 256;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -842,6 +849,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     std::vector<GroupMember> gmembers;
     std::vector<int> ginv;
     std::vector<int8_t> gflags;
+    std::vector<int64_t> gt_ptr(1, 0);
+    std::vector<int> gt_list;
     std::vector<GTile> gtiles;
     std::vector<char> grouped((size_t)nfr, 0);
     if (ctx->grouping) {
@@ -885,8 +894,15 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 gd.mem_end = (int)gmembers.size();
                 const int gi = (int)groups.size();
                 groups.push_back(gd);
+                const int nmem_g = gd.mem_end - gd.mem_begin;
+                const int8_t* fl = gflags.data() + gd.inv_base / GROUP_TILE;      // [member][block]
                 for (int bi = 0; bi < gd.nblk; ++bi)
-                    for (int bj = 0; bj <= bi; ++bj) gtiles.push_back(GTile{gi, bi, bj, 0});
+                    for (int bj = 0; bj <= bi; ++bj) {
+                        gtiles.push_back(GTile{gi, bi, bj, 0});
+                        for (int q = 0; q < nmem_g; ++q)
+                            if (fl[(size_t)q * gd.nblk + bi] && fl[(size_t)q * gd.nblk + bj]) gt_list.push_back(q);
+                        gt_ptr.push_back((int64_t)gt_list.size());
+                    }
             }
             lf->gtile_count = (int64_t)gtiles.size() - lf->gtile_begin;
             lf->G = BorderGroups();
@@ -946,6 +962,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
     ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gflags.upload(gflags, s); ctx->gtiles.upload(gtiles, s);
+    ctx->gt_ptr.upload(gt_ptr, s); ctx->gt_list.upload(gt_list, s);
     ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
