@@ -233,8 +233,10 @@ def main():
     lp, dd, nom, total_blocks, (lo, hi) = build_problem(pkg, args.config, rank, world, args.blocks_per_gpu)
     stream = torch.cuda.Stream()
     t_setup = time.perf_counter()
+    # host threads of the (one-off) symbolic phase: the ranks of one box share its cores
+    sym_threads = max(1, (os.cpu_count() or 1) // world) if world > 1 else 0
     sys_ = pkg.linsys.CudaRootLinearSystem(lp, device=local_rank, rank=rank, n_ranks=world, nccl_uid=uid,
-                                           stream=stream.cuda_stream)
+                                           threads=sym_threads, stream=stream.cuda_stream)
     t_setup = time.perf_counter() - t_setup
     kkt = sys_.kkt
     leaf_stats = [lf.stats() for lf in sys_.leaves]
