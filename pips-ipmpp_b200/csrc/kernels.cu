@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     double* X = a.XY + fd.XYoff;
     if (lane < wp)
         for (int n = 0; n < wp; ++n) X[(size_t)n * wp + lane] = Pw[n * PLD + lane];
+    // ---- direct solve only: the k-major copy  XT[k * wp + r] = X(r, k)  behind X ----
+    if (a.xt_copy && lane < wp) {
+        double* XT = X + (size_t)wp * wp;
+        for (int k = 0; k < wp; ++k) XT[(size_t)k * wp + lane] = Pw[lane * PLD + k];
+    }
 }
 void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;

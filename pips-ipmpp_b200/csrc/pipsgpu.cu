@@ -201,7 +201,7 @@ struct pipsgpu_ctx {
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
-        a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
+        a.xt_copy = solve_direct ? 1 : 0; a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -213,6 +213,16 @@ struct pipsgpu_ctx {
             cudaMemsetAsync(uflag.p, 0, sizeof(int) * (size_t)nunits, stream);
             ps_epoch = 0;
         }
+        if (solve_direct) {
+            PDirectArgs d;
+            d.df = dfront.p; d.units = sunits.p; d.nunits = nunits; d.L = L.p; d.XY = XY.p; d.BL = BL.p; d.slots = slots.p;
+            d.rowg = rowg.p; d.gidx = gidx.p; d.Did = Did.p; d.Die = Die.p; d.ptype = ptype.p;
+            d.in = in; d.out = out; d.x = x.p; d.acc = acc.p; d.ucnt = ucnt.p; d.uflag = uflag.p; d.ticket = ticket.p;
+            d.epoch = ps_epoch; d.out_mode = out_mode;
+            launch_psolve_direct(d, sm_count, stream);
+            ps_epoch += 1;
+            return;
+        }
         PStreamArgs a;
         a.sf = sfront.p; a.units = sunits.p; a.nunits = nunits; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p;
         a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.ucnt = ucnt.p; a.uflag = uflag.p; a.ticket = ticket.p;
@@ -222,8 +232,13 @@ struct pipsgpu_ctx {
     }
     void psolve_by_level(const double* in, double* out, int out_mode);   // diagnostic path, PIPSGPU_SOLVE=level
     bool solve_by_level = false;
+    bool solve_direct = false;      // PIPSGPU_SOLVE=direct: psolve_direct.cu (not yet validated on a GPU)
+    DevBuf<DirectFront> dfront;
+    DevBuf<double> BL;
+    int64_t BLtot = 0;
     // factor panels -> solve pool (after every numeric factorisation)
     void pack_solve() {
+        if (solve_direct) { launch_pack_direct(dfront.p, (int)nfronts, L.p, BL.p, stream); return; }
         launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p,
                           xform ? XY.p : nullptr, stream);
     }
@@ -477,7 +492,10 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     ctx->device = device;
     CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    if (const char* e = std::getenv("PIPSGPU_SOLVE")) ctx->solve_by_level = std::string(e) == "level";
+    if (const char* e = std::getenv("PIPSGPU_SOLVE")) {
+        ctx->solve_by_level = std::string(e) == "level";
+        ctx->solve_direct = std::string(e) == "direct";
+    }
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
     if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
@@ -752,9 +770,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
-            if (ctx->xform) {      // persistent: pack_solve reads X after the last level
+            if (ctx->xform || ctx->solve_direct) {      // persistent: pack_solve / the direct solve read X after the last level
                 fd.XYoff = ctx->XYtot;
-                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w);
+                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w) * (ctx->solve_direct ? 2 : 1);
             } else {
                 fd.XYoff = xyfill[ol];
                 xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
@@ -818,7 +836,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
-    if (!ctx->xform) {
+    if (!ctx->xform && !ctx->solve_direct) {
         ctx->XYtot = 0;
         for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
     }
@@ -1019,6 +1037,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         const int nunits = (int)(subs.size() + tops.size());
         std::vector<SolveUnit> units((size_t)nunits);
         std::vector<SolveFront> sf((size_t)nfr);
+        std::vector<DirectFront> dfv(ctx->solve_direct ? (size_t)nfr : 0);
+        int64_t bl_off = 0;
         std::vector<int> chunk_front, chunk_idx;
         std::vector<uint16_t> slots((size_t)nrows, (uint16_t)0xFFFF);
         int64_t off = 0;
@@ -1048,6 +1068,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const int rows = fd.w + fd.na, R = ps_rows_per_chunk(f.ldr);
                 const int nch = (rows + R - 1) / R;
                 f.R = R; f.nch = nch;
+                if (ctx->solve_direct) {
+                    DirectFront& d = dfv[(size_t)sfi];
+                    d.Loff = fd.Loff; d.XYoff = fd.XYoff; d.blobB = bl_off;
+                    d.col0 = fd.col0; d.rows_off = (int)fd.rows_off; d.w = fd.w; d.na = fd.na;
+                    d.m = fd.w + fd.na + fd.nb; d.wp = padded_width(fd.w);
+                    bl_off += ((int64_t)fd.na * d.wp + 3) & ~int64_t(3);
+                }
                 for (int c = 0; c < nch; ++c) { chunk_front.push_back(sfi); chunk_idx.push_back(c); }
                 off += ps_front_doubles(f.ldr, rows);
                 for (int t = 0; t < fd.na; ++t) {
@@ -1073,6 +1100,11 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         ctx->sfront.upload(sf, s); ctx->sunits.upload(units, s); ctx->chunk_front.upload(chunk_front, s);
         ctx->chunk_idx.upload(chunk_idx, s); ctx->slots.upload(slots, s);
         ctx->SL.alloc((size_t)off + 2);
+        if (ctx->solve_direct) {
+            ctx->dfront.upload(dfv, s);
+            ctx->BLtot = bl_off;
+            ctx->BL.alloc((size_t)bl_off + 4);
+        }
         ctx->acc.alloc((size_t)npos + 1);
         ctx->ucnt.alloc((size_t)nunits + 1); ctx->uflag.alloc((size_t)nunits + 1); ctx->ticket.alloc(2);
         CUDA_CHECK(cudaMemsetAsync(ctx->acc.p, 0, sizeof(double) * ((size_t)npos + 1), s));
