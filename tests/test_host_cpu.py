@@ -247,3 +247,55 @@ def test_synthetic_generator_is_deterministic_and_shaped(pkg):
     assert (nb, n + my + mz, n0 + my0 + myl + mzl) == (512, 110000, 2700)
     nb, my, mz, n, n0, my0, mz0, myl, mzl = P.CONFIGS["C2"]
     assert (nb, n + my + mz, n0 + my0 + myl + mzl) == (64, 44000, 800)
+
+
+@pytest.mark.parametrize("cfg", ["T2", "T3"])
+def test_xform_front_solve_equals_substitution(pkg, cfg):
+    """the algebra of the streaming solve kernels (psolve.cu with PIPSGPU_XFORM, psolve_direct.cu), restated in numpy on
+    the oracle's factor: per front  y = X y  (X = L11^-1),  z = D^-1 y  fused into the forward sweep,  rows above -= L21 y;
+    backward  t = x - L21^T x_anc,  x = X^T t.  Must equal the oracle's plain substitution solve (mf_solve)."""
+    from oracle import mf
+    lp = pkg.problem.synthetic(cfg)
+    dd, nom = pkg.problem.synthetic_iterate(lp, pkg.problem.CONFIG_ID[cfg])
+    ch = lp.children[0]
+    krow, jcol, val, diag_pos, nB, brow, bcol, bval = mf.leaf_kkt_and_border(lp, 0)
+    val = val.copy()
+    val[diag_pos[:ch.n]] = dd[1]
+    val[diag_pos[ch.n + ch.my:]] = nom[1]
+    n = ch.n + ch.my + ch.mz
+    none = np.zeros(0, np.int32)
+    a = pkg.capi.Symbolic(n, ch.n, ch.my, ch.mz, krow, jcol, val, 0, none, none).export()
+    leaf = mf.MfLeaf(a)
+    leaf.factorize(val, np.zeros(0))
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(n)
+    want = leaf.solve(b)
+    col, rp, rows, ns = a["sn_col"], a["sn_rowptr"], a["rowidx"], a["ns"]
+    pt, did, die = a["ptype"], leaf.dinv_d, leaf.dinv_e
+    y = b[a["perm"]].copy()
+    fronts = []
+    for s in range(ns):
+        c0, w = col[s], col[s + 1] - col[s]
+        na = a["sn_na"][s]
+        m = w + na + a["sn_nb"][s]
+        F = leaf.L[a["Loff"][s]:a["Loff"][s] + m * w].reshape(w, m).T          # column-major panel -> (m, w)
+        L11 = np.tril(F[:w, :w], -1) + np.eye(w)
+        X = np.linalg.inv(L11)
+        L21 = F[w:w + na, :]
+        r = rows[rp[s]:rp[s] + na]
+        fronts.append((c0, w, X, L21, r))
+        yk = X @ y[c0:c0 + w]                                                  # y = X y
+        z = did[c0:c0 + w] * yk                                                # z = D^-1 y (2x2 pivots couple neighbours)
+        for k in range(w):
+            if pt[c0 + k] == 1:
+                z[k] += die[c0 + k] * yk[k + 1]
+            elif pt[c0 + k] == 2:
+                z[k] += die[c0 + k - 1] * yk[k - 1]
+        y[r] -= L21 @ yk                                                       # rows above -= L21 y
+        y[c0:c0 + w] = z
+    for c0, w, X, L21, r in reversed(fronts):
+        t = y[c0:c0 + w] - L21.T @ y[r]
+        y[c0:c0 + w] = X.T @ t
+    got = np.empty(n)
+    got[a["perm"]] = y
+    assert np.linalg.norm(got - want) <= 1e-11 * np.linalg.norm(want)
