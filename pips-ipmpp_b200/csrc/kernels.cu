@@ -60,11 +60,13 @@ void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, dou
 //  (red.global.add.f64). (The first version pushed every update entry to the parent with atomics: it was bound by the
 //  RED issue rate of the SMs, ~1.3 cycles per lane - profiles/README.md.)
 //
-//  Per tree level (deepest first), four launches over ALL scenario blocks of the GPU:
+//  Per tree level (deepest first), four launches over ALL scenario blocks of the GPU (small_fronts on the main stream next
+//  to big_panel + front_update_tiles on a side stream, PIPSGPU_OVERLAP); after the last level border_group_kernel for
+//  the grouped fronts' border x border updates, next to the solve-pool pack:
 //   pivot_kernel        one warp per front: assembly + LDL^T of the w x w pivot block in shared memory (static 1x1 / 2x2
 //                       pivots, tiny pivots perturbed and counted), then X = L11^-1 to a scratch, so that the panel below
 //                       becomes a small GEMM  W21 = A21 X^T  on the FP64 tensor pipe (+ the scaling L21 = W21 D^-1)
-//   small_fronts_kernel one warp per front with < BIG_U rows: panel + update, all in m8n8k4 DMMA tiles
+//   small_fronts_kernel one warp per front with < big_u (default 64) off-diagonal rows: panel + update in m8n8k4 DMMA tiles
 //   big_panel_kernel    one CTA per big front: panel only
 //   front_update_tiles_kernel  one CTA per 64x64 tile of a big front's update (DMMA)
 // =====================================================================================================

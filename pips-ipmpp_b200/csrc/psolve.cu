@@ -13,12 +13,17 @@
 //    flushed with one red.global.add.f64 per row at the end. Only units synchronise through global memory: a
 //    child-unit counter (forward) and a completion flag (backward) per unit, monotone in the solve epoch so that nothing
 //    is cleared between launches.
-//  * The solve is HBM-bound: every factor entry is read once per sweep. pack_solve_kernel (after every numeric
-//    factorisation) copies the K-part of each front into the "solve pool": per front a sequence of self-contained
-//    chunks [ D^-1 header | L rows, row-major with odd leading dimension | shared-memory slot of every row ], chunks of
-//    one unit contiguous and in sweep order. A warp keeps a TMA bulk copy (cp.async.bulk global -> shared, completion on
-//    an mbarrier) in flight for the next chunk while it works on the current one (two buffers per warp), independent of
-//    any dependency wait.
+//  * Every factor entry is read once per sweep. pack_solve_kernel (after every numeric factorisation) copies the K-part
+//    of each front into the "solve pool": per front a sequence of self-contained chunks [ D^-1 header | rows, row-major
+//    with odd leading dimension | shared-memory slot of every row ], chunks of one unit contiguous and in sweep order,
+//    the last chunk of a front cut to its own rows. With PIPSGPU_XFORM (default) the pivot-block rows hold X = L11^-1
+//    instead of L11 and are applied as matrix-vector products instead of substitution chains. A warp keeps a TMA bulk
+//    copy (cp.async.bulk global -> shared, completion on an mbarrier) in flight for the next chunk while it works on the
+//    current one (two buffers per warp), independent of any dependency wait.
+//  * Measured (profiles/README.md): 0.90 ms per launch at C2 = 27 % of the HBM roofline on algorithmic bytes, 57 % on
+//    the 3.3 GB it really streams; at 8 warps per SM (209 KB of shared memory per CTA) it is bound by instruction issue
+//    and latency, not by bytes - rows-per-chunk and chunk counts therefore travel in SolveFront (no device-side integer
+//    division) and the next front's descriptor is prefetched. psolve_direct.cu is the no-staging successor candidate.
 //  * Tickets: forward sweep = [subtree units, largest first | top units by tree level, deepest first], backward sweep
 //    = the reverse. Warps draw tickets from a global counter, one unit ahead of the one they process (so the bulk-copy
 //    pipeline never drains). A unit's prerequisites always hold EARLIER tickets and a warp finishes its tickets in
