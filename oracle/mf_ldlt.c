@@ -7,7 +7,7 @@
  * factorisation with Schur output: PARDISO iparm[37], PardisoProjectSchurSolver.C:246-280; pivot perturbation
  * iparm[9]=8, PardisoProjectSolver.C:68-77). None of those libraries is available in /root/reference
  * (ThirdPartyLibs/* holds download scripts only) -> "parity unpinned" at this boundary; the restatement is pinned
- * instead against SuperLU (oracle/linsys.py) and dense numpy in tests/test_oracle_mf.py.
+ * instead against SuperLU (oracle/linsys.py) and dense numpy in tests/test_oracle_golden.py (test_c_multifrontal_oracle_matches_superlu_oracle).
  *
  * The symbolic structure (permutation, fronts, maps) is an INPUT: tests obtain it from the product's host-side
  * analysis through pipsgpu_symbolic_export (include/pipsgpu.h), which is how that analysis is validated on CPU.
