@@ -43,8 +43,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2")
-    ap.add_argument("--blocks-per-gpu", type=int, default=0, help="0 = the config's block count (64 for C2)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--blocks-per-gpu", type=int, default=0,
+                    help="weak scaling with this many blocks per GPU; 0 = the scaling mode's default")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="strong: the config's block count is split over the GPUs (pipsgpu_partition = "
+                         "mapChildrenToNSubTrees); weak: blocks-per-gpu blocks on every GPU; auto: C2 weak, others strong")
+    ap.add_argument("--total-blocks", type=int, default=0, help="strong scaling: override the config's block count")
     ap.add_argument("--solves", type=int, default=8, help="solveCompressed calls per IPM iteration")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -109,11 +114,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def build_problem(pkg, cfg, rank, world, blocks_per_gpu):
+def scaling_mode(args):
+    if args.scaling != "auto":
+        return args.scaling
+    if args.blocks_per_gpu:
+        return "weak"
+    return "weak" if args.config == "C2" else "strong"
+
+
+def build_problem(pkg, args, rank, world):
     P = pkg.problem
+    cfg = args.config
     base_blocks = P.CONFIGS[cfg][0]
-    bpg = blocks_per_gpu or base_blocks
-    total = bpg * world
+    if scaling_mode(args) == "weak":
+        total = (args.blocks_per_gpu or base_blocks) * world
+    else:
+        total = args.total_blocks or base_blocks
     parts = pkg.capi.partition(total, world)
     lo, hi = parts[rank]
     lp = P.synthetic(cfg, n_blocks=total, block_range=(lo, hi))
@@ -230,7 +246,7 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         uid = obj[0]
 
-    lp, dd, nom, total_blocks, (lo, hi) = build_problem(pkg, args.config, rank, world, args.blocks_per_gpu)
+    lp, dd, nom, total_blocks, (lo, hi) = build_problem(pkg, args, rank, world)
     stream = torch.cuda.Stream()
     t_setup = time.perf_counter()
     # host threads of the (one-off) symbolic phase: the ranks of one box share its cores
@@ -288,6 +304,8 @@ def main():
             ms = float(t.item())
         return ms
 
+    # measured FP64 tensor-pipe (DMMA) peak of this GPU: the denominator of the FP64-tensor fractions
+    dmma_peak = sys_.ctx.dmma_peak_tflops()
     for _ in range(max(args.warmup, 3)):
         step_e2e()
     step_resident()
@@ -365,7 +383,8 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": ms_per_step * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": False,
+                "scaling": scaling_mode(args),
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.config}: {total_blocks} blocks x {lp.n_K(0)} KKT rows "
                                        f"({hi - lo} per GPU), n_S={lp.n_S}, fixed synthetic iterate (SURVEY 8d)",
@@ -382,6 +401,7 @@ def main():
                 "kernels_ms": {k_: v_ / args.steps for k_, v_ in ktime_acc.items()},
                 "schur_fp64_tflops_credited": schur_tflops,
                 "canonical_counts": cnt,
+                "fp64_tensor_peak_measured_tflops": dmma_peak,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     sys_.close()

@@ -115,8 +115,10 @@ int pipsgpu_leaf_destroy(pipsgpu_leaf* leaf);
  * LS/sLinsysRootAug.C:210-227; fused the way PardisoSchurSolver::schur_solve does it, PardisoSchurSolver.C:434-477).
  * sc may be NULL (factorisation only). */
 int pipsgpu_ctx_factorize_leaves(pipsgpu_ctx* ctx, pipsgpu_sc* sc);
-/* addTermToSchurCompl for a single leaf (LS/DistributedRootLinearSystem.C:1490-1506): the leaf must be factorised;
- * recomputes only the border rows. Slow path, for drop-in completeness. */
+/* addTermToSchurCompl for a single leaf (LS/DistributedRootLinearSystem.C:1490-1506). The Schur term is a by-product
+ * of the elimination, so this REFACTORISES the leaf with the Schur complement attached (the way
+ * PardisoSchurSolver::schur_solve does, PardisoSchurSolver.C:434-477) and leaves it factorised. The context must be
+ * committed. Per-leaf path, for drop-in completeness; pipsgpu_ctx_factorize_leaves is the batched fast path. */
 int pipsgpu_leaf_add_schur(pipsgpu_leaf* leaf, pipsgpu_sc* sc);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def build(force=False):
     src = os.path.join(_HERE, "mf_ldlt.c")
     if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-o", out, src, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fPIC", "-shared", "-o", out, src, "-lm"])
     return out
 
 

@@ -72,8 +72,10 @@ int mf_factorize(const mf_sym* S, int64_t nnzK, const int64_t* kmap, const doubl
             if (S->ptype[g] != 1) {
                 double d = F[(size_t)k * m + k];
                 const double sg = (double)S->sgn[g];
+                /* inertia = sign of the computed pivot, before the static-pivoting perturbation (what PARDISO / MA57
+                 * report through get_inertia, LS/LinearSystem.C:296-325 relies on it) */
+                if (d >= eps) ++pos; else if (d <= -eps) ++neg; else ++zero;
                 if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-                if (d > 0) ++pos; else if (d < 0) ++neg; else ++zero;
                 d_d[g] = d; d_e[g] = 0.0; dinv_d[g] = 1.0 / d; dinv_e[g] = 0.0;
                 F[(size_t)k * m + k] = 1.0;
                 for (int i = k + 1; i < m; ++i) {
@@ -90,13 +92,15 @@ int mf_factorize(const mf_sym* S, int64_t nnzK, const int64_t* kmap, const doubl
             } else {
                 double a = F[(size_t)k * m + k], b = F[(size_t)k * m + k + 1], c = F[(size_t)(k + 1) * m + k + 1];
                 double det = a * c - b * b;
+                if (det <= -eps * eps) { ++pos; ++neg; }
+                else if (det >= eps * eps) { if (a + c > 0) pos += 2; else neg += 2; }
+                else { ++zero; if (a + c > 0) ++pos; else ++neg; }
                 if (!(det <= -eps * eps)) {   /* expected: one positive, one negative eigenvalue */
                     if (a < eps) a = eps;
                     if (c > -eps) c = -eps;
                     det = a * c - b * b;
                     ++npert;
                 }
-                if (det < 0) { ++pos; ++neg; } else if (a > 0) pos += 2; else neg += 2;
                 const double ia = c / det, ib = -b / det, ic = a / det;
                 d_d[g] = a; d_e[g] = b; d_d[g + 1] = c; d_e[g + 1] = 0.0;
                 dinv_d[g] = ia; dinv_e[g] = ib; dinv_d[g + 1] = ic; dinv_e[g + 1] = 0.0;

@@ -12,13 +12,22 @@
 
 #include <algorithm>
 #include <atomic>
+#include <string>
+
+#include "common.h"
 
 namespace pipsgpu {
 
 static std::atomic<int64_t> g_launches{0};
 int64_t kernel_launch_count() { return g_launches.load(); }
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+// every <<<>>> is followed by this: launch-configuration errors are not sticky, so an unchecked one would let the
+// caller read stale results with PIPSGPU_OK
+void count_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(PIPSGPU_ERR_CUDA, std::string("kernel launch failed (") + what + "): " + cudaGetErrorString(e));
+}
+#define COUNT_LAUNCH() count_launch(__func__)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -152,8 +161,11 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
             if (!pair) {
                 double d = __shfl_sync(full, r1, k);
                 const double sg = (double)a.sgn[g];
+                // inertia = sign of the COMPUTED pivot (what PARDISO / MA57 report), counted before the static-pivoting
+                // perturbation: a wrong-signed pivot shows up as wrong inertia and drives the caller's regularisation loop
+                // (LS/LinearSystem.C:296-325); |d| below eps counts as a zero eigenvalue
+                if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;
                 if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-                if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
                 const double inv = 1.0 / d;
                 if (lane > k && lane < w) { Pw[lane * PLD + k] = r1; Pl[lane * PLD + k] = r1 * inv; }
                 if (lane == k) {
@@ -166,13 +178,16 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
                 const double db = __shfl_sync(full, r1, k + 1);
                 double dc = __shfl_sync(full, r2, k + 1);
                 double det = da * dc - db * db;
+                // inertia of the computed 2x2 block (before any perturbation): det < 0 -> (1,1); det > 0 -> sign of the trace
+                if (det <= -eps * eps) { ++npos; ++nneg; }
+                else if (det >= eps * eps) { if (da + dc > 0) npos += 2; else nneg += 2; }
+                else { ++nzero; if (da + dc > 0) ++npos; else ++nneg; }
                 if (!(det <= -eps * eps)) {
                     if (da < eps) da = eps;
                     if (dc > -eps) dc = -eps;
                     det = da * dc - db * db;
                     ++npert;
                 }
-                if (det < 0) { ++npos; ++nneg; } else if (da > 0) npos += 2; else nneg += 2;
                 const double ia = dc / det, ib = -db / det, ic = da / det;
                 if (lane > k + 1 && lane < w) {
                     Pw[lane * PLD + k] = r1; Pw[lane * PLD + k + 1] = r2;
@@ -213,11 +228,6 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     double* X = a.XY + fd.XYoff;
     if (lane < wp)
         for (int n = 0; n < wp; ++n) X[(size_t)n * wp + lane] = Pw[n * PLD + lane];
-    // ---- direct solve only: the k-major copy  XT[k * wp + r] = X(r, k)  behind X ----
-    if (a.xt_copy && lane < wp) {
-        double* XT = X + (size_t)wp * wp;
-        for (int k = 0; k < wp; ++k) XT[(size_t)k * wp + lane] = Pw[lane * PLD + k];
-    }
 }
 void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
     if (nfronts <= 0) return;
@@ -513,11 +523,6 @@ void launch_big_panel(const FactorArgs& a, int begin, int nfronts, cudaStream_t 
     const bool small_cta = a.bp_threads == 128;      // PIPSGPU_BP_THREADS=128
     if (a.panel_staged) {
         const int smem = ((small_cta ? 128 : BF_T) / 32) * PT_TILE * (int)sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(big_panel_kernel<true, BF_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BF_T / 32) * PT_TILE * (int)sizeof(double));
-            attr_set = true;
-        }
         if (small_cta) big_panel_kernel<true, 128><<<nfronts, 128, smem, s>>>(a, begin);
         else big_panel_kernel<true, BF_T><<<nfronts, BF_T, smem, s>>>(a, begin);
     } else {
@@ -1106,8 +1111,8 @@ __global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int k
         double d = __shfl_sync(full, r1, k);
         const double sg = (kb + k < n0) ? 1.0 : -1.0;
         const double eps = eps_rel * fmax(scale[kb + k], 1e-300);   // relative to the pivot row's original max entry
+        if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
         if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-        if (d > 0) ++npos; else if (d < 0) ++nneg; else ++nzero;
         const double inv = 1.0 / d;
         if (lane > k && lane < bw) { Pw[lane][k] = r1; Pl[lane][k] = r1 * inv; }
         if (lane == k) { D[kb + k] = d; Dinv[kb + k] = inv; }
@@ -1335,7 +1340,6 @@ void launch_dense_solve(const double* A, int ld, int n, const int* perm, const i
     if (n <= 0 || nrhs <= 0) return;
     (void)work;
     const size_t smem = dense_solve_smem(n);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dense_solve_kernel<<<nrhs, DS_T, smem, s>>>(A, ld, n, perm, ptype, Dinv, Dinv_e, x, xstride);
     COUNT_LAUNCH();
 }
@@ -1591,6 +1595,17 @@ void launch_vec_zero(double* dst, int64_t n, cudaStream_t s) {
 
 }  // namespace pipsgpu
 
+// per-device function attributes (opt-in to > 48 KB of dynamic shared memory); called from pipsgpu_ctx_create
+namespace pipsgpu {
+cudaError_t init_kernel_attributes() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(big_panel_kernel<true, BF_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BF_T / 32) * PT_TILE * (int)sizeof(double));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+}
+}  // namespace pipsgpu
+
 // =====================================================================================================
 // FP64 tensor-pipe (DMMA) peak microbenchmark: register-resident mma.sync chains, 8 independent accumulator
 // tiles per warp. Gives the denominator for the "fraction of FP64 tensor peak" figures (SURVEY.md 8(d) asks for an
@@ -1616,7 +1631,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
 // returns the flops one launch performs
 double launch_dmma_peak(double* out, int iters, int ctas, cudaStream_t s) {
     dmma_peak_kernel<<<ctas, 256, 0, s>>>(out, iters);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    COUNT_LAUNCH();
     return (double)ctas * 8.0 /*warps*/ * (double)iters * 8.0 /*tiles*/ * 512.0;
 }
 }  // namespace pipsgpu

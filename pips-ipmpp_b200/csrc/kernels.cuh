@@ -83,7 +83,6 @@ struct FactorArgs {
     const int* ginv;
     const int64_t* gt_ptr;       // per group tile: range of gt_list (group-local member indices with rows in both blocks)
     const int* gt_list;
-    int xt_copy;                 // pivot_kernel also writes the k-major copy of X behind X (direct solve)
     int group_lists;             // PIPSGPU_GROUP_LISTS=1: walk gt_list instead of scanning gflags
     int bp_threads;              // CTA size of big_panel_kernel (128 or 256)
     int group_pipe;              // PIPSGPU_GROUP_PIPE=1: software-pipelined member staging in border_group_kernel
@@ -148,38 +147,6 @@ struct PStreamArgs {
     int out_mode;                // 0: out = K^-1 in, 1: out -= K^-1 in
     int xform;                   // 1: the pool's pivot-block rows hold X = L11^-1 (unit lower) instead of L11
 };
-// ---- direct streaming solve (psolve_direct.cu, PIPSGPU_SOLVE=direct): same units / tickets, nothing staged ----
-struct DirectFront {             // one per front, same order as SolveFront (fronts of a unit contiguous, postorder)
-    int64_t Loff;                // factor panel (column-major, ld = m): the forward sweep reads its K-part in place
-    int64_t XYoff;               // X = L11^-1 row-major (wp x wp) followed by its k-major copy X^T
-    int64_t blobB;               // offset of the row-major transposed copy BL[r * wp + k] of the K-part of L21
-    int col0, rows_off;
-    int w, na, m, wp;
-};
-struct PDirectArgs {
-    const DirectFront* df;
-    const SolveUnit* units;
-    int nunits;
-    const double* L;             // factor pool
-    const double* XY;            // X / X^T scratch (persistent per front)
-    const double* BL;            // transposed L21 copies
-    const uint16_t* slots;       // per front row: shared-memory slot inside the unit or 0xFFFF
-    const int* rowg;
-    const int* gidx;
-    const double* Did; const double* Die;
-    const int8_t* ptype;
-    const double* in;
-    double* out;
-    double* x;
-    double* acc;
-    int* ucnt;
-    int* uflag;
-    int* ticket;
-    int epoch;
-    int out_mode;
-};
-void launch_psolve_direct(const PDirectArgs& a, int sm_count, cudaStream_t s);
-void launch_pack_direct(const DirectFront* df, int nfronts, const double* L, double* BL, cudaStream_t s);
 __host__ __device__ int ps_rows_per_chunk(int ldr);
 __host__ __device__ int ps_chunk_doubles(int ldr);
 __host__ __device__ int ps_chunk_rows(int ldr, int rows, int c);
@@ -189,7 +156,9 @@ void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s);
 void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* chunk_idx, int nchunks, const FrontDesc* fronts,
                        const double* L, const double* Did, const double* Die, const int8_t* ptype, const uint16_t* slots,
                        double* SL, const double* XY, cudaStream_t s);   // XY != null: pivot-block rows = X = L11^-1
-void count_launch();
+void count_launch(const char* what);    // counts the launch and throws on cudaGetLastError() != cudaSuccess
+cudaError_t init_psolve_attributes();     // per-device function attributes (dynamic shared memory opt-in)
+cudaError_t init_kernel_attributes();
 
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);

@@ -110,6 +110,11 @@ struct pipsgpu_leaf {
     std::vector<int> fl_begin, fl_count;         // per (global level, small|big): sub-range of fl_fronts owned by this leaf
     std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
     int64_t gtile_begin = 0, gtile_count = 0;    // sub-range of the border-group tiles of this leaf
+    int chunk_begin = 0, chunk_count = 0;        // sub-range of the by-leaf chunk list (solve-pool pack of this leaf only)
+    // persistent work buffers of the plug-in multi-RHS solve (pipsgpu_leaf_solve), allocated on first use
+    DevBuf<double> sv_b, sv_x, sv_u, sv_r;
+    DevBuf<int> sv_perm;
+    int sv_chunk = 0;
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double flops = 0;
     int inertia[3] = {0, 0, 0};
@@ -184,7 +189,7 @@ struct pipsgpu_ctx {
     DevBuf<SolveFront> sfront;
     DevBuf<SolveUnit> sunits;
     DevBuf<double> SL, acc;
-    DevBuf<int> ucnt, uflag, ticket, chunk_front, chunk_idx;
+    DevBuf<int> ucnt, uflag, ticket, chunk_front, chunk_idx, chunk_front_l, chunk_idx_l;   // _l: the same chunks sorted by leaf
     DevBuf<uint16_t> slots;
     int nchunks = 0, nunits = 0, nsub_units = 0;
     int64_t SLtot = 0;
@@ -201,7 +206,7 @@ struct pipsgpu_ctx {
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
         a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
-        a.xt_copy = solve_direct ? 1 : 0; a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
+        a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -213,16 +218,6 @@ struct pipsgpu_ctx {
             cudaMemsetAsync(uflag.p, 0, sizeof(int) * (size_t)nunits, stream);
             ps_epoch = 0;
         }
-        if (solve_direct) {
-            PDirectArgs d;
-            d.df = dfront.p; d.units = sunits.p; d.nunits = nunits; d.L = L.p; d.XY = XY.p; d.BL = BL.p; d.slots = slots.p;
-            d.rowg = rowg.p; d.gidx = gidx.p; d.Did = Did.p; d.Die = Die.p; d.ptype = ptype.p;
-            d.in = in; d.out = out; d.x = x.p; d.acc = acc.p; d.ucnt = ucnt.p; d.uflag = uflag.p; d.ticket = ticket.p;
-            d.epoch = ps_epoch; d.out_mode = out_mode;
-            launch_psolve_direct(d, sm_count, stream);
-            ps_epoch += 1;
-            return;
-        }
         PStreamArgs a;
         a.sf = sfront.p; a.units = sunits.p; a.nunits = nunits; a.SL = SL.p; a.rowg = rowg.p; a.gidx = gidx.p;
         a.in = in; a.out = out; a.x = x.p; a.acc = acc.p; a.ucnt = ucnt.p; a.uflag = uflag.p; a.ticket = ticket.p;
@@ -232,13 +227,13 @@ struct pipsgpu_ctx {
     }
     void psolve_by_level(const double* in, double* out, int out_mode);   // diagnostic path, PIPSGPU_SOLVE=level
     bool solve_by_level = false;
-    bool solve_direct = false;      // PIPSGPU_SOLVE=direct: psolve_direct.cu (not yet validated on a GPU)
-    DevBuf<DirectFront> dfront;
-    DevBuf<double> BL;
-    int64_t BLtot = 0;
     // factor panels -> solve pool (after every numeric factorisation)
-    void pack_solve() {
-        if (solve_direct) { launch_pack_direct(dfront.p, (int)nfronts, L.p, BL.p, stream); return; }
+    void pack_solve(const pipsgpu_leaf* only = nullptr) {
+        if (only) {   // per-leaf plug-in entry points repack their own chunks only
+            launch_pack_solve(sfront.p, chunk_front_l.p + only->chunk_begin, chunk_idx_l.p + only->chunk_begin, only->chunk_count,
+                              fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p, xform ? XY.p : nullptr, stream);
+            return;
+        }
         launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p,
                           xform ? XY.p : nullptr, stream);
     }
@@ -365,7 +360,7 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cud
     }
     if (sc) launch_border_groups(fa, gb, gc, fork ? s2 : s);
     if (e_pack0) CUDA_CHECK(cudaEventRecord(e_pack0, s));
-    ctx->pack_solve();
+    ctx->pack_solve(only);
     if (e_pack1) CUDA_CHECK(cudaEventRecord(e_pack1, s));
     if (fork) {
         CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
@@ -492,9 +487,11 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     ctx->device = device;
     CUDA_CHECK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // function attributes (dynamic shared-memory opt-in) are per device: set them for every context's device
+    CUDA_CHECK(init_psolve_attributes());
+    CUDA_CHECK(init_kernel_attributes());
     if (const char* e = std::getenv("PIPSGPU_SOLVE")) {
         ctx->solve_by_level = std::string(e) == "level";
-        ctx->solve_direct = std::string(e) == "direct";
     }
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
@@ -770,9 +767,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
-            if (ctx->xform || ctx->solve_direct) {      // persistent: pack_solve / the direct solve read X after the last level
+            if (ctx->xform) {      // persistent: pack_solve reads X after the last level
                 fd.XYoff = ctx->XYtot;
-                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w) * (ctx->solve_direct ? 2 : 1);
+                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w);
             } else {
                 fd.XYoff = xyfill[ol];
                 xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
@@ -836,7 +833,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     }
     ctx->Wtot = 0;
     for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
-    if (!ctx->xform && !ctx->solve_direct) {
+    if (!ctx->xform) {
         ctx->XYtot = 0;
         for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
     }
@@ -1037,8 +1034,6 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         const int nunits = (int)(subs.size() + tops.size());
         std::vector<SolveUnit> units((size_t)nunits);
         std::vector<SolveFront> sf((size_t)nfr);
-        std::vector<DirectFront> dfv(ctx->solve_direct ? (size_t)nfr : 0);
-        int64_t bl_off = 0;
         std::vector<int> chunk_front, chunk_idx;
         std::vector<uint16_t> slots((size_t)nrows, (uint16_t)0xFFFF);
         int64_t off = 0;
@@ -1068,13 +1063,6 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const int rows = fd.w + fd.na, R = ps_rows_per_chunk(f.ldr);
                 const int nch = (rows + R - 1) / R;
                 f.R = R; f.nch = nch;
-                if (ctx->solve_direct) {
-                    DirectFront& d = dfv[(size_t)sfi];
-                    d.Loff = fd.Loff; d.XYoff = fd.XYoff; d.blobB = bl_off;
-                    d.col0 = fd.col0; d.rows_off = (int)fd.rows_off; d.w = fd.w; d.na = fd.na;
-                    d.m = fd.w + fd.na + fd.nb; d.wp = padded_width(fd.w);
-                    bl_off += ((int64_t)fd.na * d.wp + 3) & ~int64_t(3);
-                }
                 for (int c = 0; c < nch; ++c) { chunk_front.push_back(sfi); chunk_idx.push_back(c); }
                 off += ps_front_doubles(f.ldr, rows);
                 for (int t = 0; t < fd.na; ++t) {
@@ -1099,12 +1087,21 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         ctx->nchunks = (int)chunk_front.size();
         ctx->sfront.upload(sf, s); ctx->sunits.upload(units, s); ctx->chunk_front.upload(chunk_front, s);
         ctx->chunk_idx.upload(chunk_idx, s); ctx->slots.upload(slots, s);
-        ctx->SL.alloc((size_t)off + 2);
-        if (ctx->solve_direct) {
-            ctx->dfront.upload(dfv, s);
-            ctx->BLtot = bl_off;
-            ctx->BL.alloc((size_t)bl_off + 4);
+        {   // the same chunk list grouped by leaf
+            std::vector<int> ord(chunk_front.size());
+            std::iota(ord.begin(), ord.end(), 0);
+            auto leaf_of = [&](int q) { return fronts[(size_t)sf[(size_t)chunk_front[(size_t)q]].front].leaf; };
+            std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return leaf_of(x) < leaf_of(y); });
+            std::vector<int> cf(ord.size()), ci(ord.size());
+            for (auto* lf : ctx->leaves) { lf->chunk_begin = 0; lf->chunk_count = 0; }
+            for (size_t t = 0; t < ord.size(); ++t) {
+                cf[t] = chunk_front[(size_t)ord[t]]; ci[t] = chunk_idx[(size_t)ord[t]];
+                pipsgpu_leaf* lf = ctx->leaves[(size_t)leaf_of(ord[t])];
+                if (lf->chunk_count++ == 0) lf->chunk_begin = (int)t;
+            }
+            ctx->chunk_front_l.upload(cf, s); ctx->chunk_idx_l.upload(ci, s);
         }
+        ctx->SL.alloc((size_t)off + 2);
         ctx->acc.alloc((size_t)npos + 1);
         ctx->ucnt.alloc((size_t)nunits + 1); ctx->uflag.alloc((size_t)nunits + 1); ctx->ticket.alloc(2);
         CUDA_CHECK(cudaMemsetAsync(ctx->acc.p, 0, sizeof(double) * ((size_t)npos + 1), s));
@@ -1210,6 +1207,7 @@ int pipsgpu_leaf_add_schur(pipsgpu_leaf* lf, pipsgpu_sc* sc) {
     if (!lf || !sc) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_add_schur: null argument");
     pipsgpu_ctx* ctx = lf->ctx;
     require_device(ctx);
+    if (!ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_add_schur: context not committed");
     // the Schur term is a by-product of the elimination: redo this leaf's numeric phase with the SC attached
     factor_prepare(ctx, lf);
     run_factor_levels(ctx, sc, lf);
@@ -1227,14 +1225,17 @@ int pipsgpu_leaf_solve(pipsgpu_leaf* lf, int nrhs, double* rhs) {
     cudaStream_t s = ctx->stream;
     const int64_t n = lf->n;
     const int chunk = 64;
-    DevBuf<double> b, xp, up;
-    b.alloc((size_t)n * chunk); xp.alloc((size_t)n * chunk); up.alloc((size_t)std::max<int64_t>(lf->upd_size, 1) * chunk);
-    DevBuf<int> lg;   // leaf-local permutation indices
-    {
+    if (lf->sv_chunk == 0) {   // work buffers and the leaf-local permutation live on the leaf (allocated once)
+        lf->sv_b.alloc((size_t)n * chunk); lf->sv_x.alloc((size_t)n * chunk);
+        lf->sv_u.alloc((size_t)std::max<int64_t>(lf->upd_size, 1) * chunk);
         std::vector<int> h((size_t)n);
         for (int64_t p = 0; p < n; ++p) h[(size_t)p] = lf->S.perm[(size_t)p];
-        lg.upload(h, s);
+        lf->sv_perm.upload(h, s);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        lf->sv_chunk = chunk;
     }
+    DevBuf<double>&b = lf->sv_b, &xp = lf->sv_x, &up = lf->sv_u;
+    DevBuf<int>& lg = lf->sv_perm;
     for (int r0 = 0; r0 < nrhs; r0 += chunk) {
         const int nr = std::min(chunk, nrhs - r0);
         CUDA_CHECK(cudaMemcpyAsync(b.p, rhs + (size_t)r0 * n, sizeof(double) * (size_t)n * nr, cudaMemcpyHostToDevice, s));

@@ -175,7 +175,7 @@ void launch_pack_solve(const SolveFront* sf, const int* chunk_front, const int* 
                        double* SL, const double* XY, cudaStream_t s) {
     if (nchunks <= 0) return;
     pack_solve_kernel<<<(nchunks + 3) / 4, 128, 0, s>>>(sf, chunk_front, chunk_idx, nchunks, fronts, L, Did, Die, ptype, slots, SL, XY);
-    count_launch();
+    count_launch("pack_solve_kernel");
 }
 
 // -----------------------------------------------------------------------------------------------------
@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                 if (lane == 0) {
                     const int target = un.nchild * (ep + 1);
                     while (ld_relaxed(a.ucnt + ui) < target) __nanosleep(20);
+                    fence_acq_rel_gpu();      // acquire side of the producers' fence + red: acc[] / x[] reads below are ordered
                 }
                 __syncwarp();
                 for (int r = lane; r < ncols; r += 32) {
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
                 const int* fl = a.uflag + ((un.parent >= 0) ? un.parent : ui);
                 const int target = (un.parent >= 0) ? 2 * ep + 2 : 2 * ep + 1;
                 while (ld_relaxed(fl) < target) __nanosleep(20);
+                fence_acq_rel_gpu();
             }
             __syncwarp();
             for (int r = lane; r < ncols; r += 32) xs[r] = __ldcg(a.x + pbeg + r);
@@ -511,19 +513,19 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 1) psolve_stream_kernel(PStream
 
 int psolve_stream_smem_bytes() { return PS_WARPS * PS_WARP_DOUBLES * (int)sizeof(double); }
 
+// function attributes are per device: called from pipsgpu_ctx_create with the context's device current
+cudaError_t init_psolve_attributes() {
+    return cudaFuncSetAttribute(psolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, psolve_stream_smem_bytes());
+}
+
 void launch_psolve_stream(const PStreamArgs& a, int sm_count, cudaStream_t s) {
     if (a.nunits <= 0) return;
-    static bool attr_set = false;
     const int smem = psolve_stream_smem_bytes();
-    if (!attr_set) {
-        cudaFuncSetAttribute(psolve_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
     int ctas = sm_count;
     const int need = (2 * a.nunits + PS_WARPS - 1) / PS_WARPS;
     if (ctas > need) ctas = need;
     psolve_stream_kernel<<<ctas, PS_WARPS * 32, smem, s>>>(a);
-    count_launch();
+    count_launch("psolve_stream_kernel");
 }
 
 }  // namespace pipsgpu

@@ -39,6 +39,44 @@ def create_kkt_lower(ch):
     return krow, cols.astype(np.int32), vals.astype(np.float64)
 
 
+def compressed_kkt_residual(lp, dd, nomegainv, rhs, sol, reg=None, reduce_root=None):
+    """Residual  b - K x  of the system solveCompressed solves, evaluated on the host from the
+    problem data alone (plain sparse matvecs, no factorisation): per owned block  b_i - K_i x_i - Bord_i x_0  and for the
+    root  b_0 - sum_i Bord_i^T x_i - K_root x_0  with  K_root = [dd0 A0^T C0^T F0^T G0^T; A0; C0 . nOm0; F0; G0 . . . nOmL]
+    in the b0 layout [x0; y0; z0; yl; zl]. `reduce_root` (a function summing an array over the ranks) makes the root
+    part exact when the blocks are distributed. Returns (||r||_2^2 of the owned leaf parts, root residual vector).
+    Size-independent correctness property used by bench.py and the full-size parity tests."""
+    regP, regDy, regDz = reg if reg is not None else (0.0, 0.0, 0.0)
+    root = lp.root
+    n0, my0, mz0, myl, mzl = root.n, root.my, root.mz, lp.myl, lp.mzl
+    x0 = sol[0]
+    u_x, u_y, u_z = x0[:n0], x0[n0:n0 + my0], x0[n0 + my0:n0 + my0 + mz0]
+    u_yl, u_zl = x0[n0 + my0 + mz0:n0 + my0 + mz0 + myl], x0[n0 + my0 + mz0 + myl:]
+    acc = np.zeros(n0 + my0 + mz0 + myl + mzl)          # sum_i Bord_i^T x_i in the b0 layout
+    leaf_sq = 0.0
+    for k, ch in enumerate(lp.children):
+        xi = sol[1 + k]
+        n, my, mz = ch.n, ch.my, ch.mz
+        xx, xy, xz = xi[:n], xi[n:n + my], xi[n + my:]
+        r = np.array(rhs[1 + k], dtype=np.float64, copy=True)
+        r[:n] -= (dd[1 + k] + regP) * xx + ch.W.T @ xy + ch.D.T @ xz + ch.F.T @ u_yl + ch.G.T @ u_zl
+        r[n:n + my] -= ch.W @ xx - regDy * xy + ch.A @ u_x
+        r[n + my:] -= ch.D @ xx + (nomegainv[1 + k] - regDz) * xz + ch.C @ u_x
+        leaf_sq += float(r @ r)
+        acc[:n0] += ch.A.T @ xy + ch.C.T @ xz
+        acc[n0 + my0 + mz0:n0 + my0 + mz0 + myl] += ch.F @ xx
+        acc[n0 + my0 + mz0 + myl:] += ch.G @ xx
+    if reduce_root is not None:
+        acc = reduce_root(acc)
+    r0 = np.array(rhs[0], dtype=np.float64, copy=True) - acc
+    r0[:n0] -= (dd[0] + regP) * u_x + root.A.T @ u_y + root.C.T @ u_z + root.F.T @ u_yl + root.G.T @ u_zl
+    r0[n0:n0 + my0] -= root.A @ u_x - regDy * u_y
+    r0[n0 + my0:n0 + my0 + mz0] -= root.C @ u_x + (nomegainv[0] - regDz) * u_z
+    r0[n0 + my0 + mz0:n0 + my0 + mz0 + myl] -= root.F @ u_x - regDy * u_yl
+    r0[n0 + my0 + mz0 + myl:] -= root.G @ u_x + (nomegainv[-1] - regDz) * u_zl
+    return leaf_sq, r0
+
+
 class CudaRootLinearSystem:
     """Root linear system of a two-level block-angular LP on one GPU (one rank of the reference)."""
 

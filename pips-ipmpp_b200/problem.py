@@ -308,8 +308,12 @@ CONFIGS = {
     "T2": (6, 300, 200, 600, 24, 6, 5, 8, 6),
     "T3": (8, 1200, 800, 2400, 60, 10, 10, 12, 8),
     "T4": (16, 3000, 2000, 6000, 120, 20, 20, 30, 20),
+    # the ROOT dimensions of C3 / C4 / C2 (n_S = 2700 / 6300 / 800) over small blocks: full-oracle parity of the root stage
+    "T5": (4, 3000, 2000, 6000, 2000, 200, 200, 300, 200),
+    "T6": (4, 1200, 800, 2400, 3000, 300, 300, 2000, 1000),
+    "T7": (4, 1500, 1000, 3000, 500, 100, 100, 120, 80),
 }
-CONFIG_ID = {"C2": 2, "C3": 3, "C4": 4, "C5": 5, "T1": 11, "T2": 12, "T3": 13, "T4": 14}
+CONFIG_ID = {"C2": 2, "C3": 3, "C4": 4, "C5": 5, "T1": 11, "T2": 12, "T3": 13, "T4": 14, "T5": 15, "T6": 16, "T7": 17}
 TECH_WINDOW = 48   # technology columns are drawn uniformly from the +-TECH_WINDOW columns around the row's time step
 
 

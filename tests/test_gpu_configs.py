@@ -1,0 +1,121 @@
+"""Every BASELINE.json configuration under GPU parity (default `-m gpu` suite, no opt-in):
+
+  * C3 / C4 / C5 with FULL-SIZE blocks (110 000 / 22 000 / 4 400 KKT rows, 2 500 / 6 000 / 400 border columns) and a
+    reduced block count, so that the serial C oracle finishes: Schur contribution against oracle/mf_ldlt.c
+    (rel. Frobenius <= 1e-10), inertia of every leaf, residual of solveCompressed through the host KKT matvec;
+  * the ROOT dimensions of C2 / C3 / C4 (n_S = 800 / 2 700 / 6 300) over small blocks (T7 / T5 / T6) against the full
+    linear-system oracle (oracle/linsys.py: SuperLU leaves + LAPACK dsytrf root): assembled Schur complement <= 1e-10,
+    root inertia, solveCompressed <= 1e-8;
+  * the dense root solver at n = 6 300 against LAPACK (numpy.linalg.solve) - DeSymIndefSolver.C:56-130;
+  * the 64-block C2 instance bench.py times: residual of solveCompressed <= 1e-9 (size-independent property).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _residual(pkg, lp, dd, nom, gpu, seed=5, reg=None):
+    rng = np.random.default_rng(seed)
+    rhs = [rng.standard_normal(gpu.nb0)] + [rng.standard_normal(ch.n + ch.my + ch.mz) for ch in lp.children]
+    sol = gpu.solve_compressed([r.copy() for r in rhs])
+    lsq, r0 = pkg.linsys.compressed_kkt_residual(lp, dd, nom, rhs, sol, reg)
+    return np.sqrt(lsq + r0 @ r0) / np.sqrt(sum(b @ b for b in rhs))
+
+
+@pytest.mark.parametrize("cfg,n_blocks", [("C3", 2), ("C4", 2), ("C5", 16)])
+def test_config_block_properties(pkg, cfg, n_blocks):
+    from oracle import mf
+    from oracle.linsys import OracleRoot
+    P = pkg.problem
+    lp = P.synthetic(cfg, n_blocks=n_blocks)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    inertia = gpu.factorize(dd, nom)
+    assert inertia == (lp.root.n, lp.root.my + lp.myl + lp.mzl, 0)
+    sc = gpu.schur_complement()
+    n0, my0, myl, mzl = lp.root.n, lp.root.my, lp.myl, lp.mzl
+    nB = n0 + myl + mzl
+    SCb = np.zeros((nB, nB))
+    for i, ch in enumerate(lp.children):
+        krow, jcol, val, diag_pos, nB_, brow, bcol, bval = mf.leaf_kkt_and_border(lp, i)
+        val = val.copy()
+        val[diag_pos[:ch.n]] = dd[1 + i]
+        val[diag_pos[ch.n + ch.my:]] = nom[1 + i]
+        sym = pkg.capi.Symbolic(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol).export()
+        m = mf.MfLeaf(sym)
+        leaf_inertia, npert = m.factorize(val, bval, SCb)
+        assert leaf_inertia == (ch.n, ch.my + ch.mz, 0) and npert == 0
+        assert gpu.leaves[i].inertia() == ((ch.n, ch.my + ch.mz, 0), 0)
+    idx = np.concatenate([np.arange(n0), n0 + my0 + np.arange(myl + mzl)])
+    root_only = OracleRoot(lp, owned=[])
+    root_only.put_diagonals(dd, nom)
+    root_only.initialize_kkt()
+    root_only.finalize_kkt_dense()
+    contrib = (sc - np.tril(root_only.SC))[np.ix_(idx, idx)]
+    assert _rel(contrib, np.tril(SCb)) <= 1e-10
+    assert _residual(pkg, lp, dd, nom, gpu) <= 1e-9
+    gpu.close()
+
+
+@pytest.mark.parametrize("cfg", ["T7", "T5", "T6"])
+def test_root_dimensions_against_full_oracle(pkg, cfg):
+    """n_S = 800 / 2 700 / 6 300 (the dense root of C2 / C3 / C4): every stage of factorize + solveCompressed against
+    the restated reference algorithm (oracle/linsys.py)"""
+    from oracle.linsys import OracleRoot
+    P = pkg.problem
+    lp = P.synthetic(cfg)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    inertia = gpu.factorize(dd, nom)
+    ref = OracleRoot(lp)
+    ref.put_diagonals(dd, nom)
+    ref.factor2()
+    assert _rel(gpu.schur_complement(), np.tril(ref.SC)) <= 1e-10
+    assert inertia == ref.inertia() == (lp.root.n, lp.root.my + lp.myl + lp.mzl, 0)
+    rng = np.random.default_rng(2)
+    rhs = [rng.standard_normal(gpu.nb0)] + [rng.standard_normal(ch.n + ch.my + ch.mz) for ch in lp.children]
+    want = ref.solve_compressed([r.copy() for r in rhs])
+    got = gpu.solve_compressed([r.copy() for r in rhs])
+    assert _rel(np.concatenate(got), np.concatenate(want)) <= 1e-8
+    gpu.close()
+
+
+@pytest.mark.parametrize("n0,nneg", [(3000, 3300), (1500, 1203)])
+def test_dense_root_solver_large(pkg, n0, nneg):
+    """dense LDL^T + solve at the C4 root size against LAPACK (numpy.linalg.solve -> dgesv) and exact inertia"""
+    rng = np.random.default_rng(n0)
+    n = n0 + nneg
+    M = rng.standard_normal((n0, 64))
+    H = M @ M.T + np.diag(rng.uniform(0.5, 50.0, n0))
+    A = rng.standard_normal((nneg, n0)) * (rng.uniform(size=(nneg, n0)) < 0.01)
+    G = np.diag(rng.uniform(1e-3, 1.0, nneg))
+    S = np.block([[H, A.T], [A, -G]])
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, n0, 0, nneg, 0)
+    sc.upload(np.tril(S))
+    assert sc.factorize() == (n0, nneg, 0)
+    B = rng.standard_normal((2, n))
+    X = sc.solve(B)
+    assert _rel(X, np.linalg.solve(S, B.T).T) <= 1e-10
+    sc.close()
+    ctx.close()
+
+
+def test_c2_64_blocks_residual(pkg):
+    """the exact instance bench.py times (64 blocks x 44 000 KKT rows, n_S = 800): residual of solveCompressed through
+    the host matvec, inertia of the root and of every leaf, zero perturbed pivots"""
+    P = pkg.problem
+    lp = P.synthetic("C2")
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID["C2"])
+    gpu = pkg.linsys.CudaRootLinearSystem(lp)
+    assert gpu.factorize(dd, nom) == (lp.root.n, lp.root.my + lp.myl + lp.mzl, 0)
+    for i, ch in enumerate(lp.children):
+        assert gpu.leaves[i].inertia() == ((ch.n, ch.my + ch.mz, 0), 0)
+    assert _residual(pkg, lp, dd, nom, gpu) <= 1e-9
+    assert _residual(pkg, lp, dd, nom, gpu, seed=6) <= 1e-9
+    gpu.close()
