@@ -104,6 +104,10 @@ int pipsgpu_leaf_get_inertia(pipsgpu_leaf* leaf, int inertia[3], int* n_perturbe
  * entries, out[3]=#fronts, out[4]=#levels, out[5]=#2x2 pivots, out[6]=max front rows, out[7]=contribution entries;
  * *flops = sum_j eta_j(eta_j+2) (SURVEY.md 8(d) stage-1 count) */
 int pipsgpu_leaf_get_stats(pipsgpu_leaf* leaf, int64_t out[8], double* flops);
+/* executed flops of this leaf's numeric phase (valid after commit): out[0] = canonical sum_j eta_j(eta_j+2), out[1] =
+ * Schur-term flops = lower triangle of L_B D L_B^T over all fronts (sum_f w_f nb_f (nb_f+1)), out[2] = all update flops
+ * (ancestor columns + border x border), out[3] = panel flops (W21 = A21 X^T). Measurement only. */
+int pipsgpu_leaf_get_flops(pipsgpu_leaf* leaf, double out[4]);
 /* factor download for parity checks: L = the leaf's panel pool (out[2] = stored panel entries of get_stats; per front an
  * m x w column-major panel, unit diagonal, layout of pipsgpu_symbolic_export), dinv_d / dinv_e = block-diagonal D^-1
  * (length n each, permuted order; dinv_e[k] couples k and k+1 of a 2x2 pivot). Any pointer may be NULL. */
@@ -190,14 +194,21 @@ pipsgpu_sc* pipsgpu_kkt_sc(pipsgpu_kkt* kkt);
 int pipsgpu_kkt_stage_times(pipsgpu_kkt* kkt, double out[8]);
 /* device time in ms of single kernels, CUDA events on the context's stream: out[0] = the streaming solve launch of the
  * last Lsolve (one K^-1 application over all blocks), [1] = factor -> solve-pool pack of the last factorize,
- * [2] = dense root solve kernel of the last Dsolve, [3] reserved (measurement only, no reference counterpart) */
+ * [2] = dense root solve kernel of the last Dsolve, [3] = the Schur-term (border x border) kernels of the last
+ * factorize, summed over the factorisation batches (measurement only, no reference counterpart) */
 int pipsgpu_kkt_kernel_times(pipsgpu_kkt* kkt, double out[4]);
 /* sizes of the context pools after commit: out = {L entries, C entries, solve-pool entries, fronts, KKT rows, tree
  * levels, nnz(K), nnz(Bord)} (measurement only) */
 int pipsgpu_ctx_pool_sizes(pipsgpu_ctx* ctx, int64_t out[8]);
+/* number of leaf batches of the numeric factorisation (contribution / scratch pools are sized for one batch) */
+int pipsgpu_ctx_num_batches(pipsgpu_ctx* ctx);
 /* measured FP64 tensor-pipe (DMMA, mma.sync m8n8k4 f64) peak of this GPU in TFLOP/s: register-resident chains on all
  * SMs, CUDA-event timed; the denominator of the "fraction of FP64 tensor peak" figures (no reference counterpart) */
 int pipsgpu_bench_dmma_peak(pipsgpu_ctx* ctx, double* tflops);
+/* measured rate in TFLOP/s of the library's own FP64 tensor-pipe GEMM (dgemm_nt_kernel: TMA-staged operands, DMMA) on an
+ * n x n x n lower-triangular update - the kernel behind the root LDL^T trailing update and the packed Schur-term update
+ * (measurement only, no reference counterpart) */
+int pipsgpu_bench_dgemm(pipsgpu_ctx* ctx, int n, double* tflops);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 int64_t pipsgpu_ctx_launch_count(pipsgpu_ctx* ctx);
 

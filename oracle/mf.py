@@ -43,6 +43,71 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+_SYMLIB = None
+
+
+def symlib():
+    """host-only build of the product's symbolic analysis (oracle/_build/libpipssym.so, g++ of csrc/symbolic.cpp +
+    csrc/capi_host.cpp by __graft_entry__.build_oracle): the CPU arm gets its elimination plan without loading the CUDA
+    library into its process"""
+    global _SYMLIB
+    if _SYMLIB is None:
+        path = os.path.join(_HERE, "_build", "libpipssym.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built - run __graft_entry__.build()")
+        _SYMLIB = C.CDLL(path)
+        _SYMLIB.pipsgpu_last_error.restype = C.c_char_p
+    return _SYMLIB
+
+
+class HostSymbolic:
+    """pipsgpu_symbolic_* through libpipssym.so; same interface as pips-ipmpp_b200/capi.py:Symbolic (sizes / flops / export)"""
+
+    def __init__(self, n, nx, ny, nz, krow, jcol, val, nB, brow, bcol, max_width=0):
+        L = symlib()
+        self.h = C.c_void_p()
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        krow, jcol, brow, bcol = i32(krow), i32(jcol), i32(brow), i32(bcol)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        rc = L.pipsgpu_symbolic_create(C.c_int(n), C.c_int(nx), C.c_int(ny), C.c_int(nz), _p(krow), _p(jcol), _p(val),
+                                       C.c_int(nB), C.c_int64(len(brow)), _p(brow), _p(bcol), C.c_int(max_width),
+                                       C.byref(self.h))
+        if rc != 0:
+            raise RuntimeError(L.pipsgpu_last_error().decode())
+        sz = np.zeros(13, dtype=np.int64)
+        fl = C.c_double(0)
+        L.pipsgpu_symbolic_sizes(self.h, _p(sz), C.byref(fl))
+        keys = ("n", "nB", "ns", "nlevels", "nrows", "Lsize", "Csize", "nnzK", "nnzB", "nnzL", "nnzL_border", "n_pairs",
+                "nchild")
+        self.sizes = {k: int(v) for k, v in zip(keys, sz)}
+        self.flops = fl.value
+
+    def export(self):
+        s = self.sizes
+        n, ns = s["n"], s["ns"]
+        a = dict(perm=np.zeros(n, np.int32), ptype=np.zeros(n, np.int8), sgn=np.zeros(n, np.int8),
+                 sn_col=np.zeros(ns + 1, np.int32), sn_rowptr=np.zeros(ns + 1, np.int64),
+                 rowidx=np.zeros(s["nrows"], np.int32), relidx=np.zeros(s["nrows"], np.int32),
+                 sn_na=np.zeros(ns, np.int32), sn_nb=np.zeros(ns, np.int32), sn_parent=np.zeros(ns, np.int32),
+                 sn_level=np.zeros(ns, np.int32), Loff=np.zeros(ns + 1, np.int64), Coff=np.zeros(ns + 1, np.int64),
+                 kmap=np.zeros(s["nnzK"], np.int64), bmap=np.zeros(s["nnzB"], np.int64),
+                 child_ptr=np.zeros(ns + 1, np.int32), child_idx=np.zeros(s["nchild"], np.int32))
+        order = ("perm", "ptype", "sgn", "sn_col", "sn_rowptr", "rowidx", "relidx", "sn_na", "sn_nb", "sn_parent",
+                 "sn_level", "Loff", "Coff", "kmap", "bmap", "child_ptr", "child_idx")
+        rc = symlib().pipsgpu_symbolic_export(self.h, *[_p(a[k]) for k in order])
+        if rc != 0:
+            raise RuntimeError(symlib().pipsgpu_last_error().decode())
+        a.update(n=n, nB=s["nB"], ns=ns)
+        return a
+
+    def __del__(self):
+        try:
+            if self.h:
+                symlib().pipsgpu_symbolic_destroy(self.h)
+        except Exception:
+            pass
+
+
 def leaf_kkt_and_border(lp, i):
     """lower CSR of the leaf KKT (create_kkt) and the border triplets in the compressed border index space
     [0,n0) | myl | mzl  (SC index = b for b < n0, b + my0 otherwise)."""
@@ -139,14 +204,19 @@ class MfBackend:
                 v[d["diag_pos"][ch.n + ch.my:]] = nomegainv[1 + i]
                 d["inertia"], d["npert"] = d["m"].factorize(v, d["bval"], acc[t], knorm=d["knorm"])
 
+        import time
+        t0 = time.perf_counter()
         list(self.pool.map(work, range(nth)))
         SCb = np.sum(acc, axis=0)
+        self.t_leaf_factor = time.perf_counter() - t0      # leaf LDL^T + Schur terms (scales with the number of blocks)
+        t0 = time.perf_counter()
         r = self.root
         r.put_diagonals(dd, nomegainv)
         r.initialize_kkt()
         r.SC[np.ix_(self.scidx, self.scidx)] += np.tril(SCb)
         r.finalize_kkt_dense()
         r.factorize_kkt()
+        self.t_root_factor = time.perf_counter() - t0      # root assembly + dense LDL^T (does not scale with the blocks)
 
     def solve_compressed(self, b, blocks=None):
         lp = self.lp
@@ -167,9 +237,13 @@ class MfBackend:
             np.add.at(contrib, b0idx(d["bcol"]), d["bval"] * z[d["brow"]])
             return contrib
 
+        import time
+        t0 = time.perf_counter()
         for c in self.pool.map(fwd, blocks):
             b[0] -= c
+        t1 = time.perf_counter()
         r.solve_reduced_link_cons(b[0])
+        t2 = time.perf_counter()
 
         def bwd(i):
             d = self.leaf_data[i]
@@ -179,4 +253,6 @@ class MfBackend:
             b[1 + i] -= d["m"].solve(t)
 
         list(self.pool.map(bwd, blocks))
+        self.t_leaf_solve = (t1 - t0) + (time.perf_counter() - t2)
+        self.t_root_solve = t2 - t1
         return b

@@ -163,6 +163,12 @@ class Context:
         _check(lib().pipsgpu_bench_dmma_peak(self.h, C.byref(v)))
         return v.value
 
+    def dgemm_tflops(self, n=4096):
+        """measured rate of the library's own FP64 tensor-pipe GEMM kernel (TMA-staged operands) on an n^3 lower update"""
+        v = C.c_double(0)
+        _check(lib().pipsgpu_bench_dgemm(self.h, C.c_int(n), C.byref(v)))
+        return v.value
+
     def launch_count(self):
         return int(lib().pipsgpu_ctx_launch_count(self.h))
 
@@ -171,6 +177,9 @@ class Context:
         _check(lib().pipsgpu_ctx_pool_sizes(self.h, _ip(out)))
         keys = ("L", "C", "solve_pool", "fronts", "rows", "levels", "nnzK", "nnzB")
         return {k: int(v) for k, v in zip(keys, out)}
+
+    def n_batches(self):
+        return int(lib().pipsgpu_ctx_num_batches(self.h))
 
     def close(self):
         if self.h:
@@ -239,6 +248,9 @@ class Leaf:
         keys = ("nnzL", "nnzL_border", "stored", "nfronts", "nlevels", "n_pairs", "max_m", "contrib")
         d = {k: int(v) for k, v in zip(keys, out)}
         d["flops"] = fl.value
+        f4 = np.zeros(4)
+        if lib().pipsgpu_leaf_get_flops(self.h, _ip(f4)) == 0:
+            d["schur_flops"], d["update_flops"], d["panel_flops"] = float(f4[1]), float(f4[2]), float(f4[3])
         return d
 
     def download_factor(self):
@@ -365,7 +377,7 @@ class KKT:
     def kernel_times(self):
         out = np.zeros(4)
         _check(lib().pipsgpu_kkt_kernel_times(self.h, _ip(out)))
-        return dict(zip(("psolve", "pack_solve", "dense_solve"), out.tolist()))
+        return dict(zip(("psolve", "pack_solve", "dense_solve", "schur_kernels"), out.tolist()))
 
     def close(self):
         if self.h:

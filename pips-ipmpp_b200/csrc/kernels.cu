@@ -1086,148 +1086,6 @@ void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* b
     COUNT_LAUNCH();
 }
 
-// =====================================================================================================
-// dense right-looking LDL^T (no pivoting: the x0-block is eliminated first, expected pivot signs + / -)
-// =====================================================================================================
-__global__ void __launch_bounds__(32) dense_diag_kernel(double* A, int ld, int kb, int bw, int n0, double eps_rel,
-                                                        const double* __restrict__ scale, double* D, double* Dinv,
-                                                        double* diagW, int* stats) {
-    __shared__ double Pl[DENSE_NB][DENSE_NB + 1];
-    __shared__ double Pw[DENSE_NB][DENSE_NB + 1];
-    const int lane = threadIdx.x;
-    const unsigned full = 0xffffffffu;
-    for (int j = 0; j < DENSE_NB; ++j) {
-        Pl[lane][j] = (lane < bw && j <= lane) ? A[(int64_t)(kb + lane) * ld + kb + j] : 0.0;
-        Pw[lane][j] = 0.0;
-    }
-    __syncwarp();
-    int npos = 0, nneg = 0, nzero = 0, npert = 0;
-    for (int k = 0; k < bw; ++k) {
-        double r1 = 0.0;
-        if (lane >= k && lane < bw) {
-            r1 = Pl[lane][k];
-            for (int j = 0; j < k; ++j) r1 -= Pl[lane][j] * Pw[k][j];
-        }
-        double d = __shfl_sync(full, r1, k);
-        const double sg = (kb + k < n0) ? 1.0 : -1.0;
-        const double eps = eps_rel * fmax(scale[kb + k], 1e-300);   // relative to the pivot row's original max entry
-        if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
-        if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
-        const double inv = 1.0 / d;
-        if (lane > k && lane < bw) { Pw[lane][k] = r1; Pl[lane][k] = r1 * inv; }
-        if (lane == k) { D[kb + k] = d; Dinv[kb + k] = inv; }
-        __syncwarp();
-    }
-    for (int j = 0; j < DENSE_NB; ++j) {
-        if (lane < bw && j < lane) A[(int64_t)(kb + lane) * ld + kb + j] = Pl[lane][j];
-        diagW[lane * DENSE_NB + j] = (j < lane) ? Pw[lane][j] : 0.0;
-    }
-    if (lane == 0 && stats) {
-        atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
-    }
-}
-void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
-                       double* diagW, int* stats, cudaStream_t s) {
-    dense_diag_kernel<<<1, 32, 0, s>>>(A, ld, kb, bw, n0, eps_rel, scale, D, Dinv, diagW, stats);
-    COUNT_LAUNCH();
-}
-
-// rows below the diagonal block: thread per row, row in registers
-__global__ void __launch_bounds__(128) dense_trsm_kernel(double* A, int ld, int n, int kb, int bw, const double* __restrict__ Dinv,
-                                                         const double* __restrict__ diagW, double* __restrict__ Wbuf) {
-    __shared__ double Pw[DENSE_NB][DENSE_NB + 1];
-    __shared__ double s_dinv[DENSE_NB];
-    for (int idx = threadIdx.x; idx < DENSE_NB * DENSE_NB; idx += blockDim.x) Pw[idx / DENSE_NB][idx % DENSE_NB] = diagW[idx];
-    if (threadIdx.x < DENSE_NB) s_dinv[threadIdx.x] = (threadIdx.x < bw) ? Dinv[kb + threadIdx.x] : 0.0;
-    __syncthreads();
-    const int r = kb + bw + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    double* arow = A + (int64_t)r * ld + kb;
-    double l[DENSE_NB], wv[DENSE_NB];
-#pragma unroll
-    for (int k = 0; k < DENSE_NB; ++k) l[k] = (k < bw) ? arow[k] : 0.0;
-#pragma unroll
-    for (int k = 0; k < DENSE_NB; ++k) {
-        double acc = l[k];
-#pragma unroll
-        for (int j = 0; j < k; ++j) acc -= l[j] * Pw[k][j];
-        wv[k] = acc;
-        l[k] = acc * s_dinv[k];
-    }
-#pragma unroll
-    for (int k = 0; k < DENSE_NB; ++k)
-        if (k < bw) arow[k] = l[k];
-    double* wr = Wbuf + (int64_t)r * DENSE_NB;
-#pragma unroll
-    for (int k = 0; k < DENSE_NB; k += 2) *reinterpret_cast<double2*>(wr + k) = make_double2(wv[k], wv[k + 1]);
-}
-void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf,
-                       cudaStream_t s) {
-    const int rows = n - kb - bw;
-    if (rows <= 0) return;
-    dense_trsm_kernel<<<cdiv(rows, 128), 128, 0, s>>>(A, ld, n, kb, bw, Dinv, diagW, Wbuf);
-    COUNT_LAUNCH();
-}
-
-// trailing update  A(i,j) -= sum_k L(i,kb+k) * W(j,k)  for i >= j >= kb+bw  on the FP64 tensor pipe.
-// CTA tile 64x64, 4 warps x (32x32), K = 32 (one block column); operands staged in shared memory (stride 36
-// doubles => the m8n8k4 fragment loads are bank-conflict free).
-constexpr int SY_T = 64, SY_LD = 36;
-__global__ void __launch_bounds__(128) dense_syrk_kernel(double* A, int ld, int n, int kb, int bw, const double* __restrict__ Wbuf) {
-    const int t0 = kb + bw;
-    const int bi = blockIdx.y, bj = blockIdx.x;
-    if (bj > bi) return;
-    const int i0 = t0 + bi * SY_T, j0 = t0 + bj * SY_T;
-    __shared__ double As[SY_T * SY_LD];
-    __shared__ double Bs[SY_T * SY_LD];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < SY_T * DENSE_NB; idx += 128) {
-        const int r = idx / DENSE_NB, k = idx - r * DENSE_NB;
-        const int gi = i0 + r, gj = j0 + r;
-        As[r * SY_LD + k] = (gi < n && k < bw) ? A[(int64_t)gi * ld + kb + k] : 0.0;
-        Bs[r * SY_LD + k] = (gj < n && k < bw) ? Wbuf[(int64_t)gj * DENSE_NB + k] : 0.0;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
-    const int lr = lane >> 2, lk = lane & 3;
-    double acc[4][4][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-#pragma unroll
-    for (int k0 = 0; k0 < DENSE_NB; k0 += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) af[a] = As[(wr + a * 8 + lr) * SY_LD + k0 + lk];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = Bs[(wc + b * 8 + lr) * SY_LD + k0 + lk];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int gi = i0 + wr + a * 8 + lr;
-            const int gj = j0 + wc + b * 8 + lk * 2;
-            if (gi < n) {
-                if (gj <= gi) A[(int64_t)gi * ld + gj] -= acc[a][b][0];
-                if (gj + 1 <= gi) A[(int64_t)gi * ld + gj + 1] -= acc[a][b][1];
-            }
-        }
-}
-void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s) {
-    const int rows = n - kb - bw;
-    if (rows <= 0) return;
-    const int nt = cdiv(rows, SY_T);
-    dense_syrk_kernel<<<dim3(nt, nt), 128, 0, s>>>(A, ld, n, kb, bw, Wbuf);
-    COUNT_LAUNCH();
-}
-
 // forward / block-diagonal / backward solve with the dense factors  P A P^T = L D L^T, one CTA per right-hand side.
 // perm[i] = original index at pivot position i; ptype marks 2x2 pivots (Bunch-Kaufman path), Dinv_e their coupling.
 // The vector lives in shared memory; per block column the 32x32 diagonal block (one entry per thread) and the first

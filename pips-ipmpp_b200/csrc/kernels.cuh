@@ -7,7 +7,10 @@
 namespace pipsgpu {
 
 constexpr int MAXW = 32;         // maximum front width (pivot columns); symbolic analysis splits wider supernodes
-constexpr int DENSE_NB = 32;     // block size of the dense root LDL^T
+constexpr int DENSE_NB = 32;     // row-block size of the single-CTA dense solve (Bunch-Kaufman path)
+constexpr int DENSE_PANEL = 128; // panel width of the blocked dense root LDL^T (dense.cu)
+constexpr int GEMM_TILE = 128;   // CTA tile of dgemm_nt_kernel (rows of a TMA box)
+constexpr int GEMM_KS = 16;      // K extent of one pipeline stage = one 128-byte swizzle row of doubles
 constexpr int BIG_U = 64;        // default big-front threshold (PIPSGPU_BIG_U): fronts with at least this many off-diagonal rows take the CTA-parallel path
 constexpr int TILE = 64;         // output tile of the tiled update
 
@@ -178,19 +181,38 @@ void launch_border_tmult(const int* brow, const int* bidx, const double* val, in
 void launch_border_mult(const int* brow, const int* bidx, const double* val, int64_t nnz, const double* u, double* t, cudaStream_t s);
 void launch_axpy(double alpha, const double* x, double* y, int64_t n, cudaStream_t s);
 
-// ---- dense root path (lower triangle, row-major, ld = n) ----
+// ---- dense FP64 GEMM on the tensor pipe with TMA-staged operands (dense.cu) ----
+struct alignas(64) TMap { unsigned char bytes[128]; };      // CUtensorMap (cuda.h) without the driver header
+void make_tmap(TMap* out, const double* base, int64_t rows, int64_t cols, int64_t ld);   // row-major, box 16 cols x 128 rows
+enum { GEMM_EPI_TRAIL = 0, GEMM_EPI_PANEL = 1, GEMM_EPI_SCHUR = 2 };
+struct GemmArgs {
+    int a_row0, a_col0;      // TMA coordinates of the A tile of (bi, kt): row a_row0 + 128 bi, column a_col0 + 16 kt
+    int b_row0, b_col0;      // the same for B (tile column bj)
+    int K;
+    int m_tiles, n_tiles;
+    int lower;               // 1: triangular tile grid (bj <= bi) over m_tiles x m_tiles
+    double* C; int64_t ldc;  // TRAIL / PANEL: the factor; SCHUR: the dense Schur complement
+    int c_row0, c_col0;      // global row / column of tile (0,0) (PANEL: c_col0 = first column of the panel)
+    int c_rows, c_cols;      // TRAIL / PANEL: row limit (n); PANEL: panel width; SCHUR: number of packed rows
+    double* C2; int64_t ldc2;    // PANEL: W21 buffer (indexed by global row)
+    const double* scale;     // PANEL: D^-1 of the panel's pivots
+    const int* map;          // SCHUR: Schur-complement index of every packed row
+};
+void launch_dgemm_nt(int epi, const TMap& tmA, const TMap& tmB, const GemmArgs& g, cudaStream_t s);
+void launch_ldlt_diag(double* A, int64_t ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
+                      double* X, int* stats, cudaStream_t s);
+void launch_dense_trisolve(const double* F, int64_t ld, int n, const double* Xall, const double* Dinv, double* x, double* y,
+                           int* flagF, int* flagB, int epoch, int sm_count, cudaStream_t s);
+cudaError_t init_dense_attributes();
+
+// ---- dense root path (lower triangle, row-major) ----
 void launch_sc_add_sparse(double* SC, int ld, int row0, int col0, int m, const int* krow, const int* jcol, const double* val, double alpha, cudaStream_t s);
 void launch_sc_add_diag(double* SC, int ld, int off, int n, const double* d, double alpha, cudaStream_t s);
 // SC[0:n0,0:n0] (lower) -= C^T diag(1/zdiag) C   for CSR C (mz x n0)
 void launch_sc_add_ctdc(double* SC, int ld, int mz, const int* krow, const int* jcol, const double* val, const double* zdiag, cudaStream_t s);
 void launch_sc_pack(const double* SC, int ld, int n0, int my0, int nl, double* buf, bool unpack, double* SCout, cudaStream_t s);
 int64_t sc_pack_size(int n0, int nl);
-// one block column of the right-looking LDL^T; n0 = number of leading (positive) indices
-void launch_dense_diag(double* A, int ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
-                       double* diagW, int* stats, cudaStream_t s);
 void launch_row_absmax(const double* A, int ld, int n, double* out, cudaStream_t s);
-void launch_dense_trsm(double* A, int ld, int n, int kb, int bw, const double* Dinv, const double* diagW, double* Wbuf, cudaStream_t s);
-void launch_dense_syrk(double* A, int ld, int n, int kb, int bw, const double* Wbuf, cudaStream_t s);
 void launch_dense_solve(const double* A, int ld, int n, const int* perm, const int8_t* ptype, const double* Dinv,
                         const double* Dinv_e, double* x, int nrhs, int64_t xstride, double* work, cudaStream_t s);
 // Bunch-Kaufman fallback (dsytf2 restated): device-side step counter

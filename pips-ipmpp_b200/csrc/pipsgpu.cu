@@ -111,12 +111,14 @@ struct pipsgpu_leaf {
     std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
     int64_t gtile_begin = 0, gtile_count = 0;    // sub-range of the border-group tiles of this leaf
     int chunk_begin = 0, chunk_count = 0;        // sub-range of the by-leaf chunk list (solve-pool pack of this leaf only)
+    int batch = 0;                               // factorisation batch of this leaf
     // persistent work buffers of the plug-in multi-RHS solve (pipsgpu_leaf_solve), allocated on first use
     DevBuf<double> sv_b, sv_x, sv_u, sv_r;
     DevBuf<int> sv_perm;
     int sv_chunk = 0;
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double flops = 0;
+    double flops4[4] = {0, 0, 0, 0};   // canonical F1 | Schur-term flops (lower triangle of L_B D L_B^T) | update flops | panel flops
     int inertia[3] = {0, 0, 0};
     int n_perturbed = 0;
     bool factorized = false;
@@ -126,9 +128,14 @@ struct pipsgpu_sc {
     pipsgpu_ctx* ctx = nullptr;
     int n0 = 0, my0 = 0, myl = 0, mzl = 0, n = 0;
     DevBuf<double> A;        // assembled matrix, n x n row-major, lower triangle used (owned by the linear system)
-    DevBuf<double> Fm;       // the solver's own copy, overwritten by the factors (DeSymIndefSolver.C:65 copies too)
-    DevBuf<double> D, De, Dinv, Dinv_e, diagW, Wbuf, Wc, pack, rhs, swork, scale;
-    DevBuf<int> stats, perm;
+    DevBuf<double> Fm;       // the solver's own copy, overwritten by the factors (DeSymIndefSolver.C:65 copies too); n x ldf
+    int64_t ldf = 0;         // leading dimension of Fm: n rounded up to 16 doubles (TMA: 16-byte aligned rows, 128-byte here)
+    DevBuf<double> D, De, Dinv, Dinv_e, Wbuf, Wc, pack, rhs, swork, scale, Xall, ybuf;
+    TMap tmF, tmW[2], tmX;   // tensor maps of the factor, the two W21 panel buffers and the inverse diagonal blocks
+    DevBuf<int> stats, perm, tflags;
+    int ts_epoch = 0;        // epoch of the data-flow flags of dense_trisolve_kernel
+    int* h_stats = nullptr;  // pinned: inertia / perturbation counters of the last static factorisation
+    ~pipsgpu_sc() { if (h_stats) cudaFreeHost(h_stats); }
     DevBuf<int8_t> ptype;
     DevBuf<BkState> bk;
     bool factorized = false;
@@ -148,6 +155,12 @@ struct pipsgpu_ctx {
     // pools
     int64_t npos = 0, nfronts = 0, Ltot = 0, Ctot = 0, Wtot = 0, updtot = 0, nnzK = 0, nnzB = 0;
     int nlevels = 0;
+    // The numeric factorisation runs over BATCHES of consecutive leaves: the contribution pool C, the panel scratch W and
+    // the X = L11^-1 scratch are sized for the largest batch and reused (C alone would be 160 GB for the 512 blocks of C3);
+    // the factor panels L and the solve pool stay resident for every leaf. batch_ptr[b] .. batch_ptr[b+1] = leaves of batch b.
+    std::vector<int> batch_ptr;
+    std::vector<cudaEvent_t> ev_grp;    // per batch: events bracketing its border-group (Schur-term) kernel on its own stream
+    bool grp_timed = false;
     std::vector<int> level_ptr;     // nlevels*NCLS+1 into level_fronts; group g = level_order*NCLS + width class, deepest level first
     std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
     DevBuf<TileDesc> tiles;
@@ -174,6 +187,7 @@ struct pipsgpu_ctx {
     bool panel_staged = false;      // PIPSGPU_PANEL=staged
     bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream_hi = nullptr;   // high-priority side stream: look-ahead panels of the dense root LDL^T
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf<double> XY;
     int64_t XYtot = 0;
@@ -189,7 +203,7 @@ struct pipsgpu_ctx {
     DevBuf<SolveFront> sfront;
     DevBuf<SolveUnit> sunits;
     DevBuf<double> SL, acc;
-    DevBuf<int> ucnt, uflag, ticket, chunk_front, chunk_idx, chunk_front_l, chunk_idx_l;   // _l: the same chunks sorted by leaf
+    DevBuf<int> ucnt, uflag, ticket, chunk_front_l, chunk_idx_l;   // pack chunks (front, chunk index) grouped by leaf
     DevBuf<uint16_t> slots;
     int nchunks = 0, nunits = 0, nsub_units = 0;
     int64_t SLtot = 0;
@@ -228,14 +242,10 @@ struct pipsgpu_ctx {
     void psolve_by_level(const double* in, double* out, int out_mode);   // diagnostic path, PIPSGPU_SOLVE=level
     bool solve_by_level = false;
     // factor panels -> solve pool (after every numeric factorisation)
-    void pack_solve(const pipsgpu_leaf* only = nullptr) {
-        if (only) {   // per-leaf plug-in entry points repack their own chunks only
-            launch_pack_solve(sfront.p, chunk_front_l.p + only->chunk_begin, chunk_idx_l.p + only->chunk_begin, only->chunk_count,
-                              fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p, xform ? XY.p : nullptr, stream);
-            return;
-        }
-        launch_pack_solve(sfront.p, chunk_front.p, chunk_idx.p, nchunks, fronts.p, L.p, Did.p, Die.p, ptype.p, slots.p, SL.p,
-                          xform ? XY.p : nullptr, stream);
+    // chunks [begin, begin + count) of the by-leaf chunk list (a batch or a single leaf repacks its own chunks only)
+    void pack_solve(int begin, int count) {
+        launch_pack_solve(sfront.p, chunk_front_l.p + begin, chunk_idx_l.p + begin, count, fronts.p, L.p, Did.p, Die.p, ptype.p,
+                          slots.p, SL.p, xform ? XY.p : nullptr, stream);
     }
     SolveArgs solve_args(double* xbuf, int64_t xstride, double* updbuf, int64_t updstride) {
         SolveArgs a;
@@ -311,28 +321,35 @@ void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_lea
     }
 }
 
-// All levels of the numeric factorisation (deepest first), then the deferred border-group updates and the solve-pool
-// pack. e_pack0 / e_pack1 (optional) bracket the pack kernel on the main stream.
-void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cudaEvent_t e_pack0 = nullptr,
-                       cudaEvent_t e_pack1 = nullptr) {
+// All levels of the numeric factorisation (deepest first) of the leaves [lo, hi) - one batch, or a single leaf for the
+// plug-in entry points -, then their deferred border-group updates and their solve-pool pack. Fronts, tiles, group tiles
+// and pack chunks are all stored grouped by leaf inside a level, so a leaf range is a contiguous sub-range of every list.
+void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEvent_t e_pack0, cudaEvent_t e_pack1) {
+    if (lo >= hi) return;
     cudaStream_t s = ctx->stream;
     cudaStream_t s2 = ctx->overlap ? ctx->stream2 : nullptr;
     FactorArgs fa = ctx->factor_args(sc);
+    const pipsgpu_leaf* first = ctx->leaves[(size_t)lo];
+    const pipsgpu_leaf* last = ctx->leaves[(size_t)hi - 1];
+    const bool all = lo == 0 && hi == (int)ctx->leaves.size();
     for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
-        if (only) {
-            for (int c = 0; c < NCLS; ++c) launch_pivot(fa, only->level_begin[lv * NCLS + c], only->level_count[lv * NCLS + c], s);
-        } else {
+        if (all) {
             const int begin = ctx->level_ptr[lv * NCLS];
             launch_pivot(fa, begin, ctx->level_ptr[(lv + 1) * NCLS] - begin, s);
+        } else {
+            for (int c = 0; c < NCLS; ++c) {
+                const int g = lv * NCLS + c;
+                const int begin = first->level_begin[g];
+                launch_pivot(fa, begin, last->level_begin[g] + last->level_count[g] - begin, s);
+            }
         }
         int begin[2], count[2];
         for (int kind = 0; kind < 2; ++kind) {
             const int g = lv * 2 + kind;
-            begin[kind] = ctx->fl_ptr[g]; count[kind] = ctx->fl_ptr[g + 1] - ctx->fl_ptr[g];
-            if (only) { begin[kind] = only->fl_begin[g]; count[kind] = only->fl_count[g]; }
+            begin[kind] = first->fl_begin[g];
+            count[kind] = last->fl_begin[g] + last->fl_count[g] - begin[kind];
         }
-        int64_t tb = ctx->tile_ptr[lv], tc = ctx->tile_ptr[lv + 1] - ctx->tile_ptr[lv];
-        if (only) { tb = only->tile_begin[lv]; tc = only->tile_count[lv]; }
+        const int64_t tb = first->tile_begin[lv], tc = last->tile_begin[lv] + last->tile_count[lv] - tb;
         // small and big fronts of one level are independent of each other (disjoint panels, scratch and contribution
         // blocks): the latency-bound one-warp-per-front kernel runs next to the CTA-parallel panel + tile kernels
         const bool fork = s2 && count[0] > 0 && count[1] > 0;
@@ -351,20 +368,39 @@ void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cud
     }
     // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement):
     // read-only on the factor panels, like the pack kernel next to which they run
-    int64_t gb = 0, gc = ctx->ngtiles;
-    if (only) { gb = only->gtile_begin; gc = only->gtile_count; }
+    const int64_t gb = first->gtile_begin, gc = last->gtile_begin + last->gtile_count - gb;
     const bool fork = s2 && sc && gc > 0;
     if (fork) {
         CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
         CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
     }
-    if (sc) launch_border_groups(fa, gb, gc, fork ? s2 : s);
+    if (sc && gc > 0) {
+        cudaStream_t sg = fork ? s2 : s;
+        const int b = first->batch;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b], sg));
+        launch_border_groups(fa, gb, gc, sg);
+        CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b + 1], sg));
+        ctx->grp_timed = true;
+    }
     if (e_pack0) CUDA_CHECK(cudaEventRecord(e_pack0, s));
-    ctx->pack_solve(only);
+    ctx->pack_solve(first->chunk_begin, last->chunk_begin + last->chunk_count - first->chunk_begin);
     if (e_pack1) CUDA_CHECK(cudaEventRecord(e_pack1, s));
     if (fork) {
         CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
         CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    }
+}
+
+// numeric factorisation of one leaf (plug-in entry points) or of every leaf of the context, batch by batch.
+// e_pack0 / e_pack1 (optional) bracket the pack kernel of the LAST batch on the main stream.
+void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cudaEvent_t e_pack0 = nullptr,
+                       cudaEvent_t e_pack1 = nullptr) {
+    if (only) { run_factor_range(ctx, sc, only->index, only->index + 1, e_pack0, e_pack1); return; }
+    const int nb = (int)ctx->batch_ptr.size() - 1;
+    for (int b = 0; b < nb; ++b) {
+        const bool lastb = b + 1 == nb;
+        run_factor_range(ctx, sc, ctx->batch_ptr[(size_t)b], ctx->batch_ptr[(size_t)b + 1], lastb ? e_pack0 : nullptr,
+                         lastb ? e_pack1 : nullptr);
     }
 }
 
@@ -397,11 +433,16 @@ void fetch_leaf_stats(pipsgpu_ctx* ctx) {
     }
 }
 
-// static-order LDL^T on the tensor pipe (x0 block first; exact for quasi-definite Schur complements)
+// static-order blocked LDL^T (x0 block first; exact for quasi-definite Schur complements): right-looking with panels of
+// 128 columns. Per panel: ldlt_diag_kernel (diagonal block + its inverse), one GEMM for the panel below it
+// (W21 = A21 X^T, L21 = W21 D^-1) and the trailing update A22 -= L21 W21^T on the FP64 tensor pipe, all three fed by TMA.
+// Look-ahead: the first block column of the trailing update (c1) is done first; the next panel's diagonal block and panel
+// GEMM then run on the high-priority side stream next to the rest of the trailing update (c2).
 void sc_factorize_static(pipsgpu_sc* sc) {
     pipsgpu_ctx* ctx = sc->ctx;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->stream, s2 = ctx->stream_hi;
     const int n = sc->n;
+    const int64_t ld = sc->ldf;
     CUDA_CHECK(cudaMemsetAsync(sc->stats.p, 0, sizeof(int) * 4, s));
     CUDA_CHECK(cudaMemsetAsync(sc->ptype.p, 0, sizeof(int8_t) * (size_t)(n + 1), s));
     CUDA_CHECK(cudaMemsetAsync(sc->Dinv_e.p, 0, sizeof(double) * (size_t)(n + 1), s));
@@ -410,12 +451,50 @@ void sc_factorize_static(pipsgpu_sc* sc) {
     // perturbation (iparm[9], PardisoProjectIndefSolver.C:34-61) but scale-aware; the oracle applies the same rule
     const double eps_rel = 1e-12;
     launch_row_absmax(sc->A.p, n, n, sc->scale.p, s);
-    CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
-    for (int kb = 0; kb < n; kb += DENSE_NB) {
-        const int bw = std::min(DENSE_NB, n - kb);
-        launch_dense_diag(sc->Fm.p, n, kb, bw, sc->n0, eps_rel, sc->scale.p, sc->D.p, sc->Dinv.p, sc->diagW.p, sc->stats.p, s);
-        launch_dense_trsm(sc->Fm.p, n, n, kb, bw, sc->Dinv.p, sc->diagW.p, sc->Wbuf.p, s);
-        launch_dense_syrk(sc->Fm.p, n, n, kb, bw, sc->Wbuf.p, s);
+    CUDA_CHECK(cudaMemcpy2DAsync(sc->Fm.p, sizeof(double) * (size_t)ld, sc->A.p, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n,
+                                 (size_t)n, cudaMemcpyDeviceToDevice, s));
+    const int NB = DENSE_PANEL;
+    const int npanels = (n + NB - 1) / NB;
+    auto diag_and_panel = [&](int k, cudaStream_t st) {
+        const int kb = k * NB, bw = std::min(NB, n - kb);
+        launch_ldlt_diag(sc->Fm.p, ld, kb, bw, sc->n0, eps_rel, sc->scale.p, sc->D.p, sc->Dinv.p,
+                         sc->Xall.p + (size_t)k * NB * NB, sc->stats.p, st);
+        const int rows = n - kb - bw;
+        if (rows <= 0) return;
+        GemmArgs g{};
+        g.a_row0 = kb + bw; g.a_col0 = kb; g.b_row0 = k * NB; g.b_col0 = 0; g.K = NB;
+        g.m_tiles = (rows + GEMM_TILE - 1) / GEMM_TILE; g.n_tiles = 1; g.lower = 0;
+        g.C = sc->Fm.p; g.ldc = ld; g.c_row0 = kb + bw; g.c_col0 = kb; g.c_rows = n; g.c_cols = bw;
+        g.C2 = sc->Wbuf.p + (size_t)(k & 1) * (size_t)n * NB; g.ldc2 = NB; g.scale = sc->Dinv.p + kb; g.map = nullptr;
+        launch_dgemm_nt(GEMM_EPI_PANEL, sc->tmF, sc->tmX, g, st);
+    };
+    auto trailing = [&](int k, bool first_column, cudaStream_t st) {
+        const int kb = k * NB;
+        const int t0 = kb + NB + (first_column ? 0 : NB);       // c1: block column t0 .. t0+127; c2: everything right of it
+        const int rows = n - t0;
+        if (rows <= 0) return;
+        GemmArgs g{};
+        g.a_row0 = t0; g.a_col0 = kb; g.b_row0 = first_column ? t0 : t0; g.b_col0 = 0; g.K = NB;
+        g.m_tiles = (rows + GEMM_TILE - 1) / GEMM_TILE; g.n_tiles = 1; g.lower = first_column ? 0 : 1;
+        g.C = sc->Fm.p; g.ldc = ld; g.c_row0 = t0; g.c_col0 = t0; g.c_rows = n; g.c_cols = n;
+        g.C2 = nullptr; g.ldc2 = 0; g.scale = nullptr; g.map = nullptr;
+        launch_dgemm_nt(GEMM_EPI_TRAIL, sc->tmF, sc->tmW[k & 1], g, st);
+    };
+    diag_and_panel(0, s);
+    for (int k = 0; k + 1 < npanels; ++k) {
+        trailing(k, true, s);
+        const bool ahead = s2 != nullptr && (n - (k + 2) * NB) > 0;     // something is left for c2 to overlap with
+        if (ahead) {
+            CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
+            CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
+            diag_and_panel(k + 1, s2);
+            CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
+            trailing(k, false, s);
+            CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        } else {
+            trailing(k, false, s);
+            diag_and_panel(k + 1, s);
+        }
     }
 }
 
@@ -428,9 +507,11 @@ void sc_factorize_bk(pipsgpu_sc* sc) {
     CUDA_CHECK(cudaMemsetAsync(sc->ptype.p, 0, sizeof(int8_t) * (size_t)(n + 1), s));
     CUDA_CHECK(cudaMemsetAsync(sc->Dinv_e.p, 0, sizeof(double) * (size_t)(n + 1), s));
     launch_iota(sc->perm.p, n, s);
-    CUDA_CHECK(cudaMemcpyAsync(sc->Fm.p, sc->A.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, s));
+    const int ld = (int)sc->ldf;
+    CUDA_CHECK(cudaMemcpy2DAsync(sc->Fm.p, sizeof(double) * (size_t)ld, sc->A.p, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n,
+                                 (size_t)n, cudaMemcpyDeviceToDevice, s));
     for (int step = 0; step < n; ++step)
-        launch_bk_step(sc->Fm.p, n, n, step, sc->perm.p, sc->ptype.p, sc->D.p, sc->De.p, sc->Dinv.p, sc->Dinv_e.p, sc->Wc.p,
+        launch_bk_step(sc->Fm.p, ld, n, step, sc->perm.p, sc->ptype.p, sc->D.p, sc->De.p, sc->Dinv.p, sc->Dinv_e.p, sc->Wc.p,
                        sc->bk.p, 1e-12, sc->scale.p, s);
 }
 
@@ -439,7 +520,7 @@ void sc_factorize_bk(pipsgpu_sc* sc) {
 void sc_factorize_impl(pipsgpu_sc* sc) {
     pipsgpu_ctx* ctx = sc->ctx;
     sc_factorize_static(sc);
-    int h[4];
+    int* h = sc->h_stats;
     CUDA_CHECK(cudaMemcpyAsync(h, sc->stats.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     sc->inertia[0] = h[0]; sc->inertia[1] = h[1]; sc->inertia[2] = h[2]; sc->n_perturbed = h[3];
@@ -453,6 +534,28 @@ void sc_factorize_impl(pipsgpu_sc* sc) {
         sc->used_bk = true;
     }
     sc->factorized = true;
+}
+
+// x <- SC^-1 x for nrhs device-resident right-hand sides (stride xstride): blocked multi-CTA solve with the static-order
+// factors, the single-CTA permuted solve after a Bunch-Kaufman factorisation
+void sc_solve_device(pipsgpu_sc* sc, double* x, int nrhs, int64_t xstride) {
+    pipsgpu_ctx* ctx = sc->ctx;
+    cudaStream_t s = ctx->stream;
+    if (sc->used_bk) {
+        launch_dense_solve(sc->Fm.p, (int)sc->ldf, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, x, nrhs, xstride,
+                           sc->swork.p, s);
+        return;
+    }
+    const int nb = sc->n / 64 + 2;
+    for (int r = 0; r < nrhs; ++r) {
+        if (sc->ts_epoch >= (1 << 30)) {
+            CUDA_CHECK(cudaMemsetAsync(sc->tflags.p, 0, sizeof(int) * sc->tflags.n, s));
+            sc->ts_epoch = 0;
+        }
+        sc->ts_epoch += 1;
+        launch_dense_trisolve(sc->Fm.p, sc->ldf, sc->n, sc->Xall.p, sc->Dinv.p, x + (int64_t)r * xstride, sc->ybuf.p, sc->tflags.p,
+                              sc->tflags.p + nb, sc->ts_epoch, ctx->sm_count, s);
+    }
 }
 
 void sc_allreduce_impl(pipsgpu_sc* sc) {
@@ -490,6 +593,7 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     // function attributes (dynamic shared-memory opt-in) are per device: set them for every context's device
     CUDA_CHECK(init_psolve_attributes());
     CUDA_CHECK(init_kernel_attributes());
+    CUDA_CHECK(init_dense_attributes());
     if (const char* e = std::getenv("PIPSGPU_SOLVE")) {
         ctx->solve_by_level = std::string(e) == "level";
     }
@@ -503,6 +607,11 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_GROUP_LISTS")) ctx->group_lists = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_BP_THREADS")) ctx->bp_threads = (std::atoi(e) == 128) ? 128 : 256;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi_prio));
+    }
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     *out = ctx.release();
@@ -519,6 +628,8 @@ int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx) {
     if (ctx->h_dvals) cudaFreeHost(ctx->h_dvals);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->stream_hi) { cudaStreamSynchronize(ctx->stream_hi); cudaStreamDestroy(ctx->stream_hi); }
+    for (auto& e : ctx->ev_grp) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -561,6 +672,41 @@ int pipsgpu_bench_dmma_peak(pipsgpu_ctx* ctx, double* tflops) {
     for (int rep = 0; rep < 3; ++rep) {
         CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
         const double fl = launch_dmma_peak(out.p, iters, ctas, ctx->stream);
+        CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_bench_dgemm(pipsgpu_ctx* ctx, int n, double* tflops) {
+    PIPSGPU_TRY
+    require_device(ctx);
+    if (!tflops || n < GEMM_TILE) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_bench_dgemm: invalid argument");
+    n = (n / GEMM_TILE) * GEMM_TILE;
+    DevBuf<double> A, C;
+    A.alloc((size_t)n * n); C.alloc((size_t)n * n);
+    CUDA_CHECK(cudaMemsetAsync(A.p, 0, sizeof(double) * (size_t)n * n, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(C.p, 0, sizeof(double) * (size_t)n * n, ctx->stream));
+    TMap tm;
+    make_tmap(&tm, A.p, n, n, n);
+    GemmArgs g{};
+    g.K = n; g.m_tiles = n / GEMM_TILE; g.n_tiles = g.m_tiles; g.lower = 1;
+    g.C = C.p; g.ldc = n; g.c_rows = n; g.c_cols = n;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    launch_dgemm_nt(GEMM_EPI_TRAIL, tm, tm, g, ctx->stream);      // warm-up
+    double best = 0.0;
+    const double fl = 2.0 * (double)(g.m_tiles * (g.m_tiles + 1) / 2) * GEMM_TILE * GEMM_TILE * (double)n;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+        launch_dgemm_nt(GEMM_EPI_TRAIL, tm, tm, g, ctx->stream);
         CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
         CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -705,21 +851,40 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     // ---- placement ----
     int64_t npos = 0, nfr = 0, Ltot = 0, Ctot = 0, updtot = 0, nnzK = 0, nnzB = 0, nrows = 0, nchild = 0;
     int nlev = 0;
+    // batches: consecutive leaves whose contribution blocks fit PIPSGPU_BATCH_GB (default 12 GB)
+    double batch_gb = 12.0;
+    if (const char* e = std::getenv("PIPSGPU_BATCH_GB")) batch_gb = std::max(0.001, std::atof(e));
+    const int64_t c_cap = (int64_t)(batch_gb * 1e9 / 8.0);
+    int64_t cfill = 0;
+    ctx->batch_ptr.assign(1, 0);
+    std::vector<char> batch_start((size_t)nl + 1, 0);
     for (auto* lf : ctx->leaves) {
         const LeafSymbolic& S = lf->S;
         lf->pos_off = (int)npos; lf->front_base = (int)nfr;
         lf->Lbase = Ltot; lf->Lsize = S.Loff.empty() ? 0 : S.Loff.back();
-        lf->Cbase = Ctot; lf->Csize = S.Coff.empty() ? 0 : S.Coff.back();
+        lf->Csize = S.Coff.empty() ? 0 : S.Coff.back();
+        if (cfill > 0 && cfill + lf->Csize > c_cap) {
+            ctx->batch_ptr.push_back(lf->index);
+            batch_start[(size_t)lf->index] = 1;
+            cfill = 0;
+        }
+        lf->batch = (int)ctx->batch_ptr.size() - 1;
+        lf->Cbase = cfill;
+        cfill += lf->Csize;
+        Ctot = std::max(Ctot, cfill);
         lf->kval_off = nnzK; lf->bval_off = nnzB; lf->upd_base = updtot;
         int64_t us = 0;
         for (int s = 0; s < S.ns; ++s) us += S.sn_na[s];
         lf->upd_size = us;
-        npos += lf->n; nfr += S.ns; Ltot += lf->Lsize; Ctot += lf->Csize; updtot += us;
+        npos += lf->n; nfr += S.ns; Ltot += lf->Lsize; updtot += us;
         nnzK += (int64_t)lf->val.size(); nnzB += (int64_t)lf->bval.size();
         nrows += (int64_t)S.rowidx.size(); nchild += (int64_t)S.child_idx.size();
         nlev = std::max(nlev, S.nlevels);
         if (npos > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "too many KKT rows for one context (int32 positions)");
     }
+    ctx->batch_ptr.push_back(nl);
+    ctx->ev_grp.resize(2 * (ctx->batch_ptr.size() - 1));
+    for (auto& e : ctx->ev_grp) CUDA_CHECK(cudaEventCreate(&e));
     ctx->npos = npos; ctx->nfronts = nfr; ctx->Ltot = Ltot; ctx->Ctot = Ctot; ctx->updtot = updtot;
     ctx->nnzK = nnzK; ctx->nnzB = nnzB; ctx->nlevels = nlev;
 
@@ -742,10 +907,17 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     for (int l = 0; l < ngroups; ++l) ctx->level_ptr[l + 1] = ctx->level_ptr[l] + level_count[l];
     std::vector<int> level_fronts((size_t)nfr), lfill(ctx->level_ptr.begin(), ctx->level_ptr.end() - 1);
     std::vector<int64_t> wfill(nlev, 0), xyfill(nlev, 0);
+    int64_t wlev_max = 0, xy_max = 0, xy_run = 0;      // maxima over the batches
+    auto close_batch_scratch = [&]() {
+        for (int l = 0; l < nlev; ++l) { wlev_max = std::max(wlev_max, wfill[l]); xy_max = std::max(xy_max, xyfill[l]); wfill[l] = 0; xyfill[l] = 0; }
+        xy_max = std::max(xy_max, xy_run);
+        xy_run = 0;
+    };
 
     int64_t rows_off = 0, child_off = 0;
     for (auto* lf : ctx->leaves) {
         const LeafSymbolic& S = lf->S;
+        if (batch_start[(size_t)lf->index]) close_batch_scratch();
         lf->level_begin.assign(ngroups, 0); lf->level_count.assign(ngroups, 0);
         for (int l = 0; l < ngroups; ++l) lf->level_begin[l] = lfill[l];
         auto b2sc = [&](int b) { return b < lf->n0 ? b : b + lf->my0; };
@@ -767,9 +939,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             fd.Woff = wfill[ol];
             int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
             wfill[ol] += (wsz + 1) & ~int64_t(1);
-            if (ctx->xform) {      // persistent: pack_solve reads X after the last level
-                fd.XYoff = ctx->XYtot;
-                ctx->XYtot += (int64_t)padded_width(fd.w) * padded_width(fd.w);
+            if (ctx->xform) {      // persistent within a batch: pack_solve reads X after the batch's last level
+                fd.XYoff = xy_run;
+                xy_run += (int64_t)padded_width(fd.w) * padded_width(fd.w);
             } else {
                 fd.XYoff = xyfill[ol];
                 xyfill[ol] += (int64_t)padded_width(fd.w) * padded_width(fd.w);
@@ -808,6 +980,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         lf->stats8[0] = S.nnzL; lf->stats8[1] = S.nnzL_border; lf->stats8[2] = stored; lf->stats8[3] = S.ns;
         lf->stats8[4] = S.nlevels; lf->stats8[5] = S.n_pairs; lf->stats8[6] = S.max_m; lf->stats8[7] = lf->Csize;
         lf->flops = S.flops_factor;
+        lf->flops4[0] = S.flops_factor; lf->flops4[1] = lf->flops4[2] = lf->flops4[3] = 0.0;
+        for (int s = 0; s < S.ns; ++s) {
+            const double w = S.sn_col[s + 1] - S.sn_col[s], na = S.sn_na[s], nb = S.sn_nb[s], u = na + nb;
+            lf->flops4[1] += w * nb * (nb + 1.0);      // 2 * w * nb (nb + 1) / 2
+            lf->flops4[2] += w * u * (u + 1.0);        // every update entry (ancestor columns and border x border), lower
+            lf->flops4[3] += 2.0 * w * w * u;          // W21 = A21 X^T
+        }
         rows_off += (int64_t)S.rowidx.size();
         child_off += (int64_t)S.child_idx.size();
         // the symbolic arrays are now on their way to the device; drop the big host copies
@@ -831,12 +1010,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             for (int t = 0; t < fd.na + fd.nb; ++t) invmap[(size_t)fd.inv_off + relidx[(size_t)fd.rows_off + t]] = t;
         }
     }
-    ctx->Wtot = 0;
-    for (int l = 0; l < nlev; ++l) ctx->Wtot = std::max(ctx->Wtot, wfill[l]);
-    if (!ctx->xform) {
-        ctx->XYtot = 0;
-        for (int l = 0; l < nlev; ++l) ctx->XYtot = std::max(ctx->XYtot, xyfill[l]);
-    }
+    close_batch_scratch();
+    ctx->Wtot = wlev_max;
+    ctx->XYtot = xy_max;
     // ---- factorisation launch lists: fronts grouped by (level, small|big), by leaf inside a group ----
     std::vector<int> fl_fronts((size_t)nfr);
     {
@@ -869,7 +1045,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     std::vector<GTile> gtiles;
     std::vector<char> grouped((size_t)nfr, 0);
     if (ctx->grouping) {
+        int64_t gw_run = 0, gw_max = 0;      // persistent (per batch) W21 scratch of the grouped fronts, behind the per-level area
         for (auto* lf : ctx->leaves) {
+            if (batch_start[(size_t)lf->index]) { gw_max = std::max(gw_max, gw_run); gw_run = 0; }
             const BorderGroups& G = lf->G;
             const int ng = (int)G.root.size();
             for (int s2 = 0; s2 < lf->S.ns; ++s2) grouped[(size_t)lf->front_base + s2] = G.grouped[(size_t)s2];
@@ -892,9 +1070,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                     // the member's W21 = L21 D scratch moves from the per-level area to a persistent one: the group SYRK
                     // runs after the last level and reads (L_B D) from there instead of rebuilding it from L and D
                     FrontDesc& fdm = fronts[(size_t)f];
-                    fdm.Woff = ctx->Wtot;
+                    fdm.Woff = wlev_max + gw_run;
                     const int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
-                    ctx->Wtot += (wsz + 1) & ~int64_t(1);
+                    gw_run += (wsz + 1) & ~int64_t(1);
                     mb.Lb_off = fd.Loff + fd.w + fd.na; mb.Wb_off = fdm.Woff + fd.na;
                     mb.m = fd.w + fd.na + fd.nb; mb.u = fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f; mb.pad = 0;
                     gmembers.push_back(mb);
@@ -922,6 +1100,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             lf->gtile_count = (int64_t)gtiles.size() - lf->gtile_begin;
             lf->G = BorderGroups();
         }
+        ctx->Wtot = wlev_max + std::max(gw_max, gw_run);
     }
     ctx->ngtiles = (int64_t)gtiles.size();
     // ---- update tiles of the big fronts, grouped by (level, leaf); grouped fronts only keep the ancestor columns ----
@@ -1085,20 +1264,20 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         ctx->nsub_units = (int)subs.size();
         ctx->ps_epoch_max = (1 << 30) / maxchild - 2;   // the child counters are cumulative: nchild * epoch must not wrap
         ctx->nchunks = (int)chunk_front.size();
-        ctx->sfront.upload(sf, s); ctx->sunits.upload(units, s); ctx->chunk_front.upload(chunk_front, s);
-        ctx->chunk_idx.upload(chunk_idx, s); ctx->slots.upload(slots, s);
+        ctx->sfront.upload(sf, s); ctx->sunits.upload(units, s); ctx->slots.upload(slots, s);
         {   // the same chunk list grouped by leaf
             std::vector<int> ord(chunk_front.size());
             std::iota(ord.begin(), ord.end(), 0);
             auto leaf_of = [&](int q) { return fronts[(size_t)sf[(size_t)chunk_front[(size_t)q]].front].leaf; };
             std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return leaf_of(x) < leaf_of(y); });
             std::vector<int> cf(ord.size()), ci(ord.size());
-            for (auto* lf : ctx->leaves) { lf->chunk_begin = 0; lf->chunk_count = 0; }
+            for (auto* lf : ctx->leaves) lf->chunk_count = 0;
             for (size_t t = 0; t < ord.size(); ++t) {
                 cf[t] = chunk_front[(size_t)ord[t]]; ci[t] = chunk_idx[(size_t)ord[t]];
-                pipsgpu_leaf* lf = ctx->leaves[(size_t)leaf_of(ord[t])];
-                if (lf->chunk_count++ == 0) lf->chunk_begin = (int)t;
+                ++ctx->leaves[(size_t)leaf_of(ord[t])]->chunk_count;
             }
+            int run = 0;
+            for (auto* lf : ctx->leaves) { lf->chunk_begin = run; run += lf->chunk_count; }
             ctx->chunk_front_l.upload(cf, s); ctx->chunk_idx_l.upload(ci, s);
         }
         ctx->SL.alloc((size_t)off + 2);
@@ -1275,6 +1454,16 @@ int pipsgpu_leaf_get_stats(pipsgpu_leaf* lf, int64_t out[8], double* flops) {
     PIPSGPU_CATCH
 }
 
+int pipsgpu_leaf_get_flops(pipsgpu_leaf* lf, double out[4]) {
+    PIPSGPU_TRY
+    if (!lf || !out) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_get_flops: null argument");
+    if (!lf->ctx->committed) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_leaf_get_flops: context not committed");
+    for (int i = 0; i < 4; ++i) out[i] = lf->flops4[i];
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_ctx_num_batches(pipsgpu_ctx* ctx) { return ctx ? (int)ctx->batch_ptr.size() - 1 : -1; }
+
 int pipsgpu_leaf_download_factor(pipsgpu_leaf* lf, double* L, double* dinv_d, double* dinv_e) {
     PIPSGPU_TRY
     if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_download_factor: null leaf");
@@ -1306,10 +1495,26 @@ int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsg
     sc->ctx = ctx; sc->n0 = n0; sc->my0 = my0; sc->myl = myl; sc->mzl = mzl;
     sc->n = n0 + my0 + myl + mzl;
     const size_t n = (size_t)sc->n;
-    sc->A.alloc(n * n + 1); sc->Fm.alloc(n * n + 1); sc->D.alloc(n + 1); sc->Dinv.alloc(n + 1); sc->diagW.alloc(DENSE_NB * DENSE_NB);
+    sc->ldf = (int64_t)((n + 15) & ~size_t(15));
+    if (sc->ldf == 0) sc->ldf = 16;
+    const size_t ldf = (size_t)sc->ldf;
+    const size_t npanels = (n + DENSE_PANEL - 1) / DENSE_PANEL;
+    sc->A.alloc(n * n + 1); sc->Fm.alloc(std::max<size_t>(n, 1) * ldf); sc->D.alloc(n + 1); sc->Dinv.alloc(n + DENSE_PANEL + 1);
     sc->De.alloc(n + 1); sc->Dinv_e.alloc(n + 1); sc->Wc.alloc(2 * n + 2); sc->perm.alloc(n + 1); sc->ptype.alloc(n + 1);
     sc->bk.alloc(1); sc->swork.alloc(n + 1); sc->scale.alloc(n + 1);
-    sc->Wbuf.alloc(n * DENSE_NB + 2); sc->stats.alloc(4); sc->rhs.alloc(n + 1);
+    sc->Wbuf.alloc(2 * std::max<size_t>(n, 1) * DENSE_PANEL); sc->stats.alloc(4); sc->rhs.alloc(n + 1);
+    sc->Xall.alloc(std::max<size_t>(npanels, 1) * DENSE_PANEL * DENSE_PANEL); sc->ybuf.alloc(n + 64);
+    sc->tflags.alloc(2 * (n / 64 + 2));
+    CUDA_CHECK(cudaMemsetAsync(sc->tflags.p, 0, sizeof(int) * sc->tflags.n, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(sc->Dinv.p, 0, sizeof(double) * sc->Dinv.n, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(sc->Fm.p, 0, sizeof(double) * sc->Fm.n, ctx->stream));
+    CUDA_CHECK(cudaMallocHost(&sc->h_stats, sizeof(int) * 4));
+    if (n > 0) {
+        make_tmap(&sc->tmF, sc->Fm.p, (int64_t)n, (int64_t)n, sc->ldf);
+        make_tmap(&sc->tmW[0], sc->Wbuf.p, (int64_t)n, DENSE_PANEL, DENSE_PANEL);
+        make_tmap(&sc->tmW[1], sc->Wbuf.p + n * DENSE_PANEL, (int64_t)n, DENSE_PANEL, DENSE_PANEL);
+        make_tmap(&sc->tmX, sc->Xall.p, (int64_t)(npanels * DENSE_PANEL), DENSE_PANEL, DENSE_PANEL);
+    }
     CUDA_CHECK(cudaMemsetAsync(sc->A.p, 0, sizeof(double) * (n * n + 1), ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *out = sc.release();
@@ -1318,7 +1523,11 @@ int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsg
 
 int pipsgpu_sc_destroy(pipsgpu_sc* sc) {
     PIPSGPU_TRY
-    if (sc) { cudaSetDevice(sc->ctx->device); cudaStreamSynchronize(sc->ctx->stream); delete sc; }
+    if (sc) {
+        cudaSetDevice(sc->ctx->device);
+        cudaStreamSynchronize(sc->ctx->stream);
+        delete sc;
+    }
     PIPSGPU_CATCH
 }
 
@@ -1392,8 +1601,7 @@ int pipsgpu_sc_solve(pipsgpu_sc* sc, int nrhs, double* rhs) {
     x.alloc(n * (size_t)std::max(nrhs, 1));
     CUDA_CHECK(cudaMemcpyAsync(x.p, rhs, sizeof(double) * n * nrhs, cudaMemcpyHostToDevice, s));
     sc->swork.ensure(n * (size_t)std::max(nrhs, 1));
-    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, x.p, nrhs, (int64_t)n,
-                       sc->swork.p, s);
+    sc_solve_device(sc, x.p, nrhs, (int64_t)n);
     CUDA_CHECK(cudaMemcpyAsync(rhs, x.p, sizeof(double) * n * nrhs, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     PIPSGPU_CATCH
@@ -1540,6 +1748,12 @@ static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[
     }
     CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[12], k->ev[13]));
     k->ktimes[1] = ms;
+    k->ktimes[3] = 0.0;
+    if (ctx->grp_timed)
+        for (size_t b = 0; b + 1 < ctx->ev_grp.size(); b += 2) {
+            if (cudaEventElapsedTime(&ms, ctx->ev_grp[b], ctx->ev_grp[b + 1]) == cudaSuccess) k->ktimes[3] += ms;
+            else (void)cudaGetLastError();
+        }
 }
 
 int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,
@@ -1619,7 +1833,7 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
         launch_csr_tmult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, -1.0, k->t3.p, r, s);
     }
     CUDA_CHECK(cudaEventRecord(k->ev[14], s));
-    launch_dense_solve(sc->Fm.p, sc->n, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, r, 1, sc->n, sc->swork.p, s);
+    sc_solve_device(sc, r, 1, sc->n);
     CUDA_CHECK(cudaEventRecord(k->ev[15], s));
     launch_vec_copy(b, r, n0 + my0, s);
     if (mz0 > 0) {

@@ -80,7 +80,7 @@ def compressed_kkt_residual(lp, dd, nomegainv, rhs, sol, reg=None, reduce_root=N
 class CudaRootLinearSystem:
     """Root linear system of a two-level block-angular LP on one GPU (one rank of the reference)."""
 
-    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0, stream=None):
+    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0, stream=None, kkts=None):
         self.lp = lp
         root = lp.root
         self.rank, self.n_ranks = rank, n_ranks
@@ -94,8 +94,8 @@ class CudaRootLinearSystem:
         # the same effect with DistributedDummyLinearSystem children (LS/DistributedRootLinearSystem.C:725-757)
         self.kkt = capi.KKT(self.ctx, root.n, root.my, root.mz, lp.myl, lp.mzl, root.A, root.C, root.F, root.G)
         self.leaves = []
-        for ch in lp.children:
-            krow, jcol, val = create_kkt_lower(ch)
+        for k, ch in enumerate(lp.children):
+            krow, jcol, val = kkts[k] if kkts is not None else create_kkt_lower(ch)      # create_kkt, possibly precomputed
             leaf = capi.Leaf(self.ctx, ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val)
             leaf.set_border(root.n, root.my, lp.myl, lp.mzl, ch.A, ch.C, ch.F, ch.G)
             self.kkt.add_leaf(leaf)
