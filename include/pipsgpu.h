@@ -89,6 +89,11 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads);
  * Any pointer may be NULL (= zeros). Marks the leaf as changed. */
 int pipsgpu_leaf_set_diagonal(pipsgpu_leaf* leaf, const double* dd, const double* nomegainv, double regP,
                               double regDy, double regDz);
+/* this leaf's own regularisation (LS/DistributedLeafLinearSystem.C:121-143: every node of the tree carries its own
+ * primal / dual regularisation, chosen by its RegularizationStrategy in LinearSystem::factorize_with_correct_inertia,
+ * LS/LinearSystem.C:296-325). The values are ADDED to the regP / regDy / regDz of every later diagonal refresh of this
+ * leaf (pipsgpu_leaf_set_diagonal, pipsgpu_kkt_factorize) until changed again. */
+int pipsgpu_leaf_set_regularization(pipsgpu_leaf* leaf, double regP, double regDy, double regDz);
 /* full value refresh of the lower CSR (Ma27Solver.C:317-324 copies all values on every matrixChanged) */
 int pipsgpu_leaf_set_values(pipsgpu_leaf* leaf, const double* val);
 /* DoubleLinearSolver::matrixChanged() + get_inertia(): numeric LDL^T of this leaf only (batched entry point below
@@ -182,6 +187,15 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* kkt, const double* dd0, const double* nom
  * Lsolve (LS/sLinsysRootAug.C:340-341) runs over NCCL when a communicator is attached; on ranks > 0 the incoming b0
  * is ignored exactly as in the reference (:332-333). */
 int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* kkt, double* b0, double* b_leaves);
+/* LinearSystem::solveXYZS with OUTER_SOLVE = 2 (LS/LinearSystem.C:449-548): solveCompressedBiCGStab (:550-798) on the
+ * device - BiCGStab on the (regularised) full KKT system in the node layout of DistributedVector, preconditioned by
+ * solveCompressed, full-KKT matvec = system_mult (:809-844). b0 / b_leaves as for pipsgpu_kkt_solve_compressed: the
+ * right-hand side goes down once, the solution comes back once (in place); dot products are reduced over NCCL.
+ * tol = OUTER_BICG_TOL, max_iter = OUTER_BICG_MAX_ITER (75). *status receives IterativeSolverSolutionStatus
+ * (LS/LinearSystem.h:45-47: -1 max iterations, 0 converged, 1 skipped, 3 stagnation, 4 breakdown, 5 diverged), *n_iter the
+ * iteration count (0 when skipped), *rel_residual ||b - K x|| / ||b||. Any of the three may be NULL. */
+int pipsgpu_kkt_solve(pipsgpu_kkt* kkt, double* b0, double* b_leaves, double tol, int max_iter, int* status, int* n_iter,
+                      double* rel_residual);
 /* device-resident variants for measuring the kernels without PCIe traffic: reuse the diagonals / the right-hand side
  * of the last pipsgpu_kkt_factorize / pipsgpu_kkt_solve_compressed call, which stay in HBM. solve_compressed_resident
  * is asynchronous (no D2H, no host synchronisation); factorize_resident synchronises once to read the inertia. */

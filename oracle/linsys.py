@@ -483,3 +483,47 @@ def dense_reference_sc(lp, dd, nomegainv, regDy=0.0):
     d = np.arange(n0, n0 + my0 + myl)
     SC[d, d] -= regDy
     return SC
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# inertia-correcting regularisation, restated for ONE leaf on the C multifrontal oracle (oracle/mf_ldlt.c):
+# LinearSystem::factorize_with_correct_inertia (LinearSystems/LinearSystem.C:296-325) with the IPOPT strategy
+# (LinearSystems/IpoptRegularization.cpp:30-92, constants IpoptRegularization.hpp:22-27).
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_leaf_inertia_loop(lp, i, dd_i, nom_i, symbolic_factory, barrier_parameter=1.0, primal_last=0.0):
+    """returns (final (regP, regDy, regDz), number of factorisations, list of inertias seen)"""
+    from . import mf
+    ch = lp.children[i]
+    krow, jcol, val, diag_pos, nB, brow, bcol, bval = mf.leaf_kkt_and_border(lp, i)
+    sym = symbolic_factory(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol).export()
+    leaf = mf.MfLeaf(sym)
+    knorm = max(1.0, float(np.abs(val).max(initial=0.0)))
+    expected = (ch.n, ch.my + ch.mz, 0)
+
+    def factor(reg):
+        v = val.copy()
+        v[diag_pos[:ch.n]] = dd_i + reg[0]
+        v[diag_pos[ch.n:ch.n + ch.my]] = -reg[1]
+        v[diag_pos[ch.n + ch.my:]] = nom_i - reg[2]
+        inertia, _ = leaf.factorize(v, bval, None, knorm=knorm)
+        return inertia
+
+    reg = (0.0, 0.0, 0.0)                      # IpoptRegularization::get_default_regularization
+    seen = [factor(reg)]
+    primal_cur = -1.0
+    dual_cur = 0.0
+    first = True
+    while seen[-1] != expected:
+        if first:                              # get_regularization_new_matrix
+            first = False
+            dual_cur = barrier_parameter ** 0.25 if seen[-1][2] else 1e-4
+            primal_cur = 1e-4 if primal_last == 0.0 else max(1e-20, primal_last / 3.0)
+        else:                                  # get_regularization_nth_try
+            primal_cur *= 100.0 if primal_last == 0.0 else 8.0
+            if primal_cur > 1e40:
+                raise RuntimeError("cannot factorize matrix after excessive error correction")
+        reg = (primal_cur, dual_cur, dual_cur)
+        seen.append(factor(reg))
+        if len(seen) > 60:
+            raise RuntimeError("inertia loop did not terminate")
+    return reg, len(seen), seen

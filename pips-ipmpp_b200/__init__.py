@@ -5,3 +5,4 @@ The directory name contains a hyphen, so import it through `__graft_entry__.load
 from . import problem  # noqa: F401
 from . import capi  # noqa: F401
 from . import linsys  # noqa: F401
+from . import regularization  # noqa: F401

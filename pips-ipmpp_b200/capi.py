@@ -219,6 +219,9 @@ class Leaf:
         _check(lib().pipsgpu_leaf_set_diagonal(self.h, _ip(dd), _ip(nomegainv), C.c_double(regP), C.c_double(regDy),
                                                C.c_double(regDz)))
 
+    def set_regularization(self, regP=0.0, regDy=0.0, regDz=0.0):
+        _check(lib().pipsgpu_leaf_set_regularization(self.h, C.c_double(regP), C.c_double(regDy), C.c_double(regDz)))
+
     def set_values(self, val):
         val = _f64(val)
         _check(lib().pipsgpu_leaf_set_values(self.h, _ip(val)))
@@ -355,6 +358,14 @@ class KKT:
         p0 = C.c_void_p(b0) if isinstance(b0, int) else _ip(b0)
         pl = C.c_void_p(b_leaves) if isinstance(b_leaves, int) else _ip(b_leaves)
         _check(lib().pipsgpu_kkt_solve_compressed(self.h, p0, pl))
+
+    def solve_bicgstab(self, b0, b_leaves, tol=1e-10, max_iter=75):
+        """device BiCGStab preconditioned by solveCompressed, in place; returns (status, iterations, relative residual)"""
+        p0 = C.c_void_p(b0) if isinstance(b0, int) else _ip(b0)
+        pl = C.c_void_p(b_leaves) if isinstance(b_leaves, int) else _ip(b_leaves)
+        st, it, rr = C.c_int(0), C.c_int(0), C.c_double(0)
+        _check(lib().pipsgpu_kkt_solve(self.h, p0, pl, C.c_double(tol), C.c_int(max_iter), C.byref(st), C.byref(it), C.byref(rr)))
+        return st.value, it.value, rr.value
 
     def factorize_resident(self):
         inertia = np.zeros(3, dtype=np.int32)

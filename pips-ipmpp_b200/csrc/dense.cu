@@ -282,9 +282,12 @@ __global__ void __launch_bounds__(1024, 1) ldlt_diag_kernel(double* __restrict__
                                                             double* __restrict__ Dinv, double* __restrict__ X, int* __restrict__ stats) {
     extern __shared__ double sLd[];                 // L11 (scaled, strictly lower), [DENSE_PANEL][DENSE_PANEL + 1]
     __shared__ double colb[2][DENSE_PANEL];
-    __shared__ double s_dinv[DENSE_PANEL];
-    constexpr int LDS = DENSE_PANEL + 1;
+    __shared__ double s_dinv[DENSE_PANEL], s_d[DENSE_PANEL];
+    __shared__ double s_eps[DENSE_PANEL];          // pivot threshold of every column (a global load per step would sit on
+    constexpr int LDS = DENSE_PANEL + 1;           // the critical path of all 128 steps)
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x < DENSE_PANEL)
+        s_eps[threadIdx.x] = (threadIdx.x < bw) ? eps_rel * fmax(scale[kb + threadIdx.x], 1e-300) : 1.0;
     // ---------------- phase 1: LDL^T, S in registers ----------------
     {
         double S[4][4];
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(1024, 1) ldlt_diag_kernel(double* __restrict__
             __syncthreads();
             double d = colb[p][k];
             const double sg = (kb + k < n0) ? 1.0 : -1.0;
-            const double eps = eps_rel * fmax(scale[kb + k], 1e-300);
+            const double eps = s_eps[k];
             if (threadIdx.x == 0) {
                 if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
             }
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(1024, 1) ldlt_diag_kernel(double* __restrict__
             const double dinv = 1.0 / d;
             if (threadIdx.x == 0) {
                 if (pert) ++npert;
-                D[kb + k] = d; Dinv[kb + k] = dinv; s_dinv[k] = dinv;
+                s_dinv[k] = dinv; s_d[k] = d;
             }
             double wi[4], wj[4];
 #pragma unroll
@@ -349,6 +352,10 @@ __global__ void __launch_bounds__(1024, 1) ldlt_diag_kernel(double* __restrict__
             }
         if (threadIdx.x == 0 && stats) {
             atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
+        }
+        if (threadIdx.x < bw) {
+            Dinv[kb + threadIdx.x] = s_dinv[threadIdx.x];
+            D[kb + threadIdx.x] = s_d[threadIdx.x];
         }
     }
     __syncthreads();

@@ -1377,23 +1377,35 @@ void launch_bk_step(double* A, int ld, int n, int step, int* perm, int8_t* ptype
     }
 }
 
-// out[i] = max_j |A_sym(i,j)| of the symmetric matrix stored in the lower triangle (non-negative doubles order like
-// their bit patterns, so an integer atomicMax does the reduction)
-__global__ void row_absmax_kernel(const double* __restrict__ A, int ld, int n, double* out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j > i || i >= n) return;
-    const double v = fabs(A[(int64_t)i * ld + j]);
-    if (v > 0.0) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-        atomicMax(reinterpret_cast<unsigned long long*>(out + i), b);
-        atomicMax(reinterpret_cast<unsigned long long*>(out + j), b);
-    }
+// out[i] = max_j |A_sym(i,j)| of the symmetric matrix stored in the lower triangle = max(row part j <= i, column part
+// r >= i). Row part: one warp per row (coalesced); column part: thread per column over chunks of 256 rows (coalesced
+// across the threads of a block), combined with an integer atomicMax (non-negative doubles order like their bit patterns).
+__global__ void __launch_bounds__(256) row_absmax_rows_kernel(const double* __restrict__ A, int ld, int n, double* out) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const double* row = A + (int64_t)i * ld;
+    double m = 0.0;
+    for (int j = lane; j <= i; j += 32) m = fmax(m, fabs(row[j]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.0)
+        atomicMax(reinterpret_cast<unsigned long long*>(out + i), (unsigned long long)__double_as_longlong(m));
+}
+__global__ void __launch_bounds__(128) row_absmax_cols_kernel(const double* __restrict__ A, int ld, int n, double* out) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int r0 = blockIdx.y * 256;
+    if (j >= n || r0 + 255 < j) return;
+    const int lo = max(r0, j), hi = min(n, r0 + 256);
+    double m = 0.0;
+    for (int r = lo; r < hi; ++r) m = fmax(m, fabs(A[(int64_t)r * ld + j]));
+    if (m > 0.0) atomicMax(reinterpret_cast<unsigned long long*>(out + j), (unsigned long long)__double_as_longlong(m));
 }
 void launch_row_absmax(const double* A, int ld, int n, double* out, cudaStream_t s) {
     if (n <= 0) return;
     cudaMemsetAsync(out, 0, sizeof(double) * (size_t)n, s);
-    row_absmax_kernel<<<dim3(cdiv(n, 128), n), 128, 0, s>>>(A, ld, n, out);
+    row_absmax_rows_kernel<<<cdiv(n, 8), 256, 0, s>>>(A, ld, n, out);
+    COUNT_LAUNCH();
+    row_absmax_cols_kernel<<<dim3(cdiv(n, 128), cdiv(n, 256)), 128, 0, s>>>(A, ld, n, out);
     COUNT_LAUNCH();
 }
 

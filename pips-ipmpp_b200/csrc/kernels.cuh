@@ -228,6 +228,16 @@ void launch_vec_div(double* x, const double* d, int n, cudaStream_t s);   // x /
 void launch_vec_copy(double* dst, const double* src, int n, cudaStream_t s);
 void launch_vec_zero(double* dst, int64_t n, cudaStream_t s);
 
+// ---- outer solve on the device (krylov.cu) ----
+void launch_sym_spmv(int64_t nnz, const int* row, const int* col, const double* val, double alpha, const double* x, double* y,
+                     cudaStream_t s);       // y += alpha * K x, K symmetric, lower COO in global positions
+void launch_border_axpy(const int* brow, const int* bidx, const double* val, int64_t nnz, double alpha, const double* u, double* t,
+                        bool transpose, cudaStream_t s);
+void launch_axpby(int64_t n, double a, const double* x, double b, double* y, cudaStream_t s);       // y = a x + b y
+void launch_diag_axpy(int n, double alpha, const double* d, const double* x, double* y, cudaStream_t s);   // y += alpha d .* x
+void launch_dot(int64_t n, const double* x, const double* y, double* partial, double* out, cudaStream_t s);   // deterministic
+constexpr int DOT_SCRATCH = 1024;
+
 int64_t kernel_launch_count();
 // FP64 tensor-pipe peak microbenchmark (register-resident DMMA chains); returns the flops of the launch
 double launch_dmma_peak(double* out, int iters, int ctas, cudaStream_t s);

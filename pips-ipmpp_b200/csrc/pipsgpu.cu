@@ -112,8 +112,9 @@ struct pipsgpu_leaf {
     int64_t gtile_begin = 0, gtile_count = 0;    // sub-range of the border-group tiles of this leaf
     int chunk_begin = 0, chunk_count = 0;        // sub-range of the by-leaf chunk list (solve-pool pack of this leaf only)
     int batch = 0;                               // factorisation batch of this leaf
+    double reg[3] = {0.0, 0.0, 0.0};             // this leaf's own (regP, regDy, regDz), added to every diagonal refresh
     // persistent work buffers of the plug-in multi-RHS solve (pipsgpu_leaf_solve), allocated on first use
-    DevBuf<double> sv_b, sv_x, sv_u, sv_r;
+    DevBuf<double> sv_b, sv_x, sv_u, sv_r, sv_r2;
     DevBuf<int> sv_perm;
     int sv_chunk = 0;
     int64_t stats8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -199,6 +200,13 @@ struct pipsgpu_ctx {
     DevBuf<FrontDesc> fronts;
     DevBuf<LeafDev> leafdev;
     DevBuf<int64_t> kmap, bmap, diagpos;
+    DevBuf<int> kcoo_row, kcoo_col;    // lower COO of every K_i in global (original-order) positions: device KKT matvec
+    // iterative refinement of the leaf solves, applied like PARDISO's iparm[7] = 2 (PardisoProjectSolver.C:72) only when the
+    // factorisation perturbed pivots: up to refine_steps steps  z += K^-1 (b - K z)  with the resident matrix values.
+    // PIPSGPU_REFINE=<steps> (0 disables), PIPSGPU_REFINE_ALWAYS=1 refines after every factorisation.
+    int refine_steps = 2;
+    bool refine_always = false;
+    bool any_perturbed = false;
     // streaming persistent solve (psolve.cu): solve pool + per-front descriptors in sweep order
     DevBuf<SolveFront> sfront;
     DevBuf<SolveUnit> sunits;
@@ -263,7 +271,12 @@ struct pipsgpu_kkt {
     std::vector<pipsgpu_leaf*> leaves;
     std::unique_ptr<pipsgpu_sc> sc;
     bool ready = false;
-    DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl, b0_in, bl_in;
+    DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl, b0_in, bl_in, wl;
+    // device BiCGStab (pipsgpu_kkt_solve): whole-tree vectors [root part (nb0, padded) | leaf part (N)], allocated on first use
+    DevBuf<double> kv[9], kc0, kpartial, kscal;
+    double* h_scal = nullptr;       // pinned
+    int64_t kv_root = 0;            // padded length of the root part
+    ~pipsgpu_kkt() { if (h_scal) cudaFreeHost(h_scal); }
     bool have_diag = false, have_rhs = false;
     double last_regDy = 0.0;
     int64_t sum_nx = 0, sum_nz = 0, sum_n = 0;
@@ -431,6 +444,9 @@ void fetch_leaf_stats(pipsgpu_ctx* ctx) {
         lf->inertia[0] = h[4 * i]; lf->inertia[1] = h[4 * i + 1]; lf->inertia[2] = h[4 * i + 2];
         lf->n_perturbed = h[4 * i + 3];
     }
+    bool any = false;
+    for (auto* lf : ctx->leaves) any = any || lf->n_perturbed > 0;
+    ctx->any_perturbed = any;
 }
 
 // static-order blocked LDL^T (x0 block first; exact for quasi-definite Schur complements): right-looking with panels of
@@ -597,6 +613,8 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_SOLVE")) {
         ctx->solve_by_level = std::string(e) == "level";
     }
+    if (const char* e = std::getenv("PIPSGPU_REFINE")) ctx->refine_steps = std::max(0, std::min(8, std::atoi(e)));
+    if (const char* e = std::getenv("PIPSGPU_REFINE_ALWAYS")) ctx->refine_always = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
     if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
@@ -851,8 +869,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     // ---- placement ----
     int64_t npos = 0, nfr = 0, Ltot = 0, Ctot = 0, updtot = 0, nnzK = 0, nnzB = 0, nrows = 0, nchild = 0;
     int nlev = 0;
-    // batches: consecutive leaves whose contribution blocks fit PIPSGPU_BATCH_GB (default 12 GB)
-    double batch_gb = 12.0;
+    // batches: consecutive leaves whose contribution blocks fit PIPSGPU_BATCH_GB (default 16 GB)
+    double batch_gb = 16.0;
     if (const char* e = std::getenv("PIPSGPU_BATCH_GB")) batch_gb = std::max(0.001, std::atof(e));
     const int64_t c_cap = (int64_t)(batch_gb * 1e9 / 8.0);
     int64_t cfill = 0;
@@ -892,6 +910,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     std::vector<int> rowg((size_t)nrows), relidx((size_t)nrows), child_list((size_t)nchild), gidx((size_t)npos);
     std::vector<int8_t> ptype((size_t)npos), sgn((size_t)npos);
     std::vector<int64_t> kmap((size_t)nnzK), bmap((size_t)nnzB), diagpos((size_t)npos);
+    std::vector<int> kcoo_row((size_t)nnzK), kcoo_col((size_t)nnzK);
     std::vector<double> kval((size_t)nnzK), bval((size_t)nnzB);
     std::vector<int> bg_row((size_t)nnzB), bg_sc((size_t)nnzB), bg_b0((size_t)nnzB);
     std::vector<LeafDev> leafdev((size_t)nl);
@@ -963,6 +982,11 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             kmap[(size_t)lf->kval_off + e] = lf->Lbase + S.kmap[e];
             kval[(size_t)lf->kval_off + e] = lf->val[e];
         }
+        for (int i = 0; i < lf->n; ++i)
+            for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p) {
+                kcoo_row[(size_t)lf->kval_off + p] = lf->pos_off + i;
+                kcoo_col[(size_t)lf->kval_off + p] = lf->pos_off + lf->jcol[p];
+            }
         const int b0tail = lf->n0 + lf->my0;   // b0 layout [x0;y0;z0;yl;zl]: filled in by the kkt (needs mz0)
         (void)b0tail;
         for (size_t e = 0; e < lf->bval.size(); ++e) {
@@ -1152,6 +1176,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->child_list.upload(child_list, s); ctx->level_fronts.upload(level_fronts, s); ctx->gidx.upload(gidx, s);
     ctx->ptype.upload(ptype, s); ctx->sgn.upload(sgn, s); ctx->kmap.upload(kmap, s); ctx->bmap.upload(bmap, s);
     ctx->diagpos.upload(diagpos, s); ctx->Kval.upload(kval, s); ctx->Bval.upload(bval, s);
+    ctx->kcoo_row.upload(kcoo_row, s); ctx->kcoo_col.upload(kcoo_col, s);
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
@@ -1301,6 +1326,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
 
 static void leaf_fill_dvals(pipsgpu_leaf* lf, const double* dd, const double* nomegainv, double regP, double regDy, double regDz) {
     double* d = lf->ctx->h_dvals + lf->pos_off;
+    regP += lf->reg[0]; regDy += lf->reg[1]; regDz += lf->reg[2];
     for (int i = 0; i < lf->nx; ++i) d[i] = (dd ? dd[i] : 0.0) + regP;
     for (int i = 0; i < lf->ny; ++i) d[lf->nx + i] = -regDy;
     for (int i = 0; i < lf->nz; ++i) d[lf->nx + lf->ny + i] = (nomegainv ? nomegainv[i] : 0.0) - regDz;
@@ -1323,6 +1349,13 @@ int pipsgpu_leaf_set_diagonal(pipsgpu_leaf* lf, const double* dd, const double* 
     leaf_push_dvals(ctx, lf->pos_off, lf->n);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     lf->factorized = false;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_leaf_set_regularization(pipsgpu_leaf* lf, double regP, double regDy, double regDz) {
+    PIPSGPU_TRY
+    if (!lf) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_leaf_set_regularization: null leaf");
+    lf->reg[0] = regP; lf->reg[1] = regDy; lf->reg[2] = regDz;
     PIPSGPU_CATCH
 }
 
@@ -1415,6 +1448,7 @@ int pipsgpu_leaf_solve(pipsgpu_leaf* lf, int nrhs, double* rhs) {
     }
     DevBuf<double>&b = lf->sv_b, &xp = lf->sv_x, &up = lf->sv_u;
     DevBuf<int>& lg = lf->sv_perm;
+    const bool refine = ctx->refine_steps > 0 && (lf->n_perturbed > 0 || ctx->refine_always);
     for (int r0 = 0; r0 < nrhs; r0 += chunk) {
         const int nr = std::min(chunk, nrhs - r0);
         CUDA_CHECK(cudaMemcpyAsync(b.p, rhs + (size_t)r0 * n, sizeof(double) * (size_t)n * nr, cudaMemcpyHostToDevice, s));
@@ -1423,6 +1457,28 @@ int pipsgpu_leaf_solve(pipsgpu_leaf* lf, int nrhs, double* rhs) {
         // lands at the start of the private buffers
         SolveArgs sa = ctx->solve_args(xp.p - lf->pos_off, n, up.p - lf->upd_base, std::max<int64_t>(lf->upd_size, 1));
         run_leaf_solve(ctx, sa, nr, lf, lf->pos_off, n);
+        if (refine) {
+            // iterative refinement as in the reference plug-ins (PARDISO iparm[7] = 2, PardisoProjectSolver.C:72; MA27 own
+            // loop, Ma27Solver.C:184-249): x += K^-1 (b - K x) with the resident matrix values, per right-hand side
+            DevBuf<double>& xs = lf->sv_r;      // solution in original order, nr x n
+            xs.ensure((size_t)n * chunk); lf->sv_r2.ensure((size_t)n * chunk);
+            launch_scatter_perm(lg.p, xp.p, xs.p, n, nr, n, s);
+            for (int it = 0; it < ctx->refine_steps; ++it) {
+                double* res = lf->sv_r2.p;
+                CUDA_CHECK(cudaMemcpyAsync(res, b.p, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToDevice, s));
+                for (int q = 0; q < nr; ++q)      // res_q = b_q - K x_q (positions shifted to the leaf's private buffers)
+                    launch_sym_spmv((int64_t)lf->val.size(), ctx->kcoo_row.p + lf->kval_off, ctx->kcoo_col.p + lf->kval_off,
+                                    ctx->Kval.p + lf->kval_off, -1.0, xs.p + (size_t)q * n - lf->pos_off,
+                                    res + (size_t)q * n - lf->pos_off, s);
+                launch_gather_perm(lg.p, res, xp.p, n, nr, n, s);
+                run_leaf_solve(ctx, sa, nr, lf, lf->pos_off, n);
+                launch_scatter_perm(lg.p, xp.p, res, n, nr, n, s);
+                launch_axpy(1.0, res, xs.p, (int64_t)n * nr, s);
+            }
+            CUDA_CHECK(cudaMemcpyAsync(rhs + (size_t)r0 * n, xs.p, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            continue;
+        }
         launch_scatter_perm(lg.p, xp.p, b.p, n, nr, n, s);
         CUDA_CHECK(cudaMemcpyAsync(rhs + (size_t)r0 * n, b.p, sizeof(double) * (size_t)n * nr, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1702,6 +1758,7 @@ int pipsgpu_kkt_setup(pipsgpu_kkt* k, int threads) {
     }
     k->bl.alloc((size_t)k->sum_n + 1);
     k->tl.alloc((size_t)k->sum_n + 1);
+    k->wl.alloc((size_t)k->sum_n + 1);
     k->bl_in.alloc((size_t)k->sum_n + 1);
     k->b0_in.alloc((size_t)k->n0 + k->my0 + k->mz0 + k->myl + k->mzl + 1);
     if (!k->ev_init) {
@@ -1801,29 +1858,44 @@ int pipsgpu_kkt_factorize_resident(pipsgpu_kkt* k, int inertia_root[3]) {
     PIPSGPU_CATCH
 }
 
-// solveCompressed on the device-resident right-hand side (k->b0_in / k->bl_in); result in k->b0 / k->bl
-static void kkt_solve_device(pipsgpu_kkt* k) {
+// out = K^-1 in over all leaves of the context with iterative refinement (see pipsgpu_ctx::refine_steps):
+//   z = K^-1 b ; repeat: r = K z - b ; z -= K^-1 r.   `res` is scratch of npos doubles. ev0 / ev1 bracket the first psolve.
+static void leaf_solve_refined(pipsgpu_ctx* ctx, const double* in, double* out, double* res, cudaEvent_t ev0 = nullptr,
+                               cudaEvent_t ev1 = nullptr) {
+    cudaStream_t s = ctx->stream;
+    if (ev0) CUDA_CHECK(cudaEventRecord(ev0, s));
+    ctx->psolve(in, out, 0);
+    if (ev1) CUDA_CHECK(cudaEventRecord(ev1, s));
+    if (ctx->refine_steps <= 0 || !(ctx->any_perturbed || ctx->refine_always)) return;
+    for (int it = 0; it < ctx->refine_steps; ++it) {
+        launch_axpby(ctx->npos, -1.0, in, 0.0, res, s);                                              // res = -b
+        launch_sym_spmv(ctx->nnzK, ctx->kcoo_row.p, ctx->kcoo_col.p, ctx->Kval.p, 1.0, out, res, s);   // res += K z
+        ctx->psolve(res, out, 1);                                                                    // z -= K^-1 res
+    }
+}
+
+// solveCompressed on device-resident vectors: (in0 | inl) -> (out0 | outl); root parts have nb0 entries, leaf parts npos.
+// out0 may alias in0, outl may alias inl. k->r, k->t3, k->tl, k->wl are scratch.
+static void kkt_solve_device(pipsgpu_kkt* k, const double* in0, const double* inl, double* out0, double* outl) {
     pipsgpu_ctx* ctx = k->ctx;
     pipsgpu_sc* sc = k->sc.get();
     cudaStream_t s = ctx->stream;
     const int n0 = k->n0, my0 = k->my0, mz0 = k->mz0, myl = k->myl, mzl = k->mzl;
     const int nb0 = n0 + my0 + mz0 + myl + mzl;
     const int64_t N = ctx->npos;
-    if (ctx->rank > 0) launch_vec_zero(k->b0.p, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
-    else launch_vec_copy(k->b0.p, k->b0_in.p, nb0, s);
+    if (ctx->rank > 0) launch_vec_zero(out0, nb0, s);   // sLinsysRootAug::Lsolve: ranks > 0 start from zero
+    else if (out0 != in0) launch_vec_copy(out0, in0, nb0, s);
     // ---- Lsolve: z_i = K_i^-1 b_i ; b0 -= Bord_i^T z_i ; allreduce ----
-    CUDA_CHECK(cudaEventRecord(k->ev[10], s));
-    ctx->psolve(k->bl_in.p, k->bl.p, 0);
-    CUDA_CHECK(cudaEventRecord(k->ev[11], s));
-    launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, k->bl.p, k->b0.p, s);
+    leaf_solve_refined(ctx, inl, outl, k->tl.p, k->ev[10], k->ev[11]);
+    launch_border_tmult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, outl, out0, s);
     if (ctx->comm && ctx->nranks > 1) {
         NcclApi& api = NcclApi::get();
-        const int rc = api.AllReduce(k->b0.p, k->b0.p, (size_t)nb0, kNcclFloat64, kNcclSum, ctx->comm, s);
+        const int rc = api.AllReduce(out0, out0, (size_t)nb0, kNcclFloat64, kNcclSum, ctx->comm, s);
         if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce(b0): ") + api.GetErrorString(rc));
     }
     CUDA_CHECK(cudaEventRecord(k->ev[7], s));
     // ---- Dsolve: solveReducedLinkCons ----
-    double* b = k->b0.p;
+    double* b = out0;
     double* r = k->r.p;
     launch_vec_copy(r, b, n0 + my0, s);
     launch_vec_copy(r + n0 + my0, b + n0 + my0 + mz0, myl + mzl, s);
@@ -1846,9 +1918,16 @@ static void kkt_solve_device(pipsgpu_kkt* k) {
     if (N > 0) {
         launch_vec_zero(k->tl.p, N, s);
         launch_border_mult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, b, k->tl.p, s);
-        ctx->psolve(k->tl.p, k->bl.p, 1);
+        if (ctx->refine_steps > 0 && (ctx->any_perturbed || ctx->refine_always)) {
+            // w = K^-1 (Bord u) refined, then b_i -= w (residual scratch: ctx->work)
+            leaf_solve_refined(ctx, k->tl.p, k->wl.p, ctx->work.p);
+            launch_axpy(-1.0, k->wl.p, outl, N, s);
+        } else {
+            ctx->psolve(k->tl.p, outl, 1);
+        }
     }
 }
+static void kkt_solve_resident(pipsgpu_kkt* k) { kkt_solve_device(k, k->b0_in.p, k->bl_in.p, k->b0.p, k->bl.p); }
 
 static void kkt_solve_times(pipsgpu_kkt* k) {
     float ms;
@@ -1879,7 +1958,7 @@ int pipsgpu_kkt_solve_compressed(pipsgpu_kkt* k, double* b0, double* b_leaves) {
     }
     CUDA_CHECK(cudaMemcpyAsync(k->b0_in.p, b0, sizeof(double) * (size_t)nb0, cudaMemcpyHostToDevice, s));
     k->have_rhs = true;
-    kkt_solve_device(k);
+    kkt_solve_resident(k);
     if (N > 0) CUDA_CHECK(cudaMemcpyAsync(b_leaves, k->bl.p, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(b0, k->b0.p, sizeof(double) * (size_t)nb0, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaEventRecord(k->ev[9], s));
@@ -1895,8 +1974,207 @@ int pipsgpu_kkt_solve_compressed_resident(pipsgpu_kkt* k) {
     require_device(k->ctx);
     if (!k->sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve_compressed_resident: not factorized");
     CUDA_CHECK(cudaEventRecord(k->ev[6], k->ctx->stream));
-    kkt_solve_device(k);
+    kkt_solve_resident(k);
     CUDA_CHECK(cudaEventRecord(k->ev[9], k->ctx->stream));
+    PIPSGPU_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device-resident outer solve: LinearSystem::solveCompressedBiCGStab (LS/LinearSystem.C:550-798) preconditioned by
+// solveCompressed, with the full-KKT matvec LinearSystem::system_mult (:809-844) in the node layout of
+// DistributedVector (root part [x0;y0;z0;yl;zl] replicated on every rank, leaf parts distributed). The right-hand side
+// goes down once and the solution comes back once; only scalars (dot products) cross PCIe in between.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Krylov {
+    pipsgpu_kkt* k;
+    pipsgpu_ctx* ctx;
+    cudaStream_t s;
+    int nb0;
+    int64_t N, R;      // leaf length, padded root length
+    double* root(int v) { return k->kv[v].p; }
+    double* leaf(int v) { return k->kv[v].p + R; }
+    void copy(int dst, int src) { CUDA_CHECK(cudaMemcpyAsync(k->kv[dst].p, k->kv[src].p, sizeof(double) * (size_t)(R + N), cudaMemcpyDeviceToDevice, s)); }
+    void axpby(double a, int x, double b, int y) { launch_axpby(R + N, a, k->kv[x].p, b, k->kv[y].p, s); }
+    // <x, y>: the replicated root part counts once, the leaf parts are summed over the ranks
+    double dot(int x, int y) {
+        launch_dot(nb0, root(x), root(y), k->kpartial.p, k->kscal.p, s);
+        launch_dot(N, leaf(x), leaf(y), k->kpartial.p, k->kscal.p + 1, s);
+        if (ctx->comm && ctx->nranks > 1) {
+            NcclApi& api = NcclApi::get();
+            const int rc = api.AllReduce(k->kscal.p + 1, k->kscal.p + 1, 1, kNcclFloat64, kNcclSum, ctx->comm, s);
+            if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce(dot): ") + api.GetErrorString(rc));
+        }
+        CUDA_CHECK(cudaMemcpyAsync(k->h_scal, k->kscal.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        return k->h_scal[0] + k->h_scal[1];
+    }
+    double nrm2(int x) { return std::sqrt(std::max(0.0, dot(x, x))); }
+    // out = K in  (system_mult with beta = 0, alpha = 1 on the regularised system that was factorised)
+    void matvec(int out, int in) {
+        const int n0 = k->n0, my0 = k->my0, mz0 = k->mz0, myl = k->myl, mzl = k->mzl;
+        double* y0 = root(out); double* yl = leaf(out);
+        const double* x0 = root(in); const double* xl = leaf(in);
+        double* c0 = k->kc0.p;
+        launch_vec_zero(yl, N, s);
+        launch_vec_zero(c0, nb0, s);
+        // leaves: y_i = K_i x_i + Bord_i x_0 ; root contribution sum_i Bord_i^T x_i
+        launch_sym_spmv(ctx->nnzK, ctx->kcoo_row.p, ctx->kcoo_col.p, ctx->Kval.p, 1.0, xl, yl, s);
+        launch_border_axpy(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, 1.0, x0, yl, false, s);
+        launch_border_axpy(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, 1.0, xl, c0, true, s);
+        if (ctx->comm && ctx->nranks > 1) {
+            NcclApi& api = NcclApi::get();
+            const int rc = api.AllReduce(c0, c0, (size_t)nb0, kNcclFloat64, kNcclSum, ctx->comm, s);
+            if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce(matvec): ") + api.GetErrorString(rc));
+        }
+        // root rows: y_0 = c0 + K_root x_0
+        launch_vec_copy(y0, c0, nb0, s);
+        const double* ux = x0; const double* uy = x0 + n0; const double* uz = x0 + n0 + my0;
+        const double* uyl = x0 + n0 + my0 + mz0; const double* uzl = uyl + myl;
+        double* rx = y0; double* ry = y0 + n0; double* rz = y0 + n0 + my0; double* ryl = y0 + n0 + my0 + mz0; double* rzl = ryl + myl;
+        launch_diag_axpy(n0, 1.0, k->dd0.p, ux, rx, s);
+        launch_csr_tmult(my0, k->A0.krow.p, k->A0.jcol.p, k->A0.val.p, 1.0, uy, rx, s);
+        launch_csr_tmult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, 1.0, uz, rx, s);
+        launch_csr_tmult(myl, k->F0.krow.p, k->F0.jcol.p, k->F0.val.p, 1.0, uyl, rx, s);
+        launch_csr_tmult(mzl, k->G0.krow.p, k->G0.jcol.p, k->G0.val.p, 1.0, uzl, rx, s);
+        launch_csr_mult(my0, k->A0.krow.p, k->A0.jcol.p, k->A0.val.p, 1.0, ux, ry, s);
+        launch_csr_mult(mz0, k->C0.krow.p, k->C0.jcol.p, k->C0.val.p, 1.0, ux, rz, s);
+        launch_csr_mult(myl, k->F0.krow.p, k->F0.jcol.p, k->F0.val.p, 1.0, ux, ryl, s);
+        launch_csr_mult(mzl, k->G0.krow.p, k->G0.jcol.p, k->G0.val.p, 1.0, ux, rzl, s);
+        if (k->last_regDy != 0.0) {
+            launch_diag_axpy(my0, -k->last_regDy, nullptr, uy, ry, s);
+            launch_diag_axpy(myl, -k->last_regDy, nullptr, uyl, ryl, s);
+        }
+        launch_diag_axpy(mz0, 1.0, k->zdiag0.p, uz, rz, s);
+        launch_diag_axpy(mzl, 1.0, k->zdiagl.p, uzl, rzl, s);
+    }
+    void precond(int out, int in) { kkt_solve_device(k, root(in), leaf(in), root(out), leaf(out)); }
+    // res = b - K x ; returns ||res||_2
+    double residual(int res, int b, int x) {
+        matvec(res, x);
+        axpby(1.0, b, -1.0, res);
+        return nrm2(res);
+    }
+};
+
+}  // namespace
+
+int pipsgpu_kkt_solve(pipsgpu_kkt* k, double* b0, double* b_leaves, double tol, int max_iter, int* status, int* n_iter,
+                      double* rel_residual) {
+    PIPSGPU_TRY
+    if (!k || !k->ready) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve: kkt not set up");
+    if (!b0) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve: null b0");
+    pipsgpu_ctx* ctx = k->ctx;
+    require_device(ctx);
+    if (!k->sc->factorized) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_kkt_solve: not factorized");
+    cudaStream_t s = ctx->stream;
+    const int nb0 = k->n0 + k->my0 + k->mz0 + k->myl + k->mzl;
+    const int64_t N = ctx->npos;
+    if (N > 0 && !b_leaves) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_kkt_solve: null b_leaves");
+    Krylov K{k, ctx, s, nb0, N, (int64_t)((nb0 + 1) & ~1)};
+    if (k->kv[0].n == 0) {
+        for (auto& v : k->kv) { v.alloc((size_t)(K.R + N) + 2); CUDA_CHECK(cudaMemsetAsync(v.p, 0, sizeof(double) * v.n, s)); }
+        k->kc0.alloc((size_t)nb0 + 2); k->kpartial.alloc(DOT_SCRATCH); k->kscal.alloc(4);
+        CUDA_CHECK(cudaMallocHost(&k->h_scal, sizeof(double) * 4));
+    }
+    k->kv_root = K.R;
+    // vectors (aliases of LinearSystem.C:561-562): b, x, r, r0, dx, best_x, v, t, p
+    enum { B = 0, X, Rr, R0, DX, BEST, V, T, P };
+    CUDA_CHECK(cudaMemcpyAsync(K.root(B), b0, sizeof(double) * (size_t)nb0, cudaMemcpyHostToDevice, s));
+    if (N > 0) CUDA_CHECK(cudaMemcpyAsync(K.leaf(B), b_leaves, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, s));
+    const double eps = 1e-15;                     // OUTER_BICG_EPSILON
+    const int max_stagnations = 4, max_normr_div = 4;      // OUTER_BICG_MAX_STAGNATIONS / _MAX_NORMR_DIVERGENCES
+    auto is_zero = [](double v) { return std::fabs(v) < 1e-13; };      // PIPSisZero, pips_eps
+    enum { NOT_CONVERGED_MAX_ITERATIONS = -1, CONVERGED = 0, SKIPPED = 1, STAGNATION = 3, BREAKDOWN = 4, DIVERGED = 5 };
+    const double bnorm = K.nrm2(B);
+    const double tolb = std::max(bnorm * tol, eps);
+    int flag = NOT_CONVERGED_MAX_ITERATIONS, it = 0;
+    // starting point: x = K~^-1 b
+    K.precond(X, B);
+    double rnorm = K.residual(Rr, B, X);
+    double min_rnorm = rnorm, resnorm = rnorm;
+    K.copy(BEST, X);
+    if (rnorm <= tolb) {
+        flag = SKIPPED;
+    } else {
+        K.axpby(1.0 / rnorm, Rr, 0.0, R0);
+        int normr_div = 0, nstag = 0;
+        double rho = 1.0, omega = 1.0, alpha = 1.0;
+        auto stagnation = [&](double step, double step_norm) {
+            if (std::fabs(step) * step_norm <= eps * K.nrm2(X)) ++nstag; else nstag = 0;
+        };
+        for (it = 0; it < max_iter; ++it) {
+            // ---- first half ----
+            const double rho_last = rho;
+            rho = K.dot(R0, Rr);
+            if (is_zero(rho)) { flag = BREAKDOWN; break; }
+            if (it == 0) K.copy(P, Rr);
+            else {
+                const double beta = (rho / rho_last) * (alpha / omega);
+                if (is_zero(beta)) { flag = BREAKDOWN; break; }
+                K.axpby(-omega, V, 1.0, P);       // p = p - omega v
+                K.axpby(1.0, Rr, beta, P);        // p = r + beta p
+            }
+            K.precond(DX, P);
+            K.matvec(V, DX);
+            const double rtv = K.dot(R0, V);
+            if (is_zero(rtv)) { flag = BREAKDOWN; break; }
+            alpha = rho / rtv;
+            stagnation(alpha, K.nrm2(DX));
+            K.axpby(alpha, DX, 1.0, X);
+            K.axpby(-alpha, V, 1.0, Rr);
+            rnorm = K.nrm2(Rr);
+            if (rnorm <= tolb) {
+                resnorm = K.residual(Rr, B, X);
+                if (resnorm <= tolb) { flag = CONVERGED; break; }
+                min_rnorm = K.residual(DX, B, BEST);
+                rnorm = resnorm;
+            }
+            if (rnorm < min_rnorm) { min_rnorm = rnorm; K.copy(BEST, X); }
+            // ---- second half ----
+            K.precond(DX, Rr);
+            K.matvec(T, DX);
+            const double tt = K.dot(T, T);
+            if (is_zero(tt)) { flag = BREAKDOWN; break; }
+            omega = K.dot(T, Rr) / tt;
+            stagnation(omega, K.nrm2(DX));
+            K.axpby(omega, DX, 1.0, X);
+            K.axpby(-omega, T, 1.0, Rr);
+            rnorm = K.nrm2(Rr);
+            if (rnorm <= tolb || nstag >= max_stagnations) {
+                resnorm = K.residual(Rr, B, X);
+                if (resnorm <= tolb) { flag = CONVERGED; break; }
+                min_rnorm = K.residual(DX, B, BEST);
+                rnorm = resnorm;
+            } else {
+                if (rnorm >= min_rnorm) ++normr_div; else normr_div = 0;
+                if (normr_div > max_normr_div) {
+                    K.copy(X, BEST);
+                    rnorm = min_rnorm;
+                    resnorm = K.residual(DX, B, X);
+                    flag = DIVERGED;
+                    break;
+                }
+            }
+            if (rnorm < min_rnorm) { min_rnorm = rnorm; K.copy(BEST, X); }
+            if (nstag >= max_stagnations) {
+                if (min_rnorm < rnorm) { rnorm = min_rnorm; K.copy(X, BEST); }
+                resnorm = K.residual(DX, B, X);
+                flag = STAGNATION;
+                break;
+            }
+            if (is_zero(omega)) { flag = BREAKDOWN; break; }
+        }
+        if (flag == NOT_CONVERGED_MAX_ITERATIONS || flag == BREAKDOWN) resnorm = K.residual(DX, B, X);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(b0, K.root(X), sizeof(double) * (size_t)nb0, cudaMemcpyDeviceToHost, s));
+    if (N > 0) CUDA_CHECK(cudaMemcpyAsync(b_leaves, K.leaf(X), sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    k->have_rhs = true;
+    if (status) *status = flag;
+    if (n_iter) *n_iter = (flag == SKIPPED) ? 0 : std::min(it + 1, max_iter);      // iterations started
+    if (rel_residual) *rel_residual = bnorm > 0 ? resnorm / bnorm : 0.0;
     PIPSGPU_CATCH
 }
 

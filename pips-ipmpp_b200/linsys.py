@@ -114,6 +114,52 @@ class CudaRootLinearSystem:
                                                np.asarray(nomegainv[-1], float), cat(dd[1:]), cat(nomegainv[1:-1]), reg)
         return self.inertia_root
 
+    def factorize_with_correct_inertia(self, dd, nomegainv, leaf_strategies, barrier_parameter=1.0):
+        """DistributedRootLinearSystem::factor2 with REGULARIZATION = true, batched: every owned leaf runs the reference's
+        per-node loop LinearSystem::factorize_with_correct_inertia (LS/LinearSystem.C:296-325; regularization.py) with its own
+        strategy object. All leaves are factorised together (one batched device factorisation per round); a leaf whose
+        inertia is already correct keeps its regularisation. The Schur complement is always the one of the final round
+        (it is re-accumulated from zero by every pipsgpu_kkt_factorize). Returns (root inertia, per-leaf regularisation,
+        number of batched factorisations)."""
+        n = len(self.leaves)
+        assert len(leaf_strategies) == n
+        reg = []
+        for st, leaf in zip(leaf_strategies, self.leaves):
+            st.notify_new_step()
+            reg.append(tuple(st.get_default_regularization()))
+            leaf.set_regularization(*reg[-1])
+        rounds = 0
+        while True:
+            root_inertia = self.factorize(dd, nomegainv)
+            rounds += 1
+            wrong = [i for i, (st, leaf) in enumerate(zip(leaf_strategies, self.leaves))
+                     if not st.is_inertia_correct(leaf.inertia()[0])]
+            if not wrong:
+                return root_inertia, reg, rounds
+            if rounds > 60:
+                raise RuntimeError("factorize_with_correct_inertia: inertia still wrong after 60 rounds")
+            for i in wrong:
+                cur = tuple(leaf_strategies[i].get_regularization_parameters(self.leaves[i].inertia()[0], barrier_parameter))
+                assert all(c >= l for c, l in zip(cur, reg[i]))
+                reg[i] = cur
+                self.leaves[i].set_regularization(*cur)
+
+    def solve_bicgstab(self, rhs, tol=1e-10, max_iter=75):
+        """LinearSystem::solveCompressedBiCGStab on the device (pipsgpu_kkt_solve): rhs = [b0, b_1, ..., b_N], in place.
+        Returns (status, iterations, relative residual)."""
+        self._b0[:] = rhs[0]
+        off = 0
+        for b in rhs[1:]:
+            self._b_leaves[off:off + len(b)] = b
+            off += len(b)
+        out = self.kkt.solve_bicgstab(self._b0, self._b_leaves, tol, max_iter)
+        rhs[0][:] = self._b0
+        off = 0
+        for b in rhs[1:]:
+            b[:] = self._b_leaves[off:off + len(b)]
+            off += len(b)
+        return out
+
     def solve_compressed(self, rhs):
         """rhs = [b0, b_1, ..., b_N] (owned children), solved in place."""
         self._b0[:] = rhs[0]

@@ -299,3 +299,69 @@ def test_xform_front_solve_equals_substitution(pkg, cfg):
     got = np.empty(n)
     got[a["perm"]] = y
     assert np.linalg.norm(got - want) <= 1e-11 * np.linalg.norm(want)
+
+
+def test_host_kkt_residual_helper_against_oracle_solution(pkg):
+    """linsys.compressed_kkt_residual (the size-independent check bench.py and the full-size GPU tests rely on) must
+    vanish on the oracle's solveCompressed solution, with and without regularisation"""
+    from oracle.linsys import OracleRoot
+    P = pkg.problem
+    for cfg, reg in (("T2", None), ("T3", (1e-6, 1e-7, 1e-7))):
+        lp = P.synthetic(cfg)
+        dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+        ref = OracleRoot(lp)
+        ref.put_diagonals(dd, nom, *(reg or (0.0, 0.0, 0.0)))
+        ref.factor2()
+        rng = np.random.default_rng(0)
+        nb0 = lp.root.n + lp.root.my + lp.root.mz + lp.myl + lp.mzl
+        rhs = [rng.standard_normal(nb0)] + [rng.standard_normal(ch.n + ch.my + ch.mz) for ch in lp.children]
+        sol = ref.solve_compressed([b.copy() for b in rhs])
+        lsq, r0 = pkg.linsys.compressed_kkt_residual(lp, dd, nom, rhs, sol, reg)
+        assert np.sqrt(lsq + r0 @ r0) / np.sqrt(sum(b @ b for b in rhs)) <= 1e-12
+        # and it must NOT vanish for a wrong solution
+        sol[1][0] += 1.0
+        lsq, r0 = pkg.linsys.compressed_kkt_residual(lp, dd, nom, rhs, sol, reg)
+        assert np.sqrt(lsq + r0 @ r0) > 1e-6
+
+
+def test_regularisation_loop_host_logic_against_oracle(pkg):
+    """regularization.py (mirror of LinearSystem::factorize_with_correct_inertia + IpoptRegularization) driven by the C
+    oracle's factorisation must take exactly the steps of the independent restatement in oracle/linsys.py"""
+    from oracle import mf
+    from oracle.linsys import oracle_leaf_inertia_loop
+    P = pkg.problem
+    R = pkg.regularization
+    lp = P.synthetic("T2")
+    ch = lp.children[2]
+    W = ch.W.tolil()
+    W[1, :] = W[0, :]
+    ch.W = P._csr(W.tocsr(), W.shape)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID["T2"])
+    want_reg, want_n, seen = oracle_leaf_inertia_loop(lp, 2, dd[3], nom[3], mf.HostSymbolic, barrier_parameter=1e-2)
+    assert seen[0] != (ch.n, ch.my + ch.mz, 0) and seen[-1] == (ch.n, ch.my + ch.mz, 0)
+    krow, jcol, val, diag_pos, nB, brow, bcol, bval = mf.leaf_kkt_and_border(lp, 2)
+    leaf = mf.MfLeaf(mf.HostSymbolic(ch.n + ch.my + ch.mz, ch.n, ch.my, ch.mz, krow, jcol, val, nB, brow, bcol).export())
+    knorm = max(1.0, float(np.abs(val).max(initial=0.0)))
+    reg = [0.0, 0.0, 0.0]
+    state = {}
+
+    def add(dp, dy, dz):
+        reg[0] += dp; reg[1] += dy; reg[2] += dz
+
+    def changed():
+        v = val.copy()
+        v[diag_pos[:ch.n]] = dd[3] + reg[0]
+        v[diag_pos[ch.n:ch.n + ch.my]] = -reg[1]
+        v[diag_pos[ch.n + ch.my:]] = nom[3] - reg[2]
+        state["inertia"], _ = leaf.factorize(v, bval, None, knorm=knorm)
+
+    final, nfact = R.factorize_with_correct_inertia(R.IpoptRegularization(ch.n, ch.my + ch.mz), add, changed,
+                                                    lambda: state["inertia"], 1e-2)
+    assert nfact == want_n and tuple(final) == tuple(want_reg) and tuple(reg) == tuple(want_reg)
+    # Friedlander-Orban: decreasing default regularisation per new step, x100 per retry
+    fo = R.FriedlanderOrbanRegularization(3, 2)
+    fo.notify_new_step()
+    assert fo.get_default_regularization() == (1.0, 1.0, 1.0)
+    assert fo.get_regularization_parameters() == (100.0, 100.0, 100.0)
+    fo.notify_new_step()
+    assert fo.get_default_regularization() == (10.0, 10.0, 10.0)
