@@ -245,7 +245,8 @@ int pipsgpu_symbolic_export(pipsgpu_symbolic* sym, int* perm, int8_t* ptype, int
 /* grouping of the big fronts for the deferred border x border Schur-complement updates (host-only inspection of what
  * pipsgpu_ctx_commit builds; no counterpart in the reference, whose plugins keep their supernode scheduling private -
  * PardisoSchurSolver.C:434-477 just receives the finished Schur complement). Call once with null arrays to get
- * counts = {groups, members, positions}, then with arrays of those sizes (mem_ptr: groups+1, pos_ptr: members+1). */
+ * counts = {groups, members, positions}, then with arrays of those sizes (mem_ptr: groups+1, pos_ptr: members+1).
+ * frac < 0: the fraction is chosen by the cost model of the Schur-term kernel (what pipsgpu_ctx_commit does by default). */
 int pipsgpu_symbolic_border_groups(pipsgpu_symbolic* sym, int big_u, double frac, int64_t counts[3], int* root, int* N,
                                    int* mem_ptr, int* mem_front, int64_t* pos_ptr, int* pos);
 

@@ -270,140 +270,230 @@ void launch_dgemm_nt(int epi, const TMap& tmA, const TMap& tmB, const GemmArgs& 
 }
 
 // =====================================================================================================
-// 128 x 128 diagonal block: static-pivot LDL^T and X = L11^-1, everything in registers
-//   thread (ty, tx) of a 32 x 32 CTA owns S(i, j) and X(i, c) for i = ty + 32 a, j / c = tx + 32 b (a, b < 4).
-//   Step k: the owners of column k of S and of row k of X broadcast them through (double-buffered) shared memory, then
-//   every thread updates its registers:  S(i,j) -= w_i w_j / d_k  (k < j <= i),  X(i,c) -= (w_i / d_k) X(k,c)  (c <= k < i).
-//   Pivots with the wrong sign or below eps_rel * (largest entry of the pivot's original row) are replaced by
-//   +-eps (the static order is x0 first: expected signs + ... + - ... -); inertia counts the COMPUTED pivots.
+// 128 x 128 diagonal block: static-pivot LDL^T and X = L11^-1 in ONE CTA of 8 warps, blocked 4 x 4 by 32.
+//   The block lives in shared memory as ten 32 x 32 lower blocks (leading dimension 33). Step j = 0..3:
+//     (a) warp 0 factorises the diagonal block (j,j): lane = row, the row in registers, column k broadcast through a
+//         double-buffered shared-memory line (one __syncwarp per column, no CTA barrier on the 128-step chain);
+//     (b) rows below: W = A L_jj^-T by forward substitution, one thread per row (L_jj reads are warp broadcasts),
+//         L = W D^-1; W kept in a scratch tile;
+//     (c) trailing blocks (i,k), j < k <= i:  A_ik -= L_ij W_kj^T, all 256 threads, 2 x 2 register blocks.
+//   Then X = L11^-1: the four diagonal blocks by four warps (lane = column, forward substitution with broadcast reads),
+//   the off-diagonal blocks level by level (distance 1, 2, 3 from the diagonal):  X_ij = -X_ii sum_k L_ik X_kj.
+//   Pivots with the wrong sign or below eps_rel * (largest entry of the pivot's original row) are replaced by +-eps
+//   (the static order is x0 first: expected signs + ... + - ... -); inertia counts the COMPUTED pivots.
+//   The previous version kept the whole block in the registers of 1024 threads and paid two CTA barriers plus an FP64
+//   division per column on a 255-step chain (230 us per panel); this one has 128 warp-level steps and ~25 barriers.
 // =====================================================================================================
-__global__ void __launch_bounds__(1024, 1) ldlt_diag_kernel(double* __restrict__ A, int64_t ld, int kb, int bw, int n0, double eps_rel,
-                                                            const double* __restrict__ scale, double* __restrict__ D,
-                                                            double* __restrict__ Dinv, double* __restrict__ X, int* __restrict__ stats) {
-    extern __shared__ double sLd[];                 // L11 (scaled, strictly lower), [DENSE_PANEL][DENSE_PANEL + 1]
-    __shared__ double colb[2][DENSE_PANEL];
-    __shared__ double s_dinv[DENSE_PANEL], s_d[DENSE_PANEL];
-    __shared__ double s_eps[DENSE_PANEL];          // pivot threshold of every column (a global load per step would sit on
-    constexpr int LDS = DENSE_PANEL + 1;           // the critical path of all 128 steps)
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    if (threadIdx.x < DENSE_PANEL)
-        s_eps[threadIdx.x] = (threadIdx.x < bw) ? eps_rel * fmax(scale[kb + threadIdx.x], 1e-300) : 1.0;
-    // ---------------- phase 1: LDL^T, S in registers ----------------
-    {
-        double S[4][4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = ty + 32 * a, j = tx + 32 * b;
-                S[a][b] = (i < bw && j <= i) ? A[(int64_t)(kb + i) * ld + kb + j] : 0.0;
-            }
-        int npos = 0, nneg = 0, nzero = 0, npert = 0;
-        for (int k = 0; k < bw; ++k) {
-            const int p = k & 1;
-            const int ka = k >> 5, kt = k & 31;
-            if (tx == kt) {      // owners of column k broadcast it (rows i >= k; rows above hold zeros)
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (b == ka) colb[p][ty + 32 * a] = S[a][b];
-            }
-            __syncthreads();
-            double d = colb[p][k];
-            const double sg = (kb + k < n0) ? 1.0 : -1.0;
-            const double eps = s_eps[k];
-            if (threadIdx.x == 0) {
-                if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
-            }
-            bool pert = false;
-            if (!(sg * d >= eps)) { d = sg * eps; pert = true; }
-            const double dinv = 1.0 / d;
-            if (threadIdx.x == 0) {
-                if (pert) ++npert;
-                s_dinv[k] = dinv; s_d[k] = d;
-            }
-            double wi[4], wj[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) wi[a] = colb[p][ty + 32 * a] * dinv;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) wj[b] = colb[p][tx + 32 * b];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = ty + 32 * a;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int j = tx + 32 * b;
-                    if (i > k && i < bw && j > k && j <= i) S[a][b] = fma(-wi[a], wj[b], S[a][b]);
-                }
-            }
-            // no second barrier: the next step writes the other half of colb
-        }
-        __syncthreads();
-        // L11 (strictly lower, scaled columns) to shared memory and back to the factor
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = ty + 32 * a, j = tx + 32 * b;
-                const double l = (i < bw && j < i) ? S[a][b] * s_dinv[j] : 0.0;
-                sLd[i * LDS + j] = l;
-                if (i < bw && j < i) A[(int64_t)(kb + i) * ld + kb + j] = l;
-            }
-        if (threadIdx.x == 0 && stats) {
-            atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
-        }
-        if (threadIdx.x < bw) {
-            Dinv[kb + threadIdx.x] = s_dinv[threadIdx.x];
-            D[kb + threadIdx.x] = s_d[threadIdx.x];
+constexpr int DB = 32;                       // sub-block size
+constexpr int DBL = DB + 1;                  // leading dimension of a sub-block in shared memory
+constexpr int DNB = DENSE_PANEL / DB;        // 4
+constexpr int DBLK = DB * DBL;               // doubles per sub-block
+constexpr int DNLOW = DNB * (DNB + 1) / 2;   // 10 lower blocks
+__device__ __forceinline__ int dblk(int i, int j) { return (i * (i + 1) / 2 + j) * DBLK; }
+
+__global__ void __launch_bounds__(256, 1) ldlt_diag_kernel(double* __restrict__ A, int64_t ld, int kb, int bw, int n0, double eps_rel,
+                                                           const double* __restrict__ scale, double* __restrict__ D,
+                                                           double* __restrict__ Dinv, double* __restrict__ X, int* __restrict__ stats) {
+    extern __shared__ double dg_smem[];
+    double* sL = dg_smem;                         // A -> L (unit lower; W on the way), lower blocks
+    double* sX = sL + DNLOW * DBLK;               // X = L^-1, lower blocks
+    double* sW = sX + DNLOW * DBLK;               // W = L D of the rows below the current diagonal block, [96][33]
+    __shared__ double s_col[2][DB];
+    __shared__ double s_dinv[DENSE_PANEL], s_d[DENSE_PANEL], s_eps[DENSE_PANEL];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < DENSE_PANEL) s_eps[tid] = (tid < bw) ? eps_rel * fmax(scale[kb + tid], 1e-300) : 0.0;
+    // ---- load the lower blocks (rows / columns beyond bw: identity) ----
+    for (int b = 0; b < DNLOW; ++b) {
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+        const int bj = b - bi * (bi + 1) / 2;
+        for (int idx = tid; idx < DB * DB; idx += 256) {
+            const int r = idx >> 5, c = idx & 31;
+            const int gi = bi * DB + r, gj = bj * DB + c;
+            double v = (gi == gj) ? 1.0 : 0.0;
+            if (gi < bw && gj <= gi) v = A[(int64_t)(kb + gi) * ld + kb + gj];
+            sL[b * DBLK + r * DBL + c] = v;
         }
     }
     __syncthreads();
-    // ---------------- phase 2: X = L11^-1, X in registers ----------------
-    {
-        double Xr[4][4];
+    int npos = 0, nneg = 0, nzero = 0, npert = 0;      // warp 0, uniform over its lanes
+    for (int j = 0; j < DNB; ++j) {
+        double* Ljj = sL + dblk(j, j);
+        // ---------------- (a) diagonal block, warp 0 ----------------
+        if (warp == 0) {
+            double a[DB];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int c = 0; c < DB; ++c) a[c] = Ljj[lane * DBL + c];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) Xr[a][b] = (ty + 32 * a == tx + 32 * b) ? 1.0 : 0.0;
-        for (int k = 0; k + 1 < bw; ++k) {
-            const int p = k & 1;
-            const int ka = k >> 5, kt = k & 31;
-            if (ty == kt) {      // owners of row k of X broadcast it (columns c <= k; zeros to the right)
+            for (int k = 0; k < DB; ++k) {
+                const int p = k & 1;
+                const double colk = a[k];                 // A(lane, k) after the updates of columns < k
+                s_col[p][lane] = colk;
+                __syncwarp();
+                double d = s_col[p][k];
+                const int gk = j * DB + k;
+                if (gk < bw) {
+                    const double sg = (kb + gk < n0) ? 1.0 : -1.0;
+                    const double eps = s_eps[gk];
+                    if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
+                    if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
+                }
+                const double dinv = 1.0 / d;
+                const double l = colk * dinv;
+                if (lane == k) { s_d[gk] = d; s_dinv[gk] = dinv; }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (a == ka) colb[p][tx + 32 * b] = Xr[a][b];
+                for (int c = k + 1; c < DB; ++c) {
+                    const double wc = s_col[p][c];        // A(c, k) = d_k L(c, k)
+                    if (lane >= c) a[c] = fma(-l, wc, a[c]);
+                }
+                if (lane > k) a[k] = l;
             }
-            __syncthreads();
-            double xk[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) xk[b] = colb[p][tx + 32 * b];
+            for (int c = 0; c < DB; ++c) Ljj[lane * DBL + c] = (c < lane) ? a[c] : ((c == lane) ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        const int nbelow = (DNB - 1 - j) * DB;
+        if (nbelow == 0) break;
+        // ---------------- (b) rows below: W L_jj^T = A,  L = W D^-1 ----------------
+        if (tid < nbelow) {
+            const int i = j + 1 + (tid >> 5);
+            double* Aij = sL + dblk(i, j) + (tid & 31) * DBL;
+            double w[DB];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int i = ty + 32 * a;
-                if (i <= k || i >= bw) continue;
-                const double lik = sLd[i * LDS + k];
+            for (int c = 0; c < DB; ++c) w[c] = Aij[c];
 #pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (tx + 32 * b <= k) Xr[a][b] = fma(-lik, xk[b], Xr[a][b]);
+            for (int c = 1; c < DB; ++c) {
+                double acc = w[c];
+#pragma unroll
+                for (int q = 0; q < c; ++q) acc = fma(-w[q], Ljj[c * DBL + q], acc);
+                w[c] = acc;
+            }
+#pragma unroll
+            for (int c = 0; c < DB; ++c) {
+                sW[tid * DBL + c] = w[c];
+                Aij[c] = w[c] * s_dinv[j * DB + c];
             }
         }
+        __syncthreads();
+        // ---------------- (c) trailing blocks (i, k), j < k <= i:  A_ik -= L_ij W_kj^T ----------------
+        {
+            const int r2 = (tid >> 4) * 2, c2 = (tid & 15) * 2;
+            for (int i = j + 1; i < DNB; ++i)
+                for (int k = j + 1; k <= i; ++k) {
+                    const double* Lij = sL + dblk(i, j);
+                    const double* Wk = sW + (k - j - 1) * DB * DBL;
+                    double* Aik = sL + dblk(i, k);
+                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 8
+                    for (int q = 0; q < DB; ++q) {
+                        const double l0 = Lij[r2 * DBL + q], l1 = Lij[(r2 + 1) * DBL + q];
+                        const double w0 = Wk[c2 * DBL + q], w1 = Wk[(c2 + 1) * DBL + q];
+                        c00 = fma(l0, w0, c00); c01 = fma(l0, w1, c01);
+                        c10 = fma(l1, w0, c10); c11 = fma(l1, w1, c11);
+                    }
+                    Aik[r2 * DBL + c2] -= c00; Aik[r2 * DBL + c2 + 1] -= c01;
+                    Aik[(r2 + 1) * DBL + c2] -= c10; Aik[(r2 + 1) * DBL + c2 + 1] -= c11;
+                }
+        }
+        __syncthreads();
+    }
+    // ---------------- outputs of the factorisation; X diagonal blocks ----------------
+    if (tid == 0 && stats) {
+        atomicAdd(stats + 0, npos); atomicAdd(stats + 1, nneg); atomicAdd(stats + 2, nzero); atomicAdd(stats + 3, npert);
+    }
+    if (tid < bw) { Dinv[kb + tid] = s_dinv[tid]; D[kb + tid] = s_d[tid]; }
+    if (warp < DNB) {
+        // X_jj = L_jj^-1, lane = column c of X: x(r) = -sum_{c <= k < r} L(r,k) x(k), x(c) = 1 (L reads are broadcasts)
+        const double* Ljj = sL + dblk(warp, warp);
+        double x[DB];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int r = 0; r < DB; ++r) {
+            double acc = (r == lane) ? 1.0 : 0.0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int i = ty + 32 * a, j = tx + 32 * b;
-                X[i * DENSE_PANEL + j] = (i < bw && j < bw) ? Xr[a][b] : ((i == j) ? 1.0 : 0.0);
+            for (int k = 0; k < r; ++k) acc = fma(-Ljj[r * DBL + k], x[k], acc);     // x(k) = 0 for k < lane
+            x[r] = acc;
+        }
+        double* Xjj = sX + dblk(warp, warp);
+#pragma unroll
+        for (int r = 0; r < DB; ++r) Xjj[r * DBL + lane] = x[r];
+    } else {
+        // the strictly lower part of L11 goes back into the factor
+        for (int b = 0; b < DNLOW; ++b) {
+            int bi = 0;
+            while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+            const int bj = b - bi * (bi + 1) / 2;
+            for (int idx = tid - DNB * 32; idx < DB * DB; idx += 256 - DNB * 32) {
+                const int r = idx >> 5, c = idx & 31;
+                const int gi = bi * DB + r, gj = bj * DB + c;
+                if (gi < bw && gj < gi) A[(int64_t)(kb + gi) * ld + kb + gj] = sL[b * DBLK + r * DBL + c];
             }
+        }
+    }
+    __syncthreads();
+    // ---------------- off-diagonal blocks of X, by distance from the diagonal ----------------
+    {
+        const int r2 = (tid >> 4) * 2, c2 = (tid & 15) * 2;
+#pragma unroll
+        for (int dist = 1; dist < DNB; ++dist) {
+            // T_ij = sum_{k = j}^{i-1} L_ik X_kj  into the X slot (i,j), j = i - dist
+            for (int i = dist; i < DNB; ++i) {
+                const int j = i - dist;
+                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                for (int k = j; k < i; ++k) {
+                    const double* Lik = sL + dblk(i, k);
+                    const double* Xkj = sX + dblk(k, j);
+#pragma unroll 8
+                    for (int q = 0; q < DB; ++q) {
+                        const double l0 = Lik[r2 * DBL + q], l1 = Lik[(r2 + 1) * DBL + q];
+                        const double x0 = Xkj[q * DBL + c2], x1 = Xkj[q * DBL + c2 + 1];
+                        c00 = fma(l0, x0, c00); c01 = fma(l0, x1, c01);
+                        c10 = fma(l1, x0, c10); c11 = fma(l1, x1, c11);
+                    }
+                }
+                double* T = sX + dblk(i, j);
+                T[r2 * DBL + c2] = c00; T[r2 * DBL + c2 + 1] = c01;
+                T[(r2 + 1) * DBL + c2] = c10; T[(r2 + 1) * DBL + c2 + 1] = c11;
+            }
+            __syncthreads();
+            // X_ij = -X_ii T_ij (in place through registers)
+            double o[DNB][4];
+#pragma unroll
+            for (int i = dist; i < DNB; ++i) {
+                const double* Xii = sX + dblk(i, i);
+                const double* T = sX + dblk(i, i - dist);
+                double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 8
+                for (int q = 0; q < DB; ++q) {
+                    const double a0 = Xii[r2 * DBL + q], a1 = Xii[(r2 + 1) * DBL + q];
+                    const double t0 = T[q * DBL + c2], t1 = T[q * DBL + c2 + 1];
+                    c00 = fma(a0, t0, c00); c01 = fma(a0, t1, c01);
+                    c10 = fma(a1, t0, c10); c11 = fma(a1, t1, c11);
+                }
+                o[i][0] = -c00; o[i][1] = -c01; o[i][2] = -c10; o[i][3] = -c11;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = dist; i < DNB; ++i) {
+                double* Xo = sX + dblk(i, i - dist);
+                Xo[r2 * DBL + c2] = o[i][0]; Xo[r2 * DBL + c2 + 1] = o[i][1];
+                Xo[(r2 + 1) * DBL + c2] = o[i][2]; Xo[(r2 + 1) * DBL + c2 + 1] = o[i][3];
+            }
+            __syncthreads();
+        }
+    }
+    // ---------------- X to global (row-major 128 x 128, zero upper part) ----------------
+    for (int idx = tid; idx < DENSE_PANEL * DENSE_PANEL; idx += 256) {
+        const int gi = idx >> 7, gj = idx & 127;
+        double v = 0.0;
+        if (gj <= gi) v = sX[dblk(gi >> 5, gj >> 5) + (gi & 31) * DBL + (gj & 31)];
+        X[idx] = v;
     }
 }
 
-constexpr int DIAG_SMEM = DENSE_PANEL * (DENSE_PANEL + 1) * 8;
+constexpr int DIAG_SMEM = (2 * DNLOW * DBLK + (DNB - 1) * DB * DBL) * 8;
 void launch_ldlt_diag(double* A, int64_t ld, int kb, int bw, int n0, double eps_rel, const double* scale, double* D, double* Dinv,
                       double* X, int* stats, cudaStream_t s) {
-    ldlt_diag_kernel<<<1, 1024, DIAG_SMEM, s>>>(A, ld, kb, bw, n0, eps_rel, scale, D, Dinv, X, stats);
+    ldlt_diag_kernel<<<1, 256, DIAG_SMEM, s>>>(A, ld, kb, bw, n0, eps_rel, scale, D, Dinv, X, stats);
     count_launch("ldlt_diag_kernel");
 }
 

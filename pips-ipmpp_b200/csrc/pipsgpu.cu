@@ -100,6 +100,7 @@ struct pipsgpu_leaf {
     // symbolic
     LeafSymbolic S;
     BorderGroups G;                  // grouping of the big fronts (consumed by pipsgpu_ctx_commit)
+    double group_frac_used = 0.0;
     bool analyzed = false;
     double knorm = 1.0;
     // placement in the context pools (valid after commit)
@@ -168,16 +169,15 @@ struct pipsgpu_ctx {
     // deferred border x border updates (kernels.cuh: GroupDesc)
     DevBuf<GroupDesc> groups;
     DevBuf<GroupMember> gmembers;
-    DevBuf<int> ginv;
-    DevBuf<int8_t> gflags;
-    DevBuf<int64_t> gt_ptr;         // per group tile: range of gt_list = the members that have rows in both of its blocks
-    DevBuf<int> gt_list;
-    bool group_lists = false;       // PIPSGPU_GROUP_LISTS=1: the group kernel walks gt_list instead of scanning gflags
+    DevBuf<GroupMap> gmap;          // row maps of the group members (kernels.cuh: GroupMap)
+    DevBuf<STile> stiles;           // output tiles of the group SYRKs (schur_syrk_kernel), grouped by leaf
+    DevBuf<int> sitems;             // their pipeline stages
     int bp_threads = 256;           // PIPSGPU_BP_THREADS=128: smaller CTAs for the big-front panels
-    DevBuf<GTile> gtiles;
     int64_t ngtiles = 0;
     bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
-    double group_frac = 0.6;        // a front joins its parent's group if it has at least this share of the root's border rows
+    // a front joins its parent's group if it has at least this share of the group root's border rows; < 0: chosen per leaf
+    // by the cost model of symbolic.cpp (border_groups_cost). PIPSGPU_GROUP_FRAC=<f> fixes it.
+    double group_frac = -1.0;
     int big_u = BIG_U;              // PIPSGPU_BIG_U: fronts with at least this many off-diagonal rows take the CTA-parallel path
     // side stream: the small fronts of a level run next to the big-front panel / tile kernels of the same level, and the
     // border-group SYRKs next to pack_solve (PIPSGPU_OVERLAP=0 keeps everything on one stream)
@@ -186,7 +186,6 @@ struct pipsgpu_ctx {
     // two small matrix-vector products (no serial substitution chain); X scratch is then persistent per front
     bool xform = true;
     bool panel_staged = false;      // PIPSGPU_PANEL=staged
-    bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream_hi = nullptr;   // high-priority side stream: look-ahead panels of the dense root LDL^T
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -194,6 +193,7 @@ struct pipsgpu_ctx {
     int64_t XYtot = 0;
     DevBuf<double> L, C, W, Dd, De, Did, Die, Kval, Bval, x, upd, dvals, work;
     std::vector<int> fl_ptr;        // nlevels*2+1 into fl_fronts; group = level_order*2 + (0 small | 1 big)
+    std::vector<int> fl_umax;       // per level (deepest first): most off-diagonal rows of a big front (grid of big_panel_kernel)
     DevBuf<int> fl_fronts;
     DevBuf<int> rowg, relidx, invmap, child_list, level_fronts, gidx, bg_row, bg_sc, bg_b0, stats;
     DevBuf<int8_t> ptype, sgn;
@@ -204,8 +204,14 @@ struct pipsgpu_ctx {
     // iterative refinement of the leaf solves, applied like PARDISO's iparm[7] = 2 (PardisoProjectSolver.C:72) only when the
     // factorisation perturbed pivots: up to refine_steps steps  z += K^-1 (b - K z)  with the resident matrix values.
     // PIPSGPU_REFINE=<steps> (0 disables), PIPSGPU_REFINE_ALWAYS=1 refines after every factorisation.
+    // The refinement belongs to the plug-in solve (DoubleLinearSolver::solve = pipsgpu_leaf_solve), as in the reference. Inside the
+    // batched solveCompressed it is OFF by default (PIPSGPU_REFINE_KKT=1 enables it): the Schur complement was formed with the
+    // perturbed factors, so unrefined leaf solves make solveCompressed the exact solve of ONE consistent (perturbed) KKT
+    // system, while refined leaf solves mix K and K + E and measure worse (tests/test_gpu_outer_solve.py); the outer
+    // BiCGStab (pipsgpu_kkt_solve) removes the perturbation error either way.
     int refine_steps = 2;
     bool refine_always = false;
+    bool refine_kkt = false;
     bool any_perturbed = false;
     // streaming persistent solve (psolve.cu): solve pool + per-front descriptors in sweep order
     DevBuf<SolveFront> sfront;
@@ -227,8 +233,8 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
-        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
-        a.gt_ptr = gt_ptr.p; a.gt_list = gt_list.p; a.group_lists = group_lists ? 1 : 0; a.bp_threads = bp_threads;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.gmap = gmap.p; a.panel_staged = panel_staged ? 1 : 0;
+        a.stiles = stiles.p; a.sitems = sitems.p; a.bp_threads = bp_threads;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -304,7 +310,7 @@ void analyze_one(pipsgpu_leaf* lf) {
         for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p)
             if (lf->jcol[p] != i) kn = std::max(kn, std::fabs(lf->val[p]));
     lf->knorm = std::max(kn, 1.0);
-    build_border_groups(lf->S, lf->ctx ? lf->ctx->big_u : BIG_U, lf->ctx ? lf->ctx->group_frac : 0.6, lf->G);
+    lf->group_frac_used = build_border_groups_auto(lf->S, lf->ctx ? lf->ctx->big_u : BIG_U, lf->ctx ? lf->ctx->group_frac : -1.0, lf->G);
     lf->analyzed = true;
 }
 
@@ -372,7 +378,7 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
             CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
         }
         launch_small_fronts(fa, begin[0], count[0], s);
-        launch_big_panel(fa, begin[1], count[1], sb);
+        launch_big_panel(fa, begin[1], count[1], ctx->fl_umax[(size_t)lv], sb);
         launch_front_update_tiles(fa, tb, tc, sb);
         if (fork) {
             CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
@@ -391,7 +397,7 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
         cudaStream_t sg = fork ? s2 : s;
         const int b = first->batch;
         CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b], sg));
-        launch_border_groups(fa, gb, gc, sg);
+        launch_schur_syrk(fa, gb, gc, sg);
         CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b + 1], sg));
         ctx->grp_timed = true;
     }
@@ -615,14 +621,13 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     }
     if (const char* e = std::getenv("PIPSGPU_REFINE")) ctx->refine_steps = std::max(0, std::min(8, std::atoi(e)));
     if (const char* e = std::getenv("PIPSGPU_REFINE_ALWAYS")) ctx->refine_always = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_REFINE_KKT")) ctx->refine_kkt = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
-    if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
+    if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::atof(e));      // negative: automatic
     if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
     if (const char* e = std::getenv("PIPSGPU_OVERLAP")) ctx->overlap = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_XFORM")) ctx->xform = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_PANEL")) ctx->panel_staged = std::string(e) == "staged";
-    if (const char* e = std::getenv("PIPSGPU_GROUP_PIPE")) ctx->group_pipe = std::string(e) != "0";
-    if (const char* e = std::getenv("PIPSGPU_GROUP_LISTS")) ctx->group_lists = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_BP_THREADS")) ctx->bp_threads = (std::atoi(e) == 128) ? 128 : 256;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     {
@@ -1048,6 +1053,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         ctx->fl_ptr.assign(nlev * 2 + 1, 0);
         for (int g = 0; g < nlev * 2; ++g) ctx->fl_ptr[g + 1] = ctx->fl_ptr[g] + cnt2[g + 1];
         std::vector<int> fill(ctx->fl_ptr.begin(), ctx->fl_ptr.end() - 1);
+        ctx->fl_umax.assign((size_t)nlev, 0);
+        for (auto* lf : ctx->leaves)
+            for (int s2 = 0; s2 < lf->S.ns; ++s2) {
+                const FrontDesc& fd = fronts[(size_t)lf->front_base + s2];
+                int& mx = ctx->fl_umax[(size_t)(nlev - 1 - lf->S.sn_level[s2])];
+                if (kind_of(fd)) mx = std::max(mx, fd.na + fd.nb);
+            }
         for (auto* lf : ctx->leaves) {
             lf->fl_begin.assign(nlev * 2, 0); lf->fl_count.assign(nlev * 2, 0);
             for (int g = 0; g < nlev * 2; ++g) lf->fl_begin[g] = fill[g];
@@ -1062,11 +1074,9 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     // (grouping per leaf: build_border_groups in symbolic.cpp, run with the symbolic analysis on the host threads)
     std::vector<GroupDesc> groups;
     std::vector<GroupMember> gmembers;
-    std::vector<int> ginv;
-    std::vector<int8_t> gflags;
-    std::vector<int64_t> gt_ptr(1, 0);
-    std::vector<int> gt_list;
-    std::vector<GTile> gtiles;
+    std::vector<GroupMap> gmap;
+    std::vector<STile> stiles;
+    std::vector<int> sitems;
     std::vector<char> grouped((size_t)nfr, 0);
     if (ctx->grouping) {
         int64_t gw_run = 0, gw_max = 0;      // persistent (per batch) W21 scratch of the grouped fronts, behind the per-level area
@@ -1081,12 +1091,14 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
                 return G.mem_ptr[(size_t)x + 1] - G.mem_ptr[(size_t)x] > G.mem_ptr[(size_t)y + 1] - G.mem_ptr[(size_t)y];
             });
-            lf->gtile_begin = (int64_t)gtiles.size();
+            lf->gtile_begin = (int64_t)stiles.size();
+            std::vector<int8_t> gflags;      // [member][64-row block of the root's border index space]: has rows there
             for (int oi : order) {
                 GroupDesc gd;
-                gd.N = G.N[(size_t)oi]; gd.nblk = (gd.N + GROUP_TILE - 1) / GROUP_TILE;
+                gd.N = G.N[(size_t)oi]; gd.nblk = ((gd.N + SY_TM - 1) / SY_TM) * (SY_TM / GROUP_TILE);
                 gd.root = lf->front_base + G.root[(size_t)oi]; gd.pad = 0;
-                gd.mem_begin = (int)gmembers.size(); gd.inv_base = (int64_t)ginv.size();
+                gd.mem_begin = (int)gmembers.size(); gd.map_base = (int64_t)gmap.size();
+                gflags.clear();
                 for (int q = G.mem_ptr[(size_t)oi]; q < G.mem_ptr[(size_t)oi + 1]; ++q) {
                     const int f = lf->front_base + G.mem_front[(size_t)q];
                     const FrontDesc& fd = fronts[(size_t)f];
@@ -1100,33 +1112,53 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                     mb.Lb_off = fd.Loff + fd.w + fd.na; mb.Wb_off = fdm.Woff + fd.na;
                     mb.m = fd.w + fd.na + fd.nb; mb.u = fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f; mb.pad = 0;
                     gmembers.push_back(mb);
-                    const size_t base = ginv.size();
-                    ginv.resize(base + (size_t)gd.nblk * GROUP_TILE, -1);
+                    const size_t base = gmap.size();
+                    gmap.resize(base + (size_t)gd.nblk, GroupMap{0u, 0u, 0, 0u});
                     const int* pf = G.pos.data() + G.pos_ptr[(size_t)q];
                     if (G.pos_ptr[(size_t)q + 1] - G.pos_ptr[(size_t)q] != fd.nb) throw Error(PIPSGPU_ERR_INVALID, "border group: position map size mismatch");
-                    for (int t = 0; t < fd.nb; ++t) ginv[base + (size_t)pf[t]] = t;
-                    gflags.resize(base / GROUP_TILE + (size_t)gd.nblk, 0);
-                    for (int t = 0; t < fd.nb; ++t) gflags[base / GROUP_TILE + (size_t)pf[t] / GROUP_TILE] = 1;
+                    const size_t fbase = gflags.size();
+                    gflags.resize(fbase + (size_t)gd.nblk, 0);
+                    for (int t = 0; t < fd.nb; ++t) {
+                        const int p = pf[t], b = p / GROUP_TILE, r = p % GROUP_TILE;
+                        GroupMap& gm = gmap[base + (size_t)b];
+                        if (r < 32) gm.bits_lo |= 1u << r; else gm.bits_hi |= 1u << (r - 32);
+                        gm.slices |= 1u << (r >> 3);
+                        gflags[fbase + (size_t)b] = 1;
+                    }
+                    int run = 0;      // member rows are ascending in the root's index space: start = rows before the block
+                    for (int b = 0; b < gd.nblk; ++b) {
+                        GroupMap& gm = gmap[base + (size_t)b];
+                        gm.start = run;
+                        run += __builtin_popcount(gm.bits_lo) + __builtin_popcount(gm.bits_hi);
+                    }
                 }
                 gd.mem_end = (int)gmembers.size();
                 const int gi = (int)groups.size();
                 groups.push_back(gd);
                 const int nmem_g = gd.mem_end - gd.mem_begin;
-                const int8_t* fl = gflags.data() + gd.inv_base / GROUP_TILE;      // [member][block]
-                for (int bi = 0; bi < gd.nblk; ++bi)
-                    for (int bj = 0; bj <= bi; ++bj) {
-                        gtiles.push_back(GTile{gi, bi, bj, 0});
-                        for (int q = 0; q < nmem_g; ++q)
-                            if (fl[(size_t)q * gd.nblk + bi] && fl[(size_t)q * gd.nblk + bj]) gt_list.push_back(q);
-                        gt_ptr.push_back((int64_t)gt_list.size());
+                // output tiles (rows 128 bi .., columns 64 bj .., lower part) with their pipeline stages: every member that has
+                // rows in both ranges contributes its columns 0..15 and, if wider than 16, 16..31
+                const int nbi = gd.nblk / (SY_TM / GROUP_TILE), nbj = (gd.N + SY_TN - 1) / SY_TN;
+                for (int bi = 0; bi < nbi; ++bi)
+                    for (int bj = 0; bj < nbj && bj * SY_TN <= bi * SY_TM + SY_TM - 1; ++bj) {
+                        STile t;
+                        t.item_begin = (int64_t)sitems.size(); t.group = gi; t.bi = bi; t.bj = bj;
+                        for (int q = 0; q < nmem_g; ++q) {
+                            const int8_t* fl = gflags.data() + (size_t)q * gd.nblk;
+                            if (!((fl[2 * bi] || fl[2 * bi + 1]) && fl[bj])) continue;
+                            sitems.push_back(q << 1);
+                            if (gmembers[(size_t)gd.mem_begin + q].w > SY_KS) sitems.push_back((q << 1) | 1);
+                        }
+                        t.item_count = (int)((int64_t)sitems.size() - t.item_begin);
+                        if (t.item_count > 0) stiles.push_back(t);
                     }
             }
-            lf->gtile_count = (int64_t)gtiles.size() - lf->gtile_begin;
+            lf->gtile_count = (int64_t)stiles.size() - lf->gtile_begin;
             lf->G = BorderGroups();
         }
         ctx->Wtot = wlev_max + std::max(gw_max, gw_run);
     }
-    ctx->ngtiles = (int64_t)gtiles.size();
+    ctx->ngtiles = (int64_t)stiles.size();
     // ---- update tiles of the big fronts, grouped by (level, leaf); grouped fronts only keep the ancestor columns ----
     std::vector<TileDesc> tiles;
     {
@@ -1180,8 +1212,8 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
-    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gflags.upload(gflags, s); ctx->gtiles.upload(gtiles, s);
-    ctx->gt_ptr.upload(gt_ptr, s); ctx->gt_list.upload(gt_list, s);
+    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->gmap.upload(gmap, s);
+    ctx->stiles.upload(stiles, s); ctx->sitems.upload(sitems, s);
     ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
@@ -1866,7 +1898,7 @@ static void leaf_solve_refined(pipsgpu_ctx* ctx, const double* in, double* out, 
     if (ev0) CUDA_CHECK(cudaEventRecord(ev0, s));
     ctx->psolve(in, out, 0);
     if (ev1) CUDA_CHECK(cudaEventRecord(ev1, s));
-    if (ctx->refine_steps <= 0 || !(ctx->any_perturbed || ctx->refine_always)) return;
+    if (!ctx->refine_kkt || ctx->refine_steps <= 0 || !(ctx->any_perturbed || ctx->refine_always)) return;
     for (int it = 0; it < ctx->refine_steps; ++it) {
         launch_axpby(ctx->npos, -1.0, in, 0.0, res, s);                                              // res = -b
         launch_sym_spmv(ctx->nnzK, ctx->kcoo_row.p, ctx->kcoo_col.p, ctx->Kval.p, 1.0, out, res, s);   // res += K z
@@ -1918,7 +1950,7 @@ static void kkt_solve_device(pipsgpu_kkt* k, const double* in0, const double* in
     if (N > 0) {
         launch_vec_zero(k->tl.p, N, s);
         launch_border_mult(ctx->bg_row.p, ctx->bg_b0.p, ctx->Bval.p, ctx->nnzB, b, k->tl.p, s);
-        if (ctx->refine_steps > 0 && (ctx->any_perturbed || ctx->refine_always)) {
+        if (ctx->refine_kkt && ctx->refine_steps > 0 && (ctx->any_perturbed || ctx->refine_always)) {
             // w = K^-1 (Bord u) refined, then b_i -= w (residual scratch: ctx->work)
             leaf_solve_refined(ctx, k->tl.p, k->wl.p, ctx->work.p);
             launch_axpy(-1.0, k->wl.p, outl, N, s);

@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, session 5: Schur kernel with bitmap row maps + 8x8 sub-tile skipping + model-chosen grouping; blocked warp-level ldlt_diag_kernel
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -m gpu -x -q -k "dense or root_dim or sc_assembly" > gpurun_out/s5_pytest_dense.log 2>&1; echo "pytest dense rc=$?"
+tail -8 gpurun_out/s5_pytest_dense.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=5 > gpurun_out/s5_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/s5_pytest_gpu.log
+tail -25 gpurun_out/s5_pytest_gpu.log
+run() { name=$1; shift; timeout 1200 python bench.py "$@" > gpurun_out/s5_bench_$name.json 2> gpurun_out/s5_bench_$name.err; echo "bench $name rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/s5_bench_$name.json").read().strip().splitlines()[-1])
+    print("$name", "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"]*1e3,2), {k:round(v,2) for k,v in d["stages_ms"].items()}, {k:round(v,2) for k,v in d["kernels_ms"].items()}, (d.get("check") or {}).get("solve_residual_rel"))
+except Exception as e:
+    print("$name parse failed", e)
+PY
+tail -3 gpurun_out/s5_bench_$name.err; }
+run c2 --config C2 --steps 5 --warmup 3 --no-cpu-baseline
+run c3_64 --config C3 --blocks-per-gpu 64 --steps 3 --warmup 3 --no-cpu-baseline
+run c4 --config C4 --steps 3 --warmup 3 --no-cpu-baseline
+for f in 0.6 0.2 0.0; do
+PIPSGPU_GROUP_FRAC=$f run c2_f$f --config C2 --steps 5 --warmup 3 --no-cpu-baseline --no-check
+PIPSGPU_GROUP_FRAC=$f run c3_64_f$f --config C3 --blocks-per-gpu 64 --steps 3 --warmup 3 --no-cpu-baseline --no-check
+PIPSGPU_GROUP_FRAC=$f run c4_f$f --config C4 --steps 3 --warmup 3 --no-cpu-baseline --no-check
+done
+du -sh gpurun_out
