@@ -136,6 +136,20 @@ int pipsgpu_leaf_add_schur(pipsgpu_leaf* leaf, pipsgpu_sc* sc);
  * --------------------------------------------------------------------------------------------------------- */
 int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsgpu_sc** sc);
 int pipsgpu_sc_destroy(pipsgpu_sc* sc);
+/* sLinsysRootAug with hasSparseKkt (LS/sLinsysRootAug.C:79-208 finalizeKKTdist, 1629-1767 finalizeKKTsparse: kkt is a
+ * SparseSymmetricMatrix whose pattern is precomputed once). Declares the lower-triangular CSR pattern (every diagonal entry
+ * stored) of the Schur complement in its index order [x0; y0; yl; zl]. From then on
+ *   - reduceKKT all-reduces only the nnz pattern values (reduceKKTsparse / reduceToAllProcs,
+ *     LS/DistributedRootLinearSystem.C:885-925) instead of the packed dense triangle,
+ *   - factorize / solve run the sparse multifrontal LDL^T that also serves the leaves, in a private context on the same
+ *     stream (replaces the sparse root solver, SOL/PardisoSolver/PardisoIndefSolver, Ma57 root solver); symbolic analysis
+ *     happens here, once. If a pivot has to be perturbed or the inertia is not (n0, n - n0, 0) the dense solver (which can
+ *     pivot) takes over for that factorisation.
+ * The assembly target stays the dense device buffer (leaves add their Schur terms there); entries outside the pattern
+ * are ignored. */
+int pipsgpu_sc_set_sparse_pattern(pipsgpu_sc* sc, const int* krow, const int* jcol, int threads);
+/* 1 if the last pipsgpu_sc_factorize / pipsgpu_kkt_factorize used the sparse root solver */
+int pipsgpu_sc_uses_sparse_solver(pipsgpu_sc* sc);
 /* initializeKKT / myAtPutZeros (LS/DistributedRootLinearSystem.C:840-847, 1467-1488) */
 int pipsgpu_sc_zero(pipsgpu_sc* sc);
 /* reduceKKT -> reduceKKTdense (LS/DistributedRootLinearSystem.C:849-881): NCCL all-reduce (sum, f64) of the packed
@@ -245,8 +259,7 @@ int pipsgpu_symbolic_export(pipsgpu_symbolic* sym, int* perm, int8_t* ptype, int
 /* grouping of the big fronts for the deferred border x border Schur-complement updates (host-only inspection of what
  * pipsgpu_ctx_commit builds; no counterpart in the reference, whose plugins keep their supernode scheduling private -
  * PardisoSchurSolver.C:434-477 just receives the finished Schur complement). Call once with null arrays to get
- * counts = {groups, members, positions}, then with arrays of those sizes (mem_ptr: groups+1, pos_ptr: members+1).
- * frac < 0: the fraction is chosen by the cost model of the Schur-term kernel (what pipsgpu_ctx_commit does by default). */
+ * counts = {groups, members, positions}, then with arrays of those sizes (mem_ptr: groups+1, pos_ptr: members+1). */
 int pipsgpu_symbolic_border_groups(pipsgpu_symbolic* sym, int big_u, double frac, int64_t counts[3], int* root, int* N,
                                    int* mem_ptr, int* mem_front, int64_t* pos_ptr, int* pos);
 

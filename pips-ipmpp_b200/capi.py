@@ -307,6 +307,15 @@ class SchurComplement:
         _check(lib().pipsgpu_sc_solve(self.h, C.c_int(nrhs), _ip(x)))
         return x
 
+    def set_sparse_pattern(self, krow, jcol, threads=0):
+        """lower CSR pattern of the Schur complement: sparse all-reduce + sparse root LDL^T (pipsgpu_sc_set_sparse_pattern)"""
+        krow, jcol = _i32(krow), _i32(jcol)
+        assert len(krow) == self.n + 1
+        _check(lib().pipsgpu_sc_set_sparse_pattern(self.h, _ip(krow), _ip(jcol), C.c_int(threads)))
+
+    def uses_sparse_solver(self):
+        return bool(lib().pipsgpu_sc_uses_sparse_solver(self.h))
+
     def download(self):
         out = np.zeros((self.n, self.n))
         _check(lib().pipsgpu_sc_download(self.h, _ip(out)))

@@ -118,7 +118,7 @@ int pipsgpu_symbolic_border_groups(pipsgpu_symbolic* sym, int big_u, double frac
     PIPSGPU_TRY
     if (!sym || !counts) throw std::runtime_error("pipsgpu_symbolic_border_groups: null argument");
     pipsgpu::BorderGroups G;
-    pipsgpu::build_border_groups_auto(sym->S, big_u, frac, G);      // frac < 0: chosen by the cost model
+    pipsgpu::build_border_groups(sym->S, big_u, frac, G);
     counts[0] = (int64_t)G.root.size(); counts[1] = (int64_t)G.mem_front.size(); counts[2] = (int64_t)G.pos.size();
     copy_out(root, G.root); copy_out(N, G.N); copy_out(mem_ptr, G.mem_ptr); copy_out(mem_front, G.mem_front);
     copy_out(pos_ptr, G.pos_ptr); copy_out(pos, G.pos);

@@ -654,187 +654,131 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
 }
 
 // -----------------------------------------------------------------------------------------------------
-// Deferred border x border updates = the Schur term  SC -= sum_f L_B,f D_f L_B,f^T  of the grouped big fronts.
-// One CTA (4 warps, 2 CTAs per SM) per 128 x 64 output tile of a group's N x N index space (lower part). The tile's
-// pipeline stages - (member, 16-column half) pairs, listed by the host - stream through a 4-deep cp.async ring:
-//   A stage = rows of tile bi of L_B,f (128 x 16), B stage = rows of tile bj of W_B,f = L_B,f D_f (64 x 16), both
-//   k-major in shared memory; the member's rows are scattered to their positions in the root's border row list while
-//   staging (inverse row map, absent rows and columns beyond the member's width are zero-filled by cp.async itself).
-// Metadata (next stage's member descriptor and row indices) is fetched one iteration ahead, the stage id two ahead, so
-// that no dependent global load sits between the barrier and the tensor work. 64 x 32 warp tiles of m8n8k4 DMMAs
-// (12 shared loads per 32 DMMAs, as in dgemm_nt_kernel); one flush (red.global.add.f64) per tile.
+// Deferred border x border updates: one CTA per 64x64 tile (lower) of a group's N x N index space. For every member
+// front f of the group the tile receives  L_B,f(rows of tile bi) * (L_B,f D_f)(rows of tile bj)^T ; rows of f are
+// scattered to their positions in the root's border row list while staging (absent rows are zero), W = L D is
+// recomputed from L and the block-diagonal D on the fly. One flush (red.global.add.f64) per tile and group instead of
+// one per tile and front: the per-front flush was bound by the RED issue rate (~1.3 cycles per lane and SM).
 // -----------------------------------------------------------------------------------------------------
-constexpr int SY_STAGE_DOUBLES = SY_KS * (SY_LDA + SY_LDB);
-constexpr int SY_SMEM = SY_STAGES * SY_STAGE_DOUBLES * (int)sizeof(double);
-
-__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, bool valid) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-    const int sz = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-struct SyMeta {
-    const double* La;   // L_B of the member, column k0
-    const double* Wb;   // (L_B D) of the member, column k0
-    int m, u, nc;       // leading dimensions, valid columns of this stage (1 .. 16)
-    int ti, tj;         // this thread's source rows (member-local border row) for the A / B tile, or -1
-    uint32_t mask;      // bits 0..15: non-empty 8-row slices of the A tile, bits 16..23: of the B tile
-};
-
-__global__ void __launch_bounds__(128, 2) schur_syrk_kernel(FactorArgs a, int64_t tile_begin) {
-    extern __shared__ double sy_smem[];
-    __shared__ uint32_t s_info[SY_STAGES];         // per stage: slice masks (bits 0..23) | k4-steps << 24
-    const STile td = a.stiles[tile_begin + blockIdx.x];
+// one staging batch of a member: columns k0, k0+2, .., k0+14 of tile rows ti (L_B) and tj (L_B D)
+#define GROUP_LOAD_BATCH(Lb_, Wb_, m_, u_, w_, ti_, tj_, k0_, av_, bv_)                       \
+    _Pragma("unroll") for (int qq = 0; qq < 8; ++qq) {                                        \
+        const int k_ = (k0_) + 2 * qq;                                                        \
+        av_[qq] = (k_ < (w_) && (ti_) >= 0) ? (Lb_)[(size_t)k_ * (m_) + (ti_)] : 0.0;         \
+        bv_[qq] = (k_ < (w_) && (tj_) >= 0) ? (Wb_)[(size_t)k_ * (u_) + (tj_)] : 0.0;         \
+    }
+// PIPE (PIPSGPU_GROUP_PIPE=1): the first batch of the NEXT contributing member is loaded into registers before the MMA of
+// the current one, so the global round trip of the staging overlaps the tensor work and the barriers.
+// LISTS (PIPSGPU_GROUP_LISTS=1): the contributing members of the tile come from a host-built list instead of a scan of the
+// per-member block flags.
+template <bool PIPE, bool LISTS>
+__global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
+    __shared__ double As[MAXW * KLD];
+    __shared__ double Bs[MAXW * KLD];
+    const GTile td = a.gtiles[gtile_begin + blockIdx.x];
     const GroupDesc g = a.groups[td.group];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp >> 1) * 64, wc = (warp & 1) * 32;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
     const int lr = lane >> 2, lk = lane & 3;
-    const int rb = tid & 63, kh = tid >> 6;        // B staging: thread = (tile column rb, column parity kh)
-    const int n = td.item_count;
-    const int* __restrict__ items = a.sitems + td.item_begin;
-    const GroupMap* __restrict__ mapA = a.gmap + g.map_base + 2 * td.bi;      // + q * nblk; two consecutive records
-    const GroupMap* __restrict__ mapB = a.gmap + g.map_base + td.bj;
-    // 8 x 8 sub-tiles of this warp that lie above the diagonal are never computed: dmask[x] = admissible y
-    const int i0 = td.bi * SY_TM, j0 = td.bj * SY_TN;
-    uint32_t dmask = 0;                            // 4 bits per x
+    const int r = tid & 63, kq = tid >> 6;     // staging: thread = (tile row r, column parity kq)
+    double acc[4][4][2];
 #pragma unroll
-    for (int x = 0; x < 8; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y)
-            if (j0 + wc + y * 8 <= i0 + wr + x * 8 + 7) dmask |= 1u << (x * 4 + y);
-    double acc[8][4][2];
-#pragma unroll
-    for (int x = 0; x < 8; ++x)
+    for (int x = 0; x < 4; ++x)
 #pragma unroll
         for (int y = 0; y < 4; ++y) acc[x][y][0] = acc[x][y][1] = 0.0;
-
-    auto fetch = [&](int item) {
-        SyMeta M;
-        const int q = item >> 1, k0 = (item & 1) * SY_KS;
-        const GroupMember mb = a.gmembers[g.mem_begin + q];
-        M.m = mb.m; M.u = mb.u;
-        M.nc = min(SY_KS, mb.w - k0);
-        M.La = a.L + mb.Lb_off + (int64_t)k0 * mb.m;
-        M.Wb = a.W + mb.Wb_off + (int64_t)k0 * mb.u;
-        const int4 ra0 = *reinterpret_cast<const int4*>(mapA + (int64_t)q * g.nblk);
-        const int4 ra1 = *reinterpret_cast<const int4*>(mapA + (int64_t)q * g.nblk + 1);
-        const int4 rb0 = *reinterpret_cast<const int4*>(mapB + (int64_t)q * g.nblk);
-        {   // A tile row tid: root position 128 bi + tid
-            const int word = tid >> 5;
-            const uint32_t wv = (word == 0) ? (uint32_t)ra0.x : (word == 1) ? (uint32_t)ra0.y : (word == 2) ? (uint32_t)ra1.x : (uint32_t)ra1.y;
-            const int base = (word < 2) ? ra0.z + (word == 1 ? __popc((uint32_t)ra0.x) : 0)
-                                        : ra1.z + (word == 3 ? __popc((uint32_t)ra1.x) : 0);
-            M.ti = ((wv >> lane) & 1u) ? base + __popc(wv & ((1u << lane) - 1u)) : -1;
-        }
-        {   // B tile row rb: root position 64 bj + rb
-            const uint32_t wv = (rb < 32) ? (uint32_t)rb0.x : (uint32_t)rb0.y;
-            const int base = rb0.z + (rb < 32 ? 0 : __popc((uint32_t)rb0.x));
-            M.tj = ((wv >> lane) & 1u) ? base + __popc(wv & ((1u << lane) - 1u)) : -1;
-        }
-        M.mask = ((uint32_t)ra0.w & 0xffu) | (((uint32_t)ra1.w & 0xffu) << 8) | (((uint32_t)rb0.w & 0xffu) << 16);
-        return M;
+    const int64_t inv_stride = (int64_t)g.nblk * GROUP_TILE;
+    const int* inv_i = a.ginv + g.inv_base + (int64_t)td.bi * GROUP_TILE + r;
+    const int* inv_j = a.ginv + g.inv_base + (int64_t)td.bj * GROUP_TILE + r;
+    // gflags[(inv_base / 64) + member * nblk + b] != 0: the member has border rows in block b of the root's index space.
+    // Members without rows in both tile ranges are skipped without touching a barrier.
+    const int8_t* flag_i = a.gflags + g.inv_base / GROUP_TILE + td.bi;
+    const int8_t* flag_j = a.gflags + g.inv_base / GROUP_TILE + td.bj;
+    // cursor over the contributing members: an index into the tile's list (LISTS) or a member index (flag scan)
+    const int* list = LISTS ? a.gt_list + a.gt_ptr[gtile_begin + blockIdx.x] : nullptr;
+    const int nmem = LISTS ? (int)(a.gt_ptr[gtile_begin + blockIdx.x + 1] - a.gt_ptr[gtile_begin + blockIdx.x])
+                           : g.mem_end - g.mem_begin;
+    auto skip = [&](int c) {
+        if (!LISTS)
+            while (c < nmem && !(flag_i[(int64_t)c * g.nblk] && flag_j[(int64_t)c * g.nblk])) ++c;
+        return c;
     };
-    auto issue = [&](int stage, const SyMeta& M) {
-        double* As = sy_smem + (size_t)stage * SY_STAGE_DOUBLES;
-        double* Bs = As + SY_KS * SY_LDA;
-        const int kmax = (M.nc + 3) & ~3;
-        const double* sa = M.La + (M.ti >= 0 ? M.ti : 0);
-        const double* sb = M.Wb + (M.tj >= 0 ? M.tj : 0) + (int64_t)kh * M.u;
-        // rows of empty 8-row slices are neither copied nor zero-filled: the tensor work skips those slices
-        const bool rowA = (M.mask >> (tid >> 3)) & 1u, rowB = (M.mask >> (16 + (rb >> 3))) & 1u;
-        if (rowA) {
-#pragma unroll
-            for (int k = 0; k < SY_KS; ++k) {
-                if (k < kmax) cp_async8(As + k * SY_LDA + tid, sa, M.ti >= 0 && k < M.nc);
-                sa += M.m;
-            }
-        }
-        if (rowB) {
-#pragma unroll
-            for (int kk = 0; kk < SY_KS / 2; ++kk) {
-                const int k = kh + 2 * kk;
-                if (k < kmax) cp_async8(Bs + k * SY_LDB + rb, sb, M.tj >= 0 && k < M.nc);
-                sb += 2 * (int64_t)M.u;
-            }
-        }
-        if (tid == 0) s_info[stage] = M.mask | ((uint32_t)(kmax >> 2) << 24);
-    };
-
-    // ---- prologue: stages 0 .. SY_STAGES-2 in flight, metadata of stage SY_STAGES-1 fetched ----
-    int pre[SY_STAGES + 1];
-#pragma unroll
-    for (int s = 0; s <= SY_STAGES; ++s) pre[s] = (s < n) ? items[s] : 0;
-#pragma unroll
-    for (int s = 0; s < SY_STAGES - 1; ++s) {
-        if (s < n) { const SyMeta M = fetch(pre[s]); issue(s, M); }
-        cp_async_commit();
+    int q = skip(0);
+    GroupMember mb;
+    int ti = -1, tj = -1;
+    if (q < nmem) {
+        const int qm = LISTS ? list[q] : q;
+        mb = a.gmembers[g.mem_begin + qm];
+        ti = inv_i[(int64_t)qm * inv_stride];
+        tj = inv_j[(int64_t)qm * inv_stride];
     }
-    SyMeta next;
-    next.La = a.L; next.Wb = a.W; next.m = next.u = 0; next.nc = 0; next.ti = next.tj = -1; next.mask = 0;
-    if (SY_STAGES - 1 < n) next = fetch(pre[SY_STAGES - 1]);
-    int item_after = pre[SY_STAGES];               // stage id of iteration i + SY_STAGES
-
-    for (int i = 0; i < n; ++i) {
-        cp_async_wait<SY_STAGES - 2>();            // this thread's copies of stage i have landed
-        __syncthreads();                           // ... everybody's; and everybody is done with the MMAs of stage i-1
-        const int st = i % SY_STAGES;
-        if (i + SY_STAGES - 1 < n) issue((i + SY_STAGES - 1) % SY_STAGES, next);
-        cp_async_commit();
-        {
-            const int cur = item_after;
-            if (i + SY_STAGES + 1 < n) item_after = items[i + SY_STAGES + 1];
-            if (i + SY_STAGES < n) next = fetch(cur);
+    bool first = true;
+    double pav[8], pbv[8];
+    if (PIPE && q < nmem) {
+        const double* Lb0 = a.L + mb.Lb_off;
+        const double* Wb0 = a.W + mb.Wb_off;
+        GROUP_LOAD_BATCH(Lb0, Wb0, mb.m, mb.u, mb.w, ti, tj, kq, pav, pbv)
+    }
+    while (q < nmem) {
+        // the next contributing member's descriptor and row maps are requested before this member's panel is staged
+        const int qn = skip(q + 1);
+        GroupMember nmb = mb;
+        int nti = -1, ntj = -1;
+        if (qn < nmem) {
+            const int qm = LISTS ? list[qn] : qn;
+            nmb = a.gmembers[g.mem_begin + qm];
+            nti = inv_i[(int64_t)qm * inv_stride];
+            ntj = inv_j[(int64_t)qm * inv_stride];
         }
-        const double* As = sy_smem + (size_t)st * SY_STAGE_DOUBLES;
-        const double* Bs = As + SY_KS * SY_LDA;
-        const uint32_t info = s_info[st];
-        const int nk4 = (int)(info >> 24);
-        const uint32_t ma = (info >> (wr >> 3)) & 0xffu;                    // this warp's 8 row slices
-        const uint32_t mb = (info >> (16 + (wc >> 3))) & 0xfu;              // ... 4 column slices
-        if (ma == 0 || mb == 0) continue;
-        uint32_t live = 0;                                                  // (x, y) sub-tiles with work, 4 bits per x
+        const int w = mb.w, m = mb.m, u = mb.u;
+        const int w4 = (w + 3) & ~3;
+        const double* Lb = a.L + mb.Lb_off;
+        const double* Wb = a.W + mb.Wb_off;
+        // all loads of a batch of 8 columns are issued before the first one is consumed (the staging is one global
+        // round trip per batch; W = L D comes from the member's persistent panel scratch)
+        for (int kb = 0; kb < w4; kb += 16) {
+            double av[8], bv[8];
+            if (PIPE && kb == 0) {
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-            if ((ma >> x) & 1u) live |= (mb << (x * 4));
-        live &= dmask;
+                for (int qq = 0; qq < 8; ++qq) { av[qq] = pav[qq]; bv[qq] = pbv[qq]; }
+            } else {
+                GROUP_LOAD_BATCH(Lb, Wb, m, u, w, ti, tj, kb + kq, av, bv)
+            }
+            if (kb == 0 && !first) __syncthreads();      // the previous member's MMA has read As / Bs
 #pragma unroll
-        for (int kk = 0; kk < SY_KS / 4; ++kk) {
-            if (kk < nk4) {
-                double bf[4];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) bf[y] = Bs[(kk * 4 + lk) * SY_LDB + wc + y * 8 + lr];
-#pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    if ((live >> (x * 4)) & 0xfu) {
-                        const double af = As[(kk * 4 + lk) * SY_LDA + wr + x * 8 + lr];
-#pragma unroll
-                        for (int y = 0; y < 4; ++y)
-                            if ((live >> (x * 4 + y)) & 1u) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af, bf[y]);
-                    }
-                }
+            for (int qq = 0; qq < 8; ++qq) {
+                const int k = kb + kq + 2 * qq;
+                if (k < w4) { As[k * KLD + r] = av[qq]; Bs[k * KLD + r] = bv[qq]; }
             }
         }
+        first = false;
+        __syncthreads();
+        if (PIPE && qn < nmem) {
+            const double* Lbn = a.L + nmb.Lb_off;
+            const double* Wbn = a.W + nmb.Wb_off;
+            GROUP_LOAD_BATCH(Lbn, Wbn, nmb.m, nmb.u, nmb.w, nti, ntj, kq, pav, pbv)
+        }
+        for (int k0 = 0; k0 < w4; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) af[x] = As[(k0 + lk) * KLD + wr + x * 8 + lr];
+#pragma unroll
+            for (int y = 0; y < 4; ++y) bf[y] = Bs[(k0 + lk) * KLD + wc + y * 8 + lr];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) dmma_m8n8k4(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
+        }
+        mb = nmb; ti = nti; tj = ntj; q = qn;
     }
-    cp_async_wait<0>();
-    // ---- flush: SC[rowb[gi]][rowb[gj]] -= acc for gj <= gi (rowb ascending: both land in the lower triangle) ----
     const FrontDesc& rd = a.fronts[g.root];
-    const int* __restrict__ rowb = a.rowg + rd.rows_off + rd.na;   // Schur-complement index of every border row of the root
-    int cj[4][2];
+    const int* rowb = a.rowg + rd.rows_off + rd.na;            // Schur-complement index of every border row of the root
+    const int i0 = td.bi * GROUP_TILE, j0 = td.bj * GROUP_TILE;
 #pragma unroll
-    for (int y = 0; y < 4; ++y)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int gj = j0 + wc + y * 8 + lk * 2 + e;
-            cj[y][e] = (gj < g.N) ? rowb[gj] : 0;
-        }
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
+    for (int x = 0; x < 4; ++x) {
         const int gi = i0 + wr + x * 8 + lr;
         if (gi >= g.N) continue;
-        double* scrow = a.SC + (int64_t)rowb[gi] * a.ldsc;
+        const int64_t scrow = (int64_t)rowb[gi] * a.ldsc;
 #pragma unroll
         for (int y = 0; y < 4; ++y)
 #pragma unroll
@@ -842,13 +786,19 @@ __global__ void __launch_bounds__(128, 2) schur_syrk_kernel(FactorArgs a, int64_
                 const int gj = j0 + wc + y * 8 + lk * 2 + e;
                 if (gj > gi) continue;
                 const double v = acc[x][y][e];
-                if (v != 0.0) atomicAdd(scrow + cj[y][e], -v);
+                if (v != 0.0) atomicAdd(&a.SC[scrow + rowb[gj]], -v);
             }
     }
 }
-void launch_schur_syrk(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s) {
-    if (ntiles <= 0 || !a.SC) return;
-    schur_syrk_kernel<<<(unsigned)ntiles, 128, SY_SMEM, s>>>(a, tile_begin);
+void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
+    if (ngtiles <= 0 || !a.SC) return;
+    if (a.group_lists) {
+        if (a.group_pipe) border_group_kernel<true, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+        else border_group_kernel<false, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    } else {
+        if (a.group_pipe) border_group_kernel<true, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+        else border_group_kernel<false, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    }
     COUNT_LAUNCH();
 }
 
@@ -1526,8 +1476,6 @@ cudaError_t init_kernel_attributes() {
     e = cudaFuncSetAttribute(big_panel_kernel<true, BF_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (BF_T / 32) * PT_TILE * (int)sizeof(double));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM);
     return e;
 }
 }  // namespace pipsgpu

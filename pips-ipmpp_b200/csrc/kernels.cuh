@@ -16,39 +16,23 @@ constexpr int TILE = 64;         // output tile of the tiled update
 
 struct TileDesc { int front, bi, bj, grouped; };   // grouped: the border x border part of this front is left to its group
 
-// ---- deferred border x border updates = the Schur term (schur_syrk_kernel) ----
+// ---- deferred border x border updates (border_group_kernel) ----
 // A group is a connected piece of a block's front tree whose members' border row sets are nested in the group root's
 // (border rows are never eliminated, so border(child) is a subset of border(parent)). Its share of
-// SC -= Bord^T K^-1 Bord  is one SYRK over the concatenated border panels of the members in the root's index space:
-// per 128 x 64 output tile the contributing members are streamed through a cp.async ring (K = sum of their widths),
-// accumulated on the FP64 tensor pipe and flushed once per tile instead of once per front.
-constexpr int GROUP_TILE = 64;   // granularity of the inverse row maps and of the tile columns
-constexpr int SY_TM = 128;       // tile rows
-constexpr int SY_TN = 64;        // tile columns
-constexpr int SY_KS = 16;        // columns of a member per pipeline stage (members wider than 16 take two stages)
-constexpr int SY_STAGES = 4;
-constexpr int SY_LDA = SY_TM + 4;   // k-major staging, leading dimension = 4 mod 16: conflict-free fragment loads
-constexpr int SY_LDB = SY_TN + 4;
+// SC -= Bord^T K^-1 Bord  is one SYRK over the concatenated border panels of the members in the root's index space,
+// accumulated in registers and flushed once per 64x64 tile instead of once per front.
+constexpr int GROUP_TILE = 64;
 struct GroupMember {             // border rows of a member: Lb(t,k) = L[Lb_off + k*m + t],  (L_B D)(t,k) = W[Wb_off + k*u + t]
     int64_t Lb_off, Wb_off;      // Wb_off: the member's W21 scratch is persistent (not the per-level one), see pipsgpu_ctx_commit
     int m, u, w, col0, front, pad;
 };
-// Row map of a member, one record per 64-row block b of the root's border index space:
-//   bits    which of the root positions 64b .. 64b+63 are border rows of the member,
-//   start   number of member rows at root positions < 64b  (member row of position p = start + rank of p in bits),
-//   slices  bit s: the member has a row among positions 64b+8s .. 64b+8s+7  (the tensor work skips empty 8-row slices)
-struct alignas(16) GroupMap { uint32_t bits_lo, bits_hi; int start; uint32_t slices; };
 struct GroupDesc {
-    int64_t map_base;   // gmap[map_base + member*nblk + b]
+    int64_t inv_base;   // ginv[inv_base + (member*nblk + b)*64 + r] = member's border row at root position 64b+r, or -1
     int mem_begin, mem_end;
-    int N, nblk;        // N = border rows of the root front, nblk = ceil(N / 64) rounded up to even (128-row tiles)
+    int N, nblk;        // N = border rows of the root front, nblk = ceil(N / 64)
     int root, pad;
 };
-struct STile {          // one output tile: rows 128 bi .., columns 64 bj .. of the group's N x N index space (lower part)
-    int64_t item_begin; // into sitems: (group-local member << 1) | half, half = columns 16 .. 31 of the member
-    int item_count;
-    int group, bi, bj;
-};
+struct GTile { int group, bi, bj, pad; };
 
 // One front (supernode) of one scenario block. All offsets index context-wide pools.
 struct FrontDesc {
@@ -99,11 +83,15 @@ struct FactorArgs {
     const TileDesc* tiles;       // update tiles of the big fronts, grouped by level
     const GroupDesc* groups;
     const GroupMember* gmembers;
-    const GroupMap* gmap;
-    const STile* stiles;         // output tiles of the group SYRKs, grouped by leaf
-    const int* sitems;           // per tile: its pipeline stages (see STile)
+    const int* ginv;
+    const int64_t* gt_ptr;       // per group tile: range of gt_list (group-local member indices with rows in both blocks)
+    const int* gt_list;
+    int group_lists;             // PIPSGPU_GROUP_LISTS=1: walk gt_list instead of scanning gflags
     int bp_threads;              // CTA size of big_panel_kernel (128 or 256)
+    int group_pipe;              // PIPSGPU_GROUP_PIPE=1: software-pipelined member staging in border_group_kernel
     int panel_staged;            // PIPSGPU_PANEL=staged: panel chunks staged in shared memory (kernels.cu: panel_chunk_staged)
+    const int8_t* gflags;        // per (group member, 64-row block of the root's border index space): has rows there
+    const GTile* gtiles;
 };
 
 struct SolveArgs {
@@ -182,7 +170,7 @@ void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s); 
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);      // fronts fl_fronts[begin..)
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, int max_u, cudaStream_t s);   // max_u: tallest front of the range
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
-void launch_schur_syrk(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);
+void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s);
 void launch_gather_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_scatter_perm(const int* gidx, const double* src, double* dst, int64_t n, int nrhs, int64_t stride, cudaStream_t s);
 void launch_fwd_level(const SolveArgs& a, int cls, int level_begin, int nfronts, int nrhs, cudaStream_t s);
@@ -249,6 +237,9 @@ void launch_axpby(int64_t n, double a, const double* x, double b, double* y, cud
 void launch_diag_axpy(int n, double alpha, const double* d, const double* x, double* y, cudaStream_t s);   // y += alpha d .* x
 void launch_dot(int64_t n, const double* x, const double* y, double* partial, double* out, cudaStream_t s);   // deterministic
 constexpr int DOT_SCRATCH = 1024;
+void launch_gather_idx(const double* A, const int64_t* idx, int64_t n, double* out, cudaStream_t s);    // out[e] = A[idx[e]]
+void launch_scatter_idx(double* A, const int64_t* idx, int64_t n, const double* in, cudaStream_t s);    // A[idx[e]] = in[e]
+void launch_absmax_eps(const double* v, int64_t n, double rel, double* eps_out, cudaStream_t s);        // *eps_out = rel * max|v|
 
 int64_t kernel_launch_count();
 // FP64 tensor-pipe peak microbenchmark (register-resident DMMA chains); returns the flops of the launch

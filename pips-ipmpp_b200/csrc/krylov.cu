@@ -105,4 +105,42 @@ void launch_dot(int64_t n, const double* x, const double* y, double* partial, do
     count_launch("dot_final_kernel");
 }
 
+// ---- sparse root Schur complement (pipsgpu_sc_set_sparse_pattern): pattern values <-> dense assembly buffer ----
+// out[e] = A[idx[e]]  /  A[idx[e]] = in[e]
+__global__ void gather_idx_kernel(const double* __restrict__ A, const int64_t* __restrict__ idx, int64_t n, double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = A[idx[e]];
+}
+__global__ void scatter_idx_kernel(double* __restrict__ A, const int64_t* __restrict__ idx, int64_t n, const double* __restrict__ in) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) A[idx[e]] = in[e];
+}
+void launch_gather_idx(const double* A, const int64_t* idx, int64_t n, double* out, cudaStream_t s) {
+    if (n <= 0) return;
+    gather_idx_kernel<<<kr_cdiv(n, 256), 256, 0, s>>>(A, idx, n, out);
+    count_launch("gather_idx_kernel");
+}
+void launch_scatter_idx(double* A, const int64_t* idx, int64_t n, const double* in, cudaStream_t s) {
+    if (n <= 0) return;
+    scatter_idx_kernel<<<kr_cdiv(n, 256), 256, 0, s>>>(A, idx, n, in);
+    count_launch("scatter_idx_kernel");
+}
+// *eps_out = rel * max(1e-300, max_i |v_i|): static-pivot threshold of the sparse root factorisation, one block
+__global__ void __launch_bounds__(1024) absmax_eps_kernel(const double* __restrict__ v, int64_t n, double rel, double* __restrict__ eps_out) {
+    __shared__ double sh[1024];
+    double m = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) m = fmax(m, fabs(v[i]));
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *eps_out = rel * fmax(sh[0], 1e-300);
+}
+void launch_absmax_eps(const double* v, int64_t n, double rel, double* eps_out, cudaStream_t s) {
+    absmax_eps_kernel<<<1, 1024, 0, s>>>(v, n, rel, eps_out);
+    count_launch("absmax_eps_kernel");
+}
+
 }  // namespace pipsgpu

@@ -100,7 +100,6 @@ struct pipsgpu_leaf {
     // symbolic
     LeafSymbolic S;
     BorderGroups G;                  // grouping of the big fronts (consumed by pipsgpu_ctx_commit)
-    double group_frac_used = 0.0;
     bool analyzed = false;
     double knorm = 1.0;
     // placement in the context pools (valid after commit)
@@ -110,7 +109,7 @@ struct pipsgpu_leaf {
     std::vector<int> level_begin, level_count;   // per global level: sub-range of level_fronts owned by this leaf
     std::vector<int> fl_begin, fl_count;         // per (global level, small|big): sub-range of fl_fronts owned by this leaf
     std::vector<int64_t> tile_begin, tile_count; // per global level: sub-range of the update tiles of this leaf's big fronts
-    int64_t gtile_begin = 0, gtile_count = 0;    // sub-range of the border-group tiles of this leaf
+    std::vector<int64_t> gtile_begin, gtile_count;   // per global level: sub-range of the group tiles whose group root sits on that level
     int chunk_begin = 0, chunk_count = 0;        // sub-range of the by-leaf chunk list (solve-pool pack of this leaf only)
     int batch = 0;                               // factorisation batch of this leaf
     double reg[3] = {0.0, 0.0, 0.0};             // this leaf's own (regP, regDy, regDz), added to every diagonal refresh
@@ -137,9 +136,17 @@ struct pipsgpu_sc {
     DevBuf<int> stats, perm, tflags;
     int ts_epoch = 0;        // epoch of the data-flow flags of dense_trisolve_kernel
     int* h_stats = nullptr;  // pinned: inertia / perturbation counters of the last static factorisation
-    ~pipsgpu_sc() { if (h_stats) cudaFreeHost(h_stats); }
+    ~pipsgpu_sc();
     DevBuf<int8_t> ptype;
     DevBuf<BkState> bk;
+    // sparse mode (pipsgpu_sc_set_sparse_pattern; sLinsysRootAug with hasSparseKkt): the root matrix restricted to a
+    // precomputed lower CSR pattern is factorised by the sparse multifrontal LDL^T in a private context on the same stream
+    pipsgpu_ctx* sp_ctx = nullptr;
+    pipsgpu_leaf* sp_leaf = nullptr;
+    DevBuf<int64_t> sp_idx;    // per pattern entry: its position in the dense assembly buffer A
+    DevBuf<double> sp_tmp;
+    int64_t sp_nnz = 0;
+    bool used_sparse = false;  // last factorisation went through the sparse solver
     bool factorized = false;
     bool used_bk = false;      // last factorisation needed the Bunch-Kaufman path
     int inertia[3] = {0, 0, 0};
@@ -161,23 +168,27 @@ struct pipsgpu_ctx {
     // the X = L11^-1 scratch are sized for the largest batch and reused (C alone would be 160 GB for the 512 blocks of C3);
     // the factor panels L and the solve pool stay resident for every leaf. batch_ptr[b] .. batch_ptr[b+1] = leaves of batch b.
     std::vector<int> batch_ptr;
-    std::vector<cudaEvent_t> ev_grp;    // per batch: events bracketing its border-group (Schur-term) kernel on its own stream
-    bool grp_timed = false;
+    // Group (Schur-term) SYRKs: one launch per (batch, tree level) = the groups whose root front sits on that level, issued on
+    // stream_grp as soon as the level is done. ev_gt brackets every launch (2 events per (batch, level), gt_rec = recorded in
+    // the current factorisation), ev_grp_done[b] marks the end of batch b's launches.
+    std::vector<cudaEvent_t> ev_gt, ev_grp_done;
+    std::vector<char> gt_rec;
+    std::vector<char> grp_pending;      // per batch: group kernels run on stream_grp and have not been joined yet
+    cudaEvent_t ev_lvl = nullptr;
     std::vector<int> level_ptr;     // nlevels*NCLS+1 into level_fronts; group g = level_order*NCLS + width class, deepest level first
     std::vector<int64_t> tile_ptr;  // nlevels+1 into tiles
     DevBuf<TileDesc> tiles;
     // deferred border x border updates (kernels.cuh: GroupDesc)
     DevBuf<GroupDesc> groups;
     DevBuf<GroupMember> gmembers;
-    DevBuf<GroupMap> gmap;          // row maps of the group members (kernels.cuh: GroupMap)
-    DevBuf<STile> stiles;           // output tiles of the group SYRKs (schur_syrk_kernel), grouped by leaf
-    DevBuf<int> sitems;             // their pipeline stages
+    DevBuf<int> ginv;
+    DevBuf<int8_t> gflags;
+    bool group_by_level = true;     // PIPSGPU_GROUP_BY_LEVEL=0: all group tiles of a batch in one launch after its last level
     int bp_threads = 256;           // PIPSGPU_BP_THREADS=128: smaller CTAs for the big-front panels
+    DevBuf<GTile> gtiles;
     int64_t ngtiles = 0;
     bool grouping = true;           // PIPSGPU_GROUP=0: every big front flushes its own border x border update
-    // a front joins its parent's group if it has at least this share of the group root's border rows; < 0: chosen per leaf
-    // by the cost model of symbolic.cpp (border_groups_cost). PIPSGPU_GROUP_FRAC=<f> fixes it.
-    double group_frac = -1.0;
+    double group_frac = 0.5;        // a front joins its parent's group if it has at least this share of the root's border rows
     int big_u = BIG_U;              // PIPSGPU_BIG_U: fronts with at least this many off-diagonal rows take the CTA-parallel path
     // side stream: the small fronts of a level run next to the big-front panel / tile kernels of the same level, and the
     // border-group SYRKs next to pack_solve (PIPSGPU_OVERLAP=0 keeps everything on one stream)
@@ -186,7 +197,9 @@ struct pipsgpu_ctx {
     // two small matrix-vector products (no serial substitution chain); X scratch is then persistent per front
     bool xform = true;
     bool panel_staged = false;      // PIPSGPU_PANEL=staged
+    bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
     cudaStream_t stream2 = nullptr;
+    cudaStream_t stream_grp = nullptr;  // group (Schur-term) SYRKs of batch b run here next to the tree levels of batch b + 1
     cudaStream_t stream_hi = nullptr;   // high-priority side stream: look-ahead panels of the dense root LDL^T
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf<double> XY;
@@ -233,8 +246,8 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
-        a.groups = groups.p; a.gmembers = gmembers.p; a.gmap = gmap.p; a.panel_staged = panel_staged ? 1 : 0;
-        a.stiles = stiles.p; a.sitems = sitems.p; a.bp_threads = bp_threads;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
+        a.gt_ptr = nullptr; a.gt_list = nullptr; a.group_lists = 0; a.bp_threads = bp_threads;
         return a;
     }
     // one launch = out (=|-=) K^-1 in for every leaf of the context (original ordering on both sides)
@@ -310,7 +323,7 @@ void analyze_one(pipsgpu_leaf* lf) {
         for (int p = lf->krow[i]; p < lf->krow[i + 1]; ++p)
             if (lf->jcol[p] != i) kn = std::max(kn, std::fabs(lf->val[p]));
     lf->knorm = std::max(kn, 1.0);
-    lf->group_frac_used = build_border_groups_auto(lf->S, lf->ctx ? lf->ctx->big_u : BIG_U, lf->ctx ? lf->ctx->group_frac : -1.0, lf->G);
+    build_border_groups(lf->S, lf->ctx ? lf->ctx->big_u : BIG_U, lf->ctx ? lf->ctx->group_frac : 0.6, lf->G);
     lf->analyzed = true;
 }
 
@@ -343,7 +356,15 @@ void run_leaf_solve(pipsgpu_ctx* ctx, const SolveArgs& sa, int nrhs, pipsgpu_lea
 // All levels of the numeric factorisation (deepest first) of the leaves [lo, hi) - one batch, or a single leaf for the
 // plug-in entry points -, then their deferred border-group updates and their solve-pool pack. Fronts, tiles, group tiles
 // and pack chunks are all stored grouped by leaf inside a level, so a leaf range is a contiguous sub-range of every list.
-void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEvent_t e_pack0, cudaEvent_t e_pack1) {
+// the main stream waits for the group kernel of batch b (no-op if it ran on the main stream or was joined already)
+void join_group(pipsgpu_ctx* ctx, int b) {
+    if (b < 0 || b >= (int)ctx->grp_pending.size() || !ctx->grp_pending[(size_t)b]) return;
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_grp_done[(size_t)b], 0));
+    ctx->grp_pending[(size_t)b] = 0;
+}
+
+void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEvent_t e_pack0, cudaEvent_t e_pack1,
+                      bool defer_join = false) {
     if (lo >= hi) return;
     cudaStream_t s = ctx->stream;
     cudaStream_t s2 = ctx->overlap ? ctx->stream2 : nullptr;
@@ -351,6 +372,32 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
     const pipsgpu_leaf* first = ctx->leaves[(size_t)lo];
     const pipsgpu_leaf* last = ctx->leaves[(size_t)hi - 1];
     const bool all = lo == 0 && hi == (int)ctx->leaves.size();
+    // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement):
+    // read-only on the factor panels and on the batch's persistent W21 scratch. The groups whose root sits on level lv are
+    // complete once lv is done; they are launched on their own stream right then and run next to the upper levels of this
+    // batch, its solve-pool pack and - when the caller defers the join - the levels of the NEXT batch. The tree kernels are
+    // latency-bound and the group SYRK keeps the FP64 tensor pipe about a third busy, so the two overlap well.
+    const int b = first->batch;
+    cudaStream_t sg = (sc && ctx->overlap && ctx->stream_grp) ? ctx->stream_grp : s;
+    bool grp_any = false;
+    auto launch_groups = [&](int lv_lo, int lv_hi) {      // group tiles of the levels [lv_lo, lv_hi): contiguous per leaf range
+        if (!sc || ctx->ngtiles == 0) return;
+        for (int lv = lv_lo; lv < lv_hi; ++lv) {
+            const int64_t gb = first->gtile_begin[(size_t)lv];
+            const int64_t gc = last->gtile_begin[(size_t)lv] + last->gtile_count[(size_t)lv] - gb;
+            if (gc <= 0) continue;
+            if (sg != s) {
+                CUDA_CHECK(cudaEventRecord(ctx->ev_lvl, s));
+                CUDA_CHECK(cudaStreamWaitEvent(sg, ctx->ev_lvl, 0));
+            }
+            const size_t e = ((size_t)b * ctx->nlevels + lv) * 2;
+            CUDA_CHECK(cudaEventRecord(ctx->ev_gt[e], sg));
+            launch_border_groups(fa, gb, gc, sg);
+            CUDA_CHECK(cudaEventRecord(ctx->ev_gt[e + 1], sg));
+            ctx->gt_rec[e / 2] = 1;
+            grp_any = true;
+        }
+    };
     for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
         if (all) {
             const int begin = ctx->level_ptr[lv * NCLS];
@@ -384,30 +431,17 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
             CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
             CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
         }
+        if (ctx->group_by_level) launch_groups(lv, lv + 1);
     }
-    // border x border updates of the grouped big fronts (they feed nothing inside the tree, only the Schur complement):
-    // read-only on the factor panels, like the pack kernel next to which they run
-    const int64_t gb = first->gtile_begin, gc = last->gtile_begin + last->gtile_count - gb;
-    const bool fork = s2 && sc && gc > 0;
-    if (fork) {
-        CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
-        CUDA_CHECK(cudaStreamWaitEvent(s2, ctx->ev_fork, 0));
-    }
-    if (sc && gc > 0) {
-        cudaStream_t sg = fork ? s2 : s;
-        const int b = first->batch;
-        CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b], sg));
-        launch_schur_syrk(fa, gb, gc, sg);
-        CUDA_CHECK(cudaEventRecord(ctx->ev_grp[(size_t)2 * b + 1], sg));
-        ctx->grp_timed = true;
+    if (!ctx->group_by_level) launch_groups(0, ctx->nlevels);
+    if (grp_any) {
+        if (sg != s) CUDA_CHECK(cudaEventRecord(ctx->ev_grp_done[(size_t)b], sg));
+        ctx->grp_pending[(size_t)b] = (sg != s);
     }
     if (e_pack0) CUDA_CHECK(cudaEventRecord(e_pack0, s));
     ctx->pack_solve(first->chunk_begin, last->chunk_begin + last->chunk_count - first->chunk_begin);
     if (e_pack1) CUDA_CHECK(cudaEventRecord(e_pack1, s));
-    if (fork) {
-        CUDA_CHECK(cudaEventRecord(ctx->ev_join, s2));
-        CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    }
+    if (!defer_join) join_group(ctx, b);
 }
 
 // numeric factorisation of one leaf (plug-in entry points) or of every leaf of the context, batch by batch.
@@ -415,12 +449,17 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
 void run_factor_levels(pipsgpu_ctx* ctx, pipsgpu_sc* sc, pipsgpu_leaf* only, cudaEvent_t e_pack0 = nullptr,
                        cudaEvent_t e_pack1 = nullptr) {
     if (only) { run_factor_range(ctx, sc, only->index, only->index + 1, e_pack0, e_pack1); return; }
+    // The persistent W21 scratch of the grouped fronts is double-buffered by batch parity (pipsgpu_ctx_commit): the group
+    // kernel of batch b may still read it while batch b + 1 factorises; batch b + 2 reuses it and waits for that kernel.
     const int nb = (int)ctx->batch_ptr.size() - 1;
     for (int b = 0; b < nb; ++b) {
         const bool lastb = b + 1 == nb;
+        join_group(ctx, b - 2);
         run_factor_range(ctx, sc, ctx->batch_ptr[(size_t)b], ctx->batch_ptr[(size_t)b + 1], lastb ? e_pack0 : nullptr,
-                         lastb ? e_pack1 : nullptr);
+                         lastb ? e_pack1 : nullptr, true);
     }
+    join_group(ctx, nb - 2);
+    join_group(ctx, nb - 1);
 }
 
 }  // namespace
@@ -436,6 +475,10 @@ void pipsgpu_ctx::psolve_by_level(const double* in, double* out, int out_mode) {
         launch_scatter_perm(gidx.p, x.p, work.p, npos, 1, npos, stream);
         launch_axpy(-1.0, work.p, out, npos, stream);
     }
+}
+
+extern "C" {
+static void factor_prepare(pipsgpu_ctx* ctx, pipsgpu_leaf* only);      // defined with the leaf entry points below
 }
 
 namespace {
@@ -539,8 +582,34 @@ void sc_factorize_bk(pipsgpu_sc* sc) {
 
 // factorize: fast static path first; if a pivot had to be perturbed or the inertia is not (n0, n-n0, 0) the matrix is
 // not quasi-definite in this order -> redo with Bunch-Kaufman. Leaves sc->inertia / n_perturbed up to date.
+// sparse root: gather the pattern values from the assembly buffer into the private context's CSR values and run the
+// multifrontal LDL^T used for the leaves (static 1x1 / 2x2 pivots: x0 rows positive, y0 rows paired with x0 columns, link
+// rows negative). Returns false (caller falls back to the dense solver, which can pivot) if a pivot had to be perturbed or
+// the inertia is not (n0, n - n0, 0).
+bool sc_factorize_sparse(pipsgpu_sc* sc) {
+    pipsgpu_ctx* sp = sc->sp_ctx;
+    cudaStream_t s = sp->stream;
+    launch_gather_idx(sc->A.p, sc->sp_idx.p, sc->sp_nnz, sp->Kval.p, s);
+    launch_absmax_eps(sp->Kval.p, sc->sp_nnz, 1e-12, &sp->leafdev.p->eps, s);
+    factor_prepare(sp, nullptr);
+    run_factor_levels(sp, nullptr, nullptr);
+    fetch_leaf_stats(sp);
+    pipsgpu_leaf* lf = sc->sp_leaf;
+    lf->factorized = true;
+    sc->inertia[0] = lf->inertia[0]; sc->inertia[1] = lf->inertia[1]; sc->inertia[2] = lf->inertia[2];
+    sc->n_perturbed = lf->n_perturbed;
+    return lf->n_perturbed == 0 && lf->inertia[0] == sc->n0 && lf->inertia[2] == 0;
+}
+
 void sc_factorize_impl(pipsgpu_sc* sc) {
     pipsgpu_ctx* ctx = sc->ctx;
+    sc->used_sparse = false;
+    if (sc->sp_ctx && sc_factorize_sparse(sc)) {
+        sc->used_sparse = true;
+        sc->used_bk = false;
+        sc->factorized = true;
+        return;
+    }
     sc_factorize_static(sc);
     int* h = sc->h_stats;
     CUDA_CHECK(cudaMemcpyAsync(h, sc->stats.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -563,6 +632,15 @@ void sc_factorize_impl(pipsgpu_sc* sc) {
 void sc_solve_device(pipsgpu_sc* sc, double* x, int nrhs, int64_t xstride) {
     pipsgpu_ctx* ctx = sc->ctx;
     cudaStream_t s = ctx->stream;
+    if (sc->used_sparse) {
+        sc->sp_tmp.ensure((size_t)sc->n + 1);
+        for (int r = 0; r < nrhs; ++r) {
+            double* xr = x + (size_t)r * xstride;
+            sc->sp_ctx->psolve(xr, sc->sp_tmp.p, 0);
+            CUDA_CHECK(cudaMemcpyAsync(xr, sc->sp_tmp.p, sizeof(double) * (size_t)sc->n, cudaMemcpyDeviceToDevice, s));
+        }
+        return;
+    }
     if (sc->used_bk) {
         launch_dense_solve(sc->Fm.p, (int)sc->ldf, sc->n, sc->perm.p, sc->ptype.p, sc->Dinv.p, sc->Dinv_e.p, x, nrhs, xstride,
                            sc->swork.p, s);
@@ -583,6 +661,16 @@ void sc_solve_device(pipsgpu_sc* sc, double* x, int nrhs, int64_t xstride) {
 void sc_allreduce_impl(pipsgpu_sc* sc) {
     pipsgpu_ctx* ctx = sc->ctx;
     if (!ctx->comm || ctx->nranks <= 1) return;
+    if (sc->sp_ctx) {
+        // reduceKKTsparse (LS/DistributedRootLinearSystem.C:885-925): only the pattern values travel
+        sc->pack.ensure((size_t)sc->sp_nnz);
+        launch_gather_idx(sc->A.p, sc->sp_idx.p, sc->sp_nnz, sc->pack.p, ctx->stream);
+        NcclApi& api = NcclApi::get();
+        const int rc = api.AllReduce(sc->pack.p, sc->pack.p, (size_t)sc->sp_nnz, kNcclFloat64, kNcclSum, ctx->comm, ctx->stream);
+        if (rc != 0) throw Error(PIPSGPU_ERR_NCCL, std::string("ncclAllReduce(sparse SC): ") + api.GetErrorString(rc));
+        launch_scatter_idx(sc->A.p, sc->sp_idx.p, sc->sp_nnz, sc->pack.p, ctx->stream);
+        return;
+    }
     const int nl = sc->myl + sc->mzl;
     const int64_t cnt = sc_pack_size(sc->n0, nl);
     sc->pack.ensure((size_t)cnt);
@@ -623,13 +711,16 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_REFINE_ALWAYS")) ctx->refine_always = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_REFINE_KKT")) ctx->refine_kkt = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_GROUP")) ctx->grouping = std::string(e) != "0";
-    if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::atof(e));      // negative: automatic
+    if (const char* e = std::getenv("PIPSGPU_GROUP_FRAC")) ctx->group_frac = std::min(1.0, std::max(0.05, std::atof(e)));
     if (const char* e = std::getenv("PIPSGPU_BIG_U")) ctx->big_u = std::min(1 << 20, std::max(32, std::atoi(e)));
     if (const char* e = std::getenv("PIPSGPU_OVERLAP")) ctx->overlap = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_XFORM")) ctx->xform = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_PANEL")) ctx->panel_staged = std::string(e) == "staged";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_PIPE")) ctx->group_pipe = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_BY_LEVEL")) ctx->group_by_level = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_BP_THREADS")) ctx->bp_threads = (std::atoi(e) == 128) ? 128 : 256;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream_grp, cudaStreamNonBlocking));
     {
         int lo_prio = 0, hi_prio = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
@@ -651,8 +742,11 @@ int pipsgpu_ctx_destroy(pipsgpu_ctx* ctx) {
     if (ctx->h_dvals) cudaFreeHost(ctx->h_dvals);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+    if (ctx->stream_grp) { cudaStreamSynchronize(ctx->stream_grp); cudaStreamDestroy(ctx->stream_grp); }
     if (ctx->stream_hi) { cudaStreamSynchronize(ctx->stream_hi); cudaStreamDestroy(ctx->stream_hi); }
-    for (auto& e : ctx->ev_grp) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_gt) cudaEventDestroy(e);
+    for (auto& e : ctx->ev_grp_done) cudaEventDestroy(e);
+    if (ctx->ev_lvl) cudaEventDestroy(ctx->ev_lvl);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
@@ -878,6 +972,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     double batch_gb = 16.0;
     if (const char* e = std::getenv("PIPSGPU_BATCH_GB")) batch_gb = std::max(0.001, std::atof(e));
     const int64_t c_cap = (int64_t)(batch_gb * 1e9 / 8.0);
+    // ... and at least PIPSGPU_MIN_BATCHES batches when there are enough leaves (default 1: measured on C2 / C3 / C4, every
+    // additional batch costs more in under-filled top-of-tree launches than the overlap of its group SYRKs with the next
+    // batch's tree levels gains - profiles/README.md, round 2 session 8)
+    int min_batches = 1;
+    if (const char* e = std::getenv("PIPSGPU_MIN_BATCHES")) min_batches = std::max(1, std::atoi(e));
+    const int leaf_cap = (nl >= 2 * min_batches) ? (nl + min_batches - 1) / min_batches : std::max(nl, 1);
+    int leaves_in_batch = 0;
     int64_t cfill = 0;
     ctx->batch_ptr.assign(1, 0);
     std::vector<char> batch_start((size_t)nl + 1, 0);
@@ -886,11 +987,13 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         lf->pos_off = (int)npos; lf->front_base = (int)nfr;
         lf->Lbase = Ltot; lf->Lsize = S.Loff.empty() ? 0 : S.Loff.back();
         lf->Csize = S.Coff.empty() ? 0 : S.Coff.back();
-        if (cfill > 0 && cfill + lf->Csize > c_cap) {
+        if (cfill > 0 && (cfill + lf->Csize > c_cap || leaves_in_batch >= leaf_cap)) {
             ctx->batch_ptr.push_back(lf->index);
             batch_start[(size_t)lf->index] = 1;
             cfill = 0;
+            leaves_in_batch = 0;
         }
+        ++leaves_in_batch;
         lf->batch = (int)ctx->batch_ptr.size() - 1;
         lf->Cbase = cfill;
         cfill += lf->Csize;
@@ -906,8 +1009,10 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
         if (npos > 2000000000LL) throw Error(PIPSGPU_ERR_INVALID, "too many KKT rows for one context (int32 positions)");
     }
     ctx->batch_ptr.push_back(nl);
-    ctx->ev_grp.resize(2 * (ctx->batch_ptr.size() - 1));
-    for (auto& e : ctx->ev_grp) CUDA_CHECK(cudaEventCreate(&e));
+    ctx->grp_pending.assign(ctx->batch_ptr.size() - 1, 0);
+    ctx->ev_grp_done.resize(ctx->batch_ptr.size() - 1);
+    for (auto& e : ctx->ev_grp_done) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!ctx->ev_lvl) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_lvl, cudaEventDisableTiming));
     ctx->npos = npos; ctx->nfronts = nfr; ctx->Ltot = Ltot; ctx->Ctot = Ctot; ctx->updtot = updtot;
     ctx->nnzK = nnzK; ctx->nnzB = nnzB; ctx->nlevels = nlev;
 
@@ -1074,14 +1179,29 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     // (grouping per leaf: build_border_groups in symbolic.cpp, run with the symbolic analysis on the host threads)
     std::vector<GroupDesc> groups;
     std::vector<GroupMember> gmembers;
-    std::vector<GroupMap> gmap;
-    std::vector<STile> stiles;
-    std::vector<int> sitems;
+    std::vector<int> ginv;
+    std::vector<int8_t> gflags;
+    std::vector<GTile> gtiles;
+    std::vector<std::vector<GTile>> lev_gtiles((size_t)nlev);      // group tiles by level of the group root, by leaf inside a level
+    for (auto* lf : ctx->leaves) { lf->gtile_begin.assign((size_t)nlev, 0); lf->gtile_count.assign((size_t)nlev, 0); }
     std::vector<char> grouped((size_t)nfr, 0);
     if (ctx->grouping) {
-        int64_t gw_run = 0, gw_max = 0;      // persistent (per batch) W21 scratch of the grouped fronts, behind the per-level area
+        // persistent (per batch) W21 scratch of the grouped fronts, behind the per-level area; two copies, used by even / odd
+        // batches: the group kernel of a batch still reads its copy while the next batch factorises (run_factor_levels)
+        int64_t gw_run = 0, gw_max = 0;
         for (auto* lf : ctx->leaves) {
             if (batch_start[(size_t)lf->index]) { gw_max = std::max(gw_max, gw_run); gw_run = 0; }
+            for (int s2 = 0; s2 < lf->S.ns; ++s2) {
+                if (!lf->G.grouped[(size_t)s2]) continue;
+                const FrontDesc& fd = fronts[(size_t)lf->front_base + s2];
+                gw_run += ((int64_t)(fd.na + fd.nb) * padded_width(fd.w) + 1) & ~int64_t(1);
+            }
+        }
+        gw_max = std::max(gw_max, gw_run);
+        gw_run = 0;
+        for (auto* lf : ctx->leaves) {
+            if (batch_start[(size_t)lf->index]) gw_run = 0;
+            const int64_t gw_base = wlev_max + (int64_t)(lf->batch & 1) * gw_max;
             const BorderGroups& G = lf->G;
             const int ng = (int)G.root.size();
             for (int s2 = 0; s2 < lf->S.ns; ++s2) grouped[(size_t)lf->front_base + s2] = G.grouped[(size_t)s2];
@@ -1091,14 +1211,11 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
                 return G.mem_ptr[(size_t)x + 1] - G.mem_ptr[(size_t)x] > G.mem_ptr[(size_t)y + 1] - G.mem_ptr[(size_t)y];
             });
-            lf->gtile_begin = (int64_t)stiles.size();
-            std::vector<int8_t> gflags;      // [member][64-row block of the root's border index space]: has rows there
             for (int oi : order) {
                 GroupDesc gd;
-                gd.N = G.N[(size_t)oi]; gd.nblk = ((gd.N + SY_TM - 1) / SY_TM) * (SY_TM / GROUP_TILE);
+                gd.N = G.N[(size_t)oi]; gd.nblk = (gd.N + GROUP_TILE - 1) / GROUP_TILE;
                 gd.root = lf->front_base + G.root[(size_t)oi]; gd.pad = 0;
-                gd.mem_begin = (int)gmembers.size(); gd.map_base = (int64_t)gmap.size();
-                gflags.clear();
+                gd.mem_begin = (int)gmembers.size(); gd.inv_base = (int64_t)ginv.size();
                 for (int q = G.mem_ptr[(size_t)oi]; q < G.mem_ptr[(size_t)oi + 1]; ++q) {
                     const int f = lf->front_base + G.mem_front[(size_t)q];
                     const FrontDesc& fd = fronts[(size_t)f];
@@ -1106,59 +1223,44 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                     // the member's W21 = L21 D scratch moves from the per-level area to a persistent one: the group SYRK
                     // runs after the last level and reads (L_B D) from there instead of rebuilding it from L and D
                     FrontDesc& fdm = fronts[(size_t)f];
-                    fdm.Woff = wlev_max + gw_run;
+                    fdm.Woff = gw_base + gw_run;
                     const int64_t wsz = (int64_t)(fd.na + fd.nb) * padded_width(fd.w);
                     gw_run += (wsz + 1) & ~int64_t(1);
                     mb.Lb_off = fd.Loff + fd.w + fd.na; mb.Wb_off = fdm.Woff + fd.na;
                     mb.m = fd.w + fd.na + fd.nb; mb.u = fd.na + fd.nb; mb.w = fd.w; mb.col0 = fd.col0; mb.front = f; mb.pad = 0;
                     gmembers.push_back(mb);
-                    const size_t base = gmap.size();
-                    gmap.resize(base + (size_t)gd.nblk, GroupMap{0u, 0u, 0, 0u});
+                    const size_t base = ginv.size();
+                    ginv.resize(base + (size_t)gd.nblk * GROUP_TILE, -1);
                     const int* pf = G.pos.data() + G.pos_ptr[(size_t)q];
                     if (G.pos_ptr[(size_t)q + 1] - G.pos_ptr[(size_t)q] != fd.nb) throw Error(PIPSGPU_ERR_INVALID, "border group: position map size mismatch");
-                    const size_t fbase = gflags.size();
-                    gflags.resize(fbase + (size_t)gd.nblk, 0);
-                    for (int t = 0; t < fd.nb; ++t) {
-                        const int p = pf[t], b = p / GROUP_TILE, r = p % GROUP_TILE;
-                        GroupMap& gm = gmap[base + (size_t)b];
-                        if (r < 32) gm.bits_lo |= 1u << r; else gm.bits_hi |= 1u << (r - 32);
-                        gm.slices |= 1u << (r >> 3);
-                        gflags[fbase + (size_t)b] = 1;
-                    }
-                    int run = 0;      // member rows are ascending in the root's index space: start = rows before the block
-                    for (int b = 0; b < gd.nblk; ++b) {
-                        GroupMap& gm = gmap[base + (size_t)b];
-                        gm.start = run;
-                        run += __builtin_popcount(gm.bits_lo) + __builtin_popcount(gm.bits_hi);
-                    }
+                    for (int t = 0; t < fd.nb; ++t) ginv[base + (size_t)pf[t]] = t;
+                    gflags.resize(base / GROUP_TILE + (size_t)gd.nblk, 0);
+                    for (int t = 0; t < fd.nb; ++t) gflags[base / GROUP_TILE + (size_t)pf[t] / GROUP_TILE] = 1;
                 }
                 gd.mem_end = (int)gmembers.size();
                 const int gi = (int)groups.size();
                 groups.push_back(gd);
-                const int nmem_g = gd.mem_end - gd.mem_begin;
-                // output tiles (rows 128 bi .., columns 64 bj .., lower part) with their pipeline stages: every member that has
-                // rows in both ranges contributes its columns 0..15 and, if wider than 16, 16..31
-                const int nbi = gd.nblk / (SY_TM / GROUP_TILE), nbj = (gd.N + SY_TN - 1) / SY_TN;
-                for (int bi = 0; bi < nbi; ++bi)
-                    for (int bj = 0; bj < nbj && bj * SY_TN <= bi * SY_TM + SY_TM - 1; ++bj) {
-                        STile t;
-                        t.item_begin = (int64_t)sitems.size(); t.group = gi; t.bi = bi; t.bj = bj;
-                        for (int q = 0; q < nmem_g; ++q) {
-                            const int8_t* fl = gflags.data() + (size_t)q * gd.nblk;
-                            if (!((fl[2 * bi] || fl[2 * bi + 1]) && fl[bj])) continue;
-                            sitems.push_back(q << 1);
-                            if (gmembers[(size_t)gd.mem_begin + q].w > SY_KS) sitems.push_back((q << 1) | 1);
-                        }
-                        t.item_count = (int)((int64_t)sitems.size() - t.item_begin);
-                        if (t.item_count > 0) stiles.push_back(t);
-                    }
+                const int ol = nlev - 1 - lf->S.sn_level[(size_t)G.root[(size_t)oi]];      // level order of the group root
+                for (int bi = 0; bi < gd.nblk; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) lev_gtiles[(size_t)ol].push_back(GTile{gi, bi, bj, 0});
+                lf->gtile_count[(size_t)ol] += (int64_t)gd.nblk * (gd.nblk + 1) / 2;
             }
-            lf->gtile_count = (int64_t)stiles.size() - lf->gtile_begin;
             lf->G = BorderGroups();
         }
-        ctx->Wtot = wlev_max + std::max(gw_max, gw_run);
+        ctx->Wtot = wlev_max + 2 * gw_max;
+        int64_t run = 0;
+        for (int l = 0; l < nlev; ++l) {
+            for (auto* lf : ctx->leaves) { lf->gtile_begin[(size_t)l] = run; run += lf->gtile_count[(size_t)l]; }
+            gtiles.insert(gtiles.end(), lev_gtiles[(size_t)l].begin(), lev_gtiles[(size_t)l].end());
+            if ((int64_t)gtiles.size() != run) throw Error(PIPSGPU_ERR_INVALID, "group tile count mismatch");
+            std::vector<GTile>().swap(lev_gtiles[(size_t)l]);
+        }
     }
-    ctx->ngtiles = (int64_t)stiles.size();
+    ctx->ngtiles = (int64_t)gtiles.size();
+    for (auto& e : ctx->ev_gt) cudaEventDestroy(e);
+    ctx->ev_gt.resize((size_t)2 * (ctx->batch_ptr.size() - 1) * nlev);
+    for (auto& e : ctx->ev_gt) CUDA_CHECK(cudaEventCreate(&e));
+    ctx->gt_rec.assign(ctx->ev_gt.size() / 2, 0);
     // ---- update tiles of the big fronts, grouped by (level, leaf); grouped fronts only keep the ancestor columns ----
     std::vector<TileDesc> tiles;
     {
@@ -1212,8 +1314,7 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
     ctx->bg_row.upload(bg_row, s); ctx->bg_sc.upload(bg_sc, s); ctx->bg_b0.upload(bg_b0, s);
     ctx->leafdev.upload(leafdev, s);
     ctx->tiles.upload(tiles, s);
-    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->gmap.upload(gmap, s);
-    ctx->stiles.upload(stiles, s); ctx->sitems.upload(sitems, s);
+    ctx->groups.upload(groups, s); ctx->gmembers.upload(gmembers, s); ctx->ginv.upload(ginv, s); ctx->gflags.upload(gflags, s); ctx->gtiles.upload(gtiles, s);
     ctx->fl_fronts.upload(fl_fronts, s);
     ctx->L.alloc((size_t)Ltot + 2); ctx->C.alloc((size_t)Ctot + 2); ctx->W.alloc((size_t)ctx->Wtot + 2); ctx->XY.alloc((size_t)ctx->XYtot + 2);
     ctx->Dd.alloc((size_t)npos + 1); ctx->De.alloc((size_t)npos + 1); ctx->Did.alloc((size_t)npos + 1);
@@ -1609,6 +1710,50 @@ int pipsgpu_sc_create(pipsgpu_ctx* ctx, int n0, int my0, int myl, int mzl, pipsg
     PIPSGPU_CATCH
 }
 
+pipsgpu_sc::~pipsgpu_sc() {
+    if (h_stats) cudaFreeHost(h_stats);
+    if (sp_leaf) pipsgpu_leaf_destroy(sp_leaf);
+    if (sp_ctx) pipsgpu_ctx_destroy(sp_ctx);
+}
+
+int pipsgpu_sc_set_sparse_pattern(pipsgpu_sc* sc, const int* krow, const int* jcol, int threads) {
+    PIPSGPU_TRY
+    if (!sc || !krow || !jcol) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_set_sparse_pattern: null argument");
+    if (sc->sp_ctx) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_sc_set_sparse_pattern: pattern already set");
+    pipsgpu_ctx* ctx = sc->ctx;
+    require_device(ctx);
+    const int n = sc->n;
+    const int64_t nnz = krow[n];
+    std::vector<int64_t> idx((size_t)nnz);
+    std::vector<double> ones((size_t)nnz, 1.0);
+    for (int i = 0; i < n; ++i)
+        for (int p = krow[i]; p < krow[i + 1]; ++p) {
+            if (jcol[p] < 0 || jcol[p] > i) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_set_sparse_pattern: pattern must be lower triangular CSR");
+            idx[(size_t)p] = (int64_t)i * n + jcol[p];
+            // symbolic analysis only sees magnitudes (2x2 pivot matching prefers heavy edges): expected sign on the diagonal
+            if (jcol[p] == i) ones[(size_t)p] = (i < sc->n0) ? 1.0 : ((i < sc->n0 + sc->my0) ? 0.0 : -1.0);
+        }
+    pipsgpu_ctx* sp = nullptr;
+    int rc = pipsgpu_ctx_create(ctx->device, &sp);
+    if (rc != 0) return rc;
+    sc->sp_ctx = sp;
+    rc = pipsgpu_ctx_set_stream(sp, (void*)ctx->stream);
+    if (rc != 0) return rc;
+    // SC index order [x0; y0; yl; zl] = leaf order [x; y; z]: x0 rows are positive pivots, y0 rows (zero diagonal) are
+    // paired with x0 columns, the link rows carry the negative (semi)definite block
+    rc = pipsgpu_leaf_create(sp, n, sc->n0, sc->my0, sc->myl + sc->mzl, krow, jcol, ones.data(), &sc->sp_leaf);
+    if (rc != 0) return rc;
+    rc = pipsgpu_ctx_commit(sp, threads);
+    if (rc != 0) return rc;
+    sc->sp_nnz = nnz;
+    sc->sp_idx.upload(idx, ctx->stream);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    sc->factorized = false;
+    PIPSGPU_CATCH
+}
+
+int pipsgpu_sc_uses_sparse_solver(pipsgpu_sc* sc) { return (sc && sc->used_sparse) ? 1 : 0; }
+
 int pipsgpu_sc_destroy(pipsgpu_sc* sc) {
     PIPSGPU_TRY
     if (sc) {
@@ -1838,11 +1983,12 @@ static void kkt_factorize_device(pipsgpu_kkt* k, double regDy, int inertia_root[
     CUDA_CHECK(cudaEventElapsedTime(&ms, k->ev[12], k->ev[13]));
     k->ktimes[1] = ms;
     k->ktimes[3] = 0.0;
-    if (ctx->grp_timed)
-        for (size_t b = 0; b + 1 < ctx->ev_grp.size(); b += 2) {
-            if (cudaEventElapsedTime(&ms, ctx->ev_grp[b], ctx->ev_grp[b + 1]) == cudaSuccess) k->ktimes[3] += ms;
-            else (void)cudaGetLastError();
-        }
+    for (size_t e = 0; e < ctx->gt_rec.size(); ++e) {      // group launches are serialised on their stream: sum of kernel times
+        if (!ctx->gt_rec[e]) continue;
+        if (cudaEventElapsedTime(&ms, ctx->ev_gt[2 * e], ctx->ev_gt[2 * e + 1]) == cudaSuccess) k->ktimes[3] += ms;
+        else (void)cudaGetLastError();
+        ctx->gt_rec[e] = 0;
+    }
 }
 
 int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomegainv0, const double* nomegainv_link,

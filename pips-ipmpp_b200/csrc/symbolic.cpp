@@ -529,59 +529,4 @@ void build_border_groups(const LeafSymbolic& S, int big_u, double frac, BorderGr
     }
 }
 
-GroupCost border_groups_cost(const LeafSymbolic& S, const BorderGroups& G) {
-    GroupCost c;
-    const int TM = 128, TN = 64;
-    std::vector<int> sa, sb, pre;
-    std::vector<char> tile_used;
-    for (size_t g = 0; g < G.root.size(); ++g) {
-        const int N = G.N[g];
-        const int nbi = (N + TM - 1) / TM, nbj = (N + TN - 1) / TN;
-        c.flush += 0.5 * (double)N * (N + 1);
-        tile_used.assign((size_t)nbi * nbj, 0);
-        for (int q = G.mem_ptr[g]; q < G.mem_ptr[g + 1]; ++q) {
-            const int f = G.mem_front[(size_t)q];
-            const int w = S.sn_col[f + 1] - S.sn_col[f];
-            const int w4 = (w + 3) & ~3;
-            const int nst = w > 16 ? 2 : 1;
-            const int* pf = G.pos.data() + G.pos_ptr[(size_t)q];
-            const int nb = (int)(G.pos_ptr[(size_t)q + 1] - G.pos_ptr[(size_t)q]);
-            // non-empty 8-row slices per row tile (128) and per column tile (64)
-            sa.assign((size_t)nbi, 0); sb.assign((size_t)nbj, 0);
-            int last = -1;
-            for (int t = 0; t < nb; ++t) {
-                const int sl = pf[t] >> 3;
-                if (sl == last) continue;
-                last = sl;
-                ++sa[(size_t)(sl >> 4)]; ++sb[(size_t)(sl >> 3)];
-            }
-            pre.assign((size_t)nbj + 1, 0);
-            for (int bj = 0; bj < nbj; ++bj) pre[(size_t)bj + 1] = pre[(size_t)bj] + sb[(size_t)bj];
-            for (int bi = 0; bi < nbi; ++bi) {
-                if (!sa[(size_t)bi]) continue;
-                const int jmax = std::min(nbj, 2 * bi + 2);
-                c.exec_flops += 2.0 * 64.0 * w4 * sa[(size_t)bi] * pre[(size_t)jmax];
-                for (int bj = 0; bj < jmax; ++bj)
-                    if (sb[(size_t)bj]) { c.stages += nst; tile_used[(size_t)bi * nbj + bj] = 1; }
-            }
-        }
-        for (char u : tile_used) c.tiles += u;
-    }
-    c.seconds = c.exec_flops / 30e12 + c.flush / 300e9 + c.tiles * 14e-9 + c.stages * 1.5e-9;
-    return c;
-}
-
-double build_border_groups_auto(const LeafSymbolic& S, int big_u, double frac, BorderGroups& out) {
-    if (frac >= 0.0) { build_border_groups(S, big_u, frac, out); return frac; }
-    const double ladder[] = {0.6, 0.45, 0.3, 0.2, 0.12, 0.06, 0.0};
-    double best = -1.0, best_cost = 0.0;
-    BorderGroups trial;
-    for (double f : ladder) {
-        build_border_groups(S, big_u, f, trial);
-        const double cost = border_groups_cost(S, trial).seconds;
-        if (best < 0.0 || cost < best_cost) { best = f; best_cost = cost; out = trial; }
-    }
-    return best;
-}
-
 }  // namespace pipsgpu

@@ -77,12 +77,4 @@ struct BorderGroups {
 };
 void build_border_groups(const LeafSymbolic& S, int big_u, double frac, BorderGroups& out);
 
-// Model of the time (seconds, one block alone on the whole GPU) schur_syrk_kernel needs for a grouping: tensor work that
-// survives the 8 x 8 sub-tile skipping, flush atomics, per-tile and per-stage overheads (constants fitted to B200
-// measurements, profiles/README.md round 2). Small frac = few big groups = few flushes but more zero fill.
-struct GroupCost { double exec_flops = 0, flush = 0, tiles = 0, stages = 0, seconds = 0; };
-GroupCost border_groups_cost(const LeafSymbolic& S, const BorderGroups& G);
-// frac < 0: try a ladder of fractions and keep the cheapest grouping under the model; returns the fraction used
-double build_border_groups_auto(const LeafSymbolic& S, int big_u, double frac, BorderGroups& out);
-
 }  // namespace pipsgpu

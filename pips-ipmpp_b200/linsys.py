@@ -77,10 +77,45 @@ def compressed_kkt_residual(lp, dd, nomegainv, rhs, sol, reg=None, reduce_root=N
     return leaf_sq, r0
 
 
+def sc_lower_pattern(lp):
+    """Structural lower-triangular CSR pattern (krow, jcol) of the root Schur complement in its index order
+    [x0; y0; yl; zl] - what the reference precomputes once for its sparse root KKT (LS/sLinsysRootAug.C:79-208, the
+    SparseSymmetricMatrix handed to finalizeKKTsparse, :1629-1767). Every block contributes the clique of the linking
+    variables / linking rows it touches (its term Bord_i^T K_i^-1 Bord_i), the root its own blocks. `lp` must hold ALL
+    blocks (every rank needs the same global pattern)."""
+    import scipy.sparse as sp
+    root = lp.root
+    n0, my0, myl, mzl = root.n, root.my, lp.myl, lp.mzl
+    n = n0 + my0 + myl + mzl
+    rows, cols = [np.arange(n)], [np.arange(n)]
+
+    def clique(idx):
+        idx = np.unique(idx)
+        if len(idx):
+            r, c = np.meshgrid(idx, idx, indexing="ij")
+            m = r >= c
+            rows.append(r[m]); cols.append(c[m])
+
+    for ch in lp.children:
+        touched = [ch.A.tocoo().col, ch.C.tocoo().col,
+                   n0 + my0 + np.unique(ch.F.tocoo().row), n0 + my0 + myl + np.unique(ch.G.tocoo().row)]
+        clique(np.concatenate(touched))
+    C0 = root.C.tocsr()
+    for r in range(root.mz):                      # - C0^T diag C0: columns sharing a row
+        clique(C0.indices[C0.indptr[r]:C0.indptr[r + 1]])
+    for M, off in ((root.A, n0), (root.F, n0 + my0), (root.G, n0 + my0 + myl)):
+        M = M.tocoo()
+        rows.append(off + M.row); cols.append(M.col)
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    P = sp.coo_matrix((np.ones(len(r)), (r, c)), shape=(n, n)).tocsr()
+    P.sum_duplicates(); P.sort_indices()
+    return P.indptr.astype(np.int32), P.indices.astype(np.int32)
+
+
 class CudaRootLinearSystem:
     """Root linear system of a two-level block-angular LP on one GPU (one rank of the reference)."""
 
-    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0, stream=None, kkts=None):
+    def __init__(self, lp, device=0, rank=0, n_ranks=1, nccl_uid=None, threads=0, stream=None, kkts=None, sc_pattern=None):
         self.lp = lp
         root = lp.root
         self.rank, self.n_ranks = rank, n_ranks
@@ -101,6 +136,8 @@ class CudaRootLinearSystem:
             self.kkt.add_leaf(leaf)
             self.leaves.append(leaf)
         self.kkt.setup(threads)
+        if sc_pattern is not None:          # sparse root KKT (sLinsysRootAug with hasSparseKkt): (krow, jcol) of sc_lower_pattern
+            self.kkt.sc().set_sparse_pattern(sc_pattern[0], sc_pattern[1], threads)
         self.nb0 = root.n + root.my + root.mz + lp.myl + lp.mzl
         self.sum_n = sum(ch.n + ch.my + ch.mz for ch in lp.children)
         self._b_leaves = np.zeros(max(self.sum_n, 1))

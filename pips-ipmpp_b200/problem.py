@@ -312,8 +312,10 @@ CONFIGS = {
     "T5": (4, 3000, 2000, 6000, 2000, 200, 200, 300, 200),
     "T6": (4, 1200, 800, 2400, 3000, 300, 300, 2000, 1000),
     "T7": (4, 1500, 1000, 3000, 500, 100, 100, 120, 80),
+    # many blocks over a mid-sized root: with localize_links() the Schur complement is block-banded (sparse root path)
+    "S1": (24, 300, 200, 600, 480, 20, 20, 120, 80),
 }
-CONFIG_ID = {"C2": 2, "C3": 3, "C4": 4, "C5": 5, "T1": 11, "T2": 12, "T3": 13, "T4": 14, "T5": 15, "T6": 16, "T7": 17}
+CONFIG_ID = {"C2": 2, "C3": 3, "C4": 4, "C5": 5, "T1": 11, "T2": 12, "T3": 13, "T4": 14, "T5": 15, "T6": 16, "T7": 17, "S1": 21}
 TECH_WINDOW = 48   # technology columns are drawn uniformly from the +-TECH_WINDOW columns around the row's time step
 
 
@@ -411,6 +413,49 @@ def synthetic(cfg: str = "T2", n_blocks: Optional[int] = None, block_range=None)
     return BlockAngularLP(root=root, children=children, myl=myl, mzl=mzl, bl=bl, dllow=np.zeros(mzl),
                           idllow=np.zeros(mzl), dlupp=dl, idlupp=np.ones(mzl), name=f"synthetic-{cfg}",
                           meta=dict(config=cfg, n_blocks_total=N, block_range=(lo, hi)))
+
+
+def localize_links(lp: BlockAngularLP, halo: float = 0.5) -> BlockAngularLP:
+    """Variant with LOCAL linking structure (the '2-links' situation the reference's sparse Schur complement exists for,
+    LS/sLinsysRootAug.C:79-208): block g of N only touches the linking variables / linking rows of its own 1/N-th of the
+    index range plus `halo` of a range on either side, so the root Schur complement becomes block-banded. Entries outside
+    the window are dropped from A_i, C_i (columns) and F_i, G_i (rows); right-hand sides are NOT regenerated - the result
+    is meant for linear-system level tests (factorize / solveCompressed on a given iterate), not for IPM runs."""
+    import copy
+    out = copy.copy(lp)
+    N = lp.meta.get("n_blocks_total", len(lp.children))
+    lo = lp.meta.get("block_range", (0, len(lp.children)))[0]
+    n0 = lp.root.n
+
+    def window(g, size):
+        w = size / max(N, 1)
+        return int(np.floor((g - halo) * w)), int(np.ceil((g + 1 + halo) * w))
+
+    def keep_cols(M, a, b):
+        M = M.tocoo()
+        ok = (M.col >= a) & (M.col < b)
+        return _csr(sp.coo_matrix((M.data[ok], (M.row[ok], M.col[ok])), shape=M.shape), M.shape)
+
+    def keep_rows(M, a, b):
+        M = M.tocoo()
+        ok = (M.row >= a) & (M.row < b)
+        return _csr(sp.coo_matrix((M.data[ok], (M.row[ok], M.col[ok])), shape=M.shape), M.shape)
+
+    kids = []
+    for i, ch in enumerate(lp.children):
+        g = lo + i
+        c = copy.copy(ch)
+        a, b = window(g, n0)
+        c.A, c.C = keep_cols(ch.A, a, b), keep_cols(ch.C, a, b)
+        a, b = window(g, lp.myl)
+        c.F = keep_rows(ch.F, a, b)
+        a, b = window(g, lp.mzl)
+        c.G = keep_rows(ch.G, a, b)
+        kids.append(c)
+    out.children = kids
+    out.name = lp.name + "-local-links"
+    out.meta = dict(lp.meta, local_links=halo)
+    return out
 
 
 def synthetic_iterate(lp: BlockAngularLP, cfg_id: int = 0):

@@ -365,3 +365,29 @@ def test_regularisation_loop_host_logic_against_oracle(pkg):
     assert fo.get_regularization_parameters() == (100.0, 100.0, 100.0)
     fo.notify_new_step()
     assert fo.get_default_regularization() == (10.0, 10.0, 10.0)
+
+
+def test_sparse_root_pattern_covers_the_oracle_schur_complement(pkg):
+    """sc_lower_pattern (what the reference precomputes for its sparse root KKT, LS/sLinsysRootAug.C:79-208) must contain
+    every structural nonzero of the Schur complement the oracle assembles, and be sparse on an LP with local links."""
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle.linsys import OracleRoot
+    P = pkg.problem
+    for lp in (P.localize_links(P.synthetic("S1"), halo=0.5), P.synthetic("T2"), P.c1_hier_4blocks()):
+        krow, jcol = pkg.linsys.sc_lower_pattern(lp)
+        n = len(krow) - 1
+        assert n == lp.root.n + lp.root.my + lp.myl + lp.mzl
+        pat = sp.csr_matrix((np.ones(krow[-1]), jcol, krow), shape=(n, n)).toarray() > 0
+        assert np.all(np.diag(pat)) and not np.any(np.triu(pat, 1))
+        rng = np.random.default_rng(0)
+        nodes = [lp.root] + lp.children
+        dd = [rng.uniform(0.5, 2.0, nd.n) for nd in nodes]
+        nom = [-rng.uniform(0.5, 2.0, nd.mz) for nd in nodes] + [-rng.uniform(0.5, 2.0, lp.mzl)]
+        ref = OracleRoot(lp)
+        ref.put_diagonals(dd, nom)
+        ref.factor2()
+        assert not np.any((np.tril(ref.SC) != 0) & ~pat)
+    krow, _ = pkg.linsys.sc_lower_pattern(P.localize_links(P.synthetic("S1"), halo=0.5))
+    n = len(krow) - 1
+    assert krow[-1] < 0.35 * n * (n + 1) / 2
