@@ -194,8 +194,14 @@ public:
         PIPSGPU_SHIM_CHECK(pipsgpu_leaf_solve(leaf_, nrhss, rhss));
     }
 
+    // inertia of the COMPUTED pivots (a wrong-signed / vanishing pivot shows up here even though the factorisation went on
+    // with a perturbed one): LinearSystem::factorize_with_correct_inertia (LS/LinearSystem.C:296-325) can react to it
     [[nodiscard]] bool reports_inertia() const override { return true; }
     [[nodiscard]] std::tuple<unsigned int, unsigned int, unsigned int> get_inertia() const override { return inertia_; }
+    // this node's own regularisation for the batched system-level factorisation (RegularizationStrategy per node)
+    void set_regularization(double regP, double regDy, double regDz) {
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_set_regularization(leaf_, regP, regDy, regDz));
+    }
 
     pipsgpu_leaf* handle() const { return leaf_; }
 
@@ -314,6 +320,19 @@ public:
     }
     // DistributedLinearSystem::solveCompressed (Lsolve; Dsolve; Ltsolve) in place
     void solveCompressed(double* b0, double* b_leaves) { PIPSGPU_SHIM_CHECK(pipsgpu_kkt_solve_compressed(kkt_, b0, b_leaves)); }
+    // LinearSystem::solveCompressedBiCGStab (LS/LinearSystem.C:550-798) on the device, preconditioned by solveCompressed, with
+    // the full-KKT matvec system_mult (:809-844): right-hand side down once, step back once. Returns the reference's
+    // IterativeSolverSolutionStatus code (LS/LinearSystem.h:45-47).
+    int solve(double* b0, double* b_leaves, double tol, int max_iter, int* n_iter = nullptr, double* rel_residual = nullptr) {
+        int status = 0;
+        PIPSGPU_SHIM_CHECK(pipsgpu_kkt_solve(kkt_, b0, b_leaves, tol, max_iter, &status, n_iter, rel_residual));
+        return status;
+    }
+    // sparse root KKT (sLinsysRootAug with hasSparseKkt): lower CSR pattern of the Schur complement, declared once
+    void set_sparse_pattern(const int* krow, const int* jcol, int threads = 0) {
+        PIPSGPU_SHIM_CHECK(pipsgpu_sc_set_sparse_pattern(pipsgpu_kkt_sc(kkt_), krow, jcol, threads));
+    }
+    pipsgpu_kkt* handle() const { return kkt_; }
     pipsgpu_sc* schur_complement() const { return pipsgpu_kkt_sc(kkt_); }
     int root_rhs_length() const { return nb0_; }
 

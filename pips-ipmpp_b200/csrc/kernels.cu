@@ -668,10 +668,10 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
         bv_[qq] = (k_ < (w_) && (tj_) >= 0) ? (Wb_)[(size_t)k_ * (u_) + (tj_)] : 0.0;         \
     }
 // PIPE (PIPSGPU_GROUP_PIPE=1): the first batch of the NEXT contributing member is loaded into registers before the MMA of
-// the current one, so the global round trip of the staging overlaps the tensor work and the barriers.
-// LISTS (PIPSGPU_GROUP_LISTS=1): the contributing members of the tile come from a host-built list instead of a scan of the
-// per-member block flags.
-template <bool PIPE, bool LISTS>
+// the current one, so the global round trip of the staging overlaps the tensor work and the barriers (measured equal).
+// (Host-built per-tile member lists instead of the flag scan were measured equal too and are gone; so are the
+// cp.async-pipelined 128 x 64 variants of round 2: profiles/README.md.)
+template <bool PIPE>
 __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
     __shared__ double As[MAXW * KLD];
     __shared__ double Bs[MAXW * KLD];
@@ -694,20 +694,17 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
     // Members without rows in both tile ranges are skipped without touching a barrier.
     const int8_t* flag_i = a.gflags + g.inv_base / GROUP_TILE + td.bi;
     const int8_t* flag_j = a.gflags + g.inv_base / GROUP_TILE + td.bj;
-    // cursor over the contributing members: an index into the tile's list (LISTS) or a member index (flag scan)
-    const int* list = LISTS ? a.gt_list + a.gt_ptr[gtile_begin + blockIdx.x] : nullptr;
-    const int nmem = LISTS ? (int)(a.gt_ptr[gtile_begin + blockIdx.x + 1] - a.gt_ptr[gtile_begin + blockIdx.x])
-                           : g.mem_end - g.mem_begin;
+    // cursor over the contributing members (flag scan)
+    const int nmem = g.mem_end - g.mem_begin;
     auto skip = [&](int c) {
-        if (!LISTS)
-            while (c < nmem && !(flag_i[(int64_t)c * g.nblk] && flag_j[(int64_t)c * g.nblk])) ++c;
+        while (c < nmem && !(flag_i[(int64_t)c * g.nblk] && flag_j[(int64_t)c * g.nblk])) ++c;
         return c;
     };
     int q = skip(0);
     GroupMember mb;
     int ti = -1, tj = -1;
     if (q < nmem) {
-        const int qm = LISTS ? list[q] : q;
+        const int qm = q;
         mb = a.gmembers[g.mem_begin + qm];
         ti = inv_i[(int64_t)qm * inv_stride];
         tj = inv_j[(int64_t)qm * inv_stride];
@@ -725,7 +722,7 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
         GroupMember nmb = mb;
         int nti = -1, ntj = -1;
         if (qn < nmem) {
-            const int qm = LISTS ? list[qn] : qn;
+            const int qm = qn;
             nmb = a.gmembers[g.mem_begin + qm];
             nti = inv_i[(int64_t)qm * inv_stride];
             ntj = inv_j[(int64_t)qm * inv_stride];
@@ -792,13 +789,8 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
 }
 void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
     if (ngtiles <= 0 || !a.SC) return;
-    if (a.group_lists) {
-        if (a.group_pipe) border_group_kernel<true, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-        else border_group_kernel<false, true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-    } else {
-        if (a.group_pipe) border_group_kernel<true, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-        else border_group_kernel<false, false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-    }
+    if (a.group_pipe) border_group_kernel<true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    else border_group_kernel<false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
     COUNT_LAUNCH();
 }
 

@@ -84,9 +84,6 @@ struct FactorArgs {
     const GroupDesc* groups;
     const GroupMember* gmembers;
     const int* ginv;
-    const int64_t* gt_ptr;       // per group tile: range of gt_list (group-local member indices with rows in both blocks)
-    const int* gt_list;
-    int group_lists;             // PIPSGPU_GROUP_LISTS=1: walk gt_list instead of scanning gflags
     int bp_threads;              // CTA size of big_panel_kernel (128 or 256)
     int group_pipe;              // PIPSGPU_GROUP_PIPE=1: software-pipelined member staging in border_group_kernel
     int panel_staged;            // PIPSGPU_PANEL=staged: panel chunks staged in shared memory (kernels.cu: panel_chunk_staged)

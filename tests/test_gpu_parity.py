@@ -249,6 +249,13 @@ def test_against_committed_golden_fixtures(pkg, name):
     gpu.close()
 
 
+def _two_gpu_lp(P, cfg, block_range=None):
+    """cfg 'S1-local' = S1 with local linking structure (sparse root Schur complement)"""
+    if cfg == "S1-local":
+        return P.localize_links(P.synthetic("S1", block_range=block_range), halo=0.5), "S1"
+    return P.synthetic(cfg, block_range=block_range), cfg
+
+
 def _two_gpu_worker(rank, world, port, cfg, q):
     import os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -264,12 +271,16 @@ def _two_gpu_worker(rank, world, port, cfg, q):
         P = pkg.problem
         obj = [pkg.capi.Context.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
-        nblocks = P.CONFIGS[cfg][0]
+        nblocks = P.CONFIGS["S1" if cfg == "S1-local" else cfg][0]
         lo, hi = pkg.capi.partition(nblocks, world)[rank]
-        lp = P.synthetic(cfg, block_range=(lo, hi))
-        dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
-        sys_ = pkg.linsys.CudaRootLinearSystem(lp, device=rank, rank=rank, n_ranks=world, nccl_uid=obj[0])
+        lp, base = _two_gpu_lp(P, cfg, (lo, hi))
+        dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[base])
+        pattern = None
+        if cfg == "S1-local":       # the pattern is global: every rank derives it from the whole problem structure
+            pattern = pkg.linsys.sc_lower_pattern(_two_gpu_lp(P, cfg)[0])
+        sys_ = pkg.linsys.CudaRootLinearSystem(lp, device=rank, rank=rank, n_ranks=world, nccl_uid=obj[0], sc_pattern=pattern)
         inertia = sys_.factorize(dd, nom)
+        sparse_used = sys_.kkt.sc().uses_sparse_solver()
         sc = sys_.schur_complement()
         rng = np.random.default_rng(11)
         b0 = rng.standard_normal(sys_.nb0)
@@ -278,17 +289,21 @@ def _two_gpu_worker(rank, world, port, cfg, q):
         # ranks > 0 pass garbage in b0: the reference ignores it (sLinsysRootAug.C:332-333)
         rhs = [b0.copy() if rank == 0 else np.full(sys_.nb0, 1e30)] + [ball[i].copy() for i in range(lo, hi)]
         sol = sys_.solve_compressed(rhs)
-        q.put((rank, lo, hi, inertia, sc, sol[0], np.stack(sol[1:])))
+        # device BiCGStab over both ranks (dot products all-reduced): the root part of the vectors is replicated
+        ksol = [b0.copy()] + [ball[i].copy() for i in range(lo, hi)]
+        kstat = sys_.solve_bicgstab(ksol, tol=1e-10)
+        q.put((rank, lo, hi, inertia, sc, sol[0], np.stack(sol[1:]), sparse_used, kstat, ksol[0], np.stack(ksol[1:])))
         dist.barrier()
         sys_.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfg", ["T2", "T3"])
+@pytest.mark.parametrize("cfg", ["T2", "T3", "S1-local"])
 def test_two_gpus_nccl_allreduce_equals_single_rank_oracle(pkg, cfg):
-    """blocks partitioned over 2 GPUs as mapChildrenToNSubTrees does over 2 MPI ranks; reduceKKT and the Lsolve b0
-    reduction run as ncclAllReduce. Needs 2 visible GPUs (gpurun --gpus 2)."""
+    """blocks partitioned over 2 GPUs as mapChildrenToNSubTrees does over 2 MPI ranks; reduceKKT (dense pack, or the
+    pattern values of the sparse root for 'S1-local'), the Lsolve b0 reduction and the dot products of the device BiCGStab
+    run as ncclAllReduce. Needs 2 visible GPUs (gpurun --gpus 2)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -306,8 +321,8 @@ def test_two_gpus_nccl_allreduce_equals_single_rank_oracle(pkg, cfg):
         p.join(timeout=120)
         assert p.exitcode == 0
     P = pkg.problem
-    lp = P.synthetic(cfg)
-    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[cfg])
+    lp, base = _two_gpu_lp(P, cfg)
+    dd, nom = P.synthetic_iterate(lp, P.CONFIG_ID[base])
     ref = OracleRoot(lp)
     ref.put_diagonals(dd, nom)
     ref.factor2()
@@ -316,11 +331,18 @@ def test_two_gpus_nccl_allreduce_equals_single_rank_oracle(pkg, cfg):
     nK = lp.children[0].n + lp.children[0].my + lp.children[0].mz
     ball = rng.standard_normal((len(lp.children), nK))
     want = ref.solve_compressed([b0.copy()] + [ball[i].copy() for i in range(len(lp.children))])
-    for rank, lo, hi, inertia, sc, sol0, soll in res:
+    for rank, lo, hi, inertia, sc, sol0, soll, sparse_used, kstat, ksol0, ksoll in res:
         assert _rel(sc, np.tril(ref.SC)) <= 1e-10
         assert inertia == ref.inertia()
+        assert sparse_used == (cfg == "S1-local")
         assert _rel(sol0, want[0]) <= 1e-8
         assert _rel(soll, np.stack(want[1 + lo:1 + hi])) <= 1e-8
+        assert kstat[0] in (0, 1) and kstat[2] <= 1e-10
+        assert _rel(ksol0, want[0]) <= 1e-7
+        assert _rel(ksoll, np.stack(want[1 + lo:1 + hi])) <= 1e-7
+    # both ranks took the same Krylov path (the residual norms agree to rounding: the replicated root parts are updated
+    # with rank-local atomics)
+    assert res[0][8][:2] == res[1][8][:2] and abs(res[0][8][2] - res[1][8][2]) <= 1e-6 * max(res[0][8][2], 1e-300)
 
 
 @pytest.mark.parametrize("cfg", ["T1", "T3"])
