@@ -242,6 +242,15 @@ class LinearSystem:
         stepz = stepz - self.nomegainv * steps
         if self.outer_solve == 0:
             sx, sy, sz = self._precond(stepx, stepy, stepz)
+        elif self.outer_solve == 3:
+            # the backend runs solveCompressedBiCGStab itself (the CUDA product's pipsgpu_kkt_solve): the driver only hands
+            # over the right-hand side in node layout and reads back status / iteration count / relative residual
+            nodes = self.join_rhs(stepx, stepy, stepz)
+            status, iters, relres = self.backend.solve_bicgstab(nodes, tol=self.bicg_tol, max_iter=self.bicg_max_iter)
+            self.bicg_converged, self.bicg_skipped = status in (0, 1), status == 1
+            self.bicg_niter, self.bicg_relres = iters, relres
+            self.stats["bicg_iters"].append(iters)
+            sx, sy, sz = self.separate_vars(nodes)
         else:
             sx, sy, sz = self._bicgstab(stepx, stepy, stepz)
         sy = -sy

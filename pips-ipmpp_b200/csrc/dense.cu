@@ -302,18 +302,29 @@ __global__ void __launch_bounds__(256, 1) ldlt_diag_kernel(double* __restrict__ 
     __shared__ double s_dinv[DENSE_PANEL], s_d[DENSE_PANEL], s_eps[DENSE_PANEL];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < DENSE_PANEL) s_eps[tid] = (tid < bw) ? eps_rel * fmax(scale[kb + tid], 1e-300) : 0.0;
-    // ---- load the lower blocks (rows / columns beyond bw: identity) ----
-    for (int b = 0; b < DNLOW; ++b) {
-        int bi = 0;
-        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
-        const int bj = b - bi * (bi + 1) / 2;
-        for (int idx = tid; idx < DB * DB; idx += 256) {
-            const int r = idx >> 5, c = idx & 31;
-            const int gi = bi * DB + r, gj = bj * DB + c;
-            double v = (gi == gj) ? 1.0 : 0.0;
-            if (gi < bw && gj <= gi) v = A[(int64_t)(kb + gi) * ld + kb + gj];
-            sL[b * DBLK + r * DBL + c] = v;
+    // ---- load the lower blocks (rows / columns beyond bw: identity). All 40 loads of a thread are issued before the first
+    // one is consumed: the block comes from HBM / L2 and sits on the critical path of the whole root factorisation ----
+    {
+        double v[DNLOW * 4];
+#pragma unroll
+        for (int b = 0; b < DNLOW; ++b) {
+            const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
+            const int bj = b - bi * (bi + 1) / 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + q * 256;
+                const int r = idx >> 5, c = idx & 31;
+                const int gi = bi * DB + r, gj = bj * DB + c;
+                v[b * 4 + q] = (gi < bw && gj <= gi) ? A[(int64_t)(kb + gi) * ld + kb + gj] : ((gi == gj) ? 1.0 : 0.0);
+            }
         }
+#pragma unroll
+        for (int b = 0; b < DNLOW; ++b)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = tid + q * 256;
+                sL[b * DBLK + (idx >> 5) * DBL + (idx & 31)] = v[b * 4 + q];
+            }
     }
     __syncthreads();
     int npos = 0, nneg = 0, nzero = 0, npert = 0;      // warp 0, uniform over its lanes
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(256, 1) ldlt_diag_kernel(double* __restrict__ 
                     if (d >= eps) ++npos; else if (d <= -eps) ++nneg; else ++nzero;      // inertia of the computed pivot
                     if (!(sg * d >= eps)) { d = sg * eps; ++npert; }
                 }
-                const double dinv = 1.0 / d;
+                const double dinv = __drcp_rn(d);        // correctly rounded reciprocal, shorter than the general division
                 const double l = colk * dinv;
                 if (lane == k) { s_d[gk] = d; s_dinv[gk] = dinv; }
 #pragma unroll

@@ -671,8 +671,9 @@ void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t 
 // the current one, so the global round trip of the staging overlaps the tensor work and the barriers (measured equal).
 // (Host-built per-tile member lists instead of the flag scan were measured equal too and are gone; so are the
 // cp.async-pipelined 128 x 64 variants of round 2: profiles/README.md.)
-template <bool PIPE>
-__global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
+// MINB = CTAs per SM the register allocation is tuned for (PIPSGPU_GROUP_OCC: 4 = 128 registers, 5 = 96, 6 = 80 with spills)
+template <bool PIPE, int MINB>
+__global__ void __launch_bounds__(128, PIPE ? 3 : MINB) border_group_kernel(FactorArgs a, int64_t gtile_begin) {
     __shared__ double As[MAXW * KLD];
     __shared__ double Bs[MAXW * KLD];
     const GTile td = a.gtiles[gtile_begin + blockIdx.x];
@@ -789,8 +790,10 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : 4) border_group_kernel(FactorA
 }
 void launch_border_groups(const FactorArgs& a, int64_t gtile_begin, int64_t ngtiles, cudaStream_t s) {
     if (ngtiles <= 0 || !a.SC) return;
-    if (a.group_pipe) border_group_kernel<true><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
-    else border_group_kernel<false><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    if (a.group_pipe) border_group_kernel<true, 4><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    else if (a.group_occ == 5) border_group_kernel<false, 5><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    else if (a.group_occ == 6) border_group_kernel<false, 6><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
+    else border_group_kernel<false, 4><<<(unsigned)ngtiles, 128, 0, s>>>(a, gtile_begin);
     COUNT_LAUNCH();
 }
 

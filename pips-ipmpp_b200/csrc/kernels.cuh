@@ -86,6 +86,7 @@ struct FactorArgs {
     const int* ginv;
     int bp_threads;              // CTA size of big_panel_kernel (128 or 256)
     int group_pipe;              // PIPSGPU_GROUP_PIPE=1: software-pipelined member staging in border_group_kernel
+    int group_occ;               // PIPSGPU_GROUP_OCC: CTAs per SM border_group_kernel is compiled for (4, 5 or 6)
     int panel_staged;            // PIPSGPU_PANEL=staged: panel chunks staged in shared memory (kernels.cu: panel_chunk_staged)
     const int8_t* gflags;        // per (group member, 64-row block of the root's border index space): has rows there
     const GTile* gtiles;

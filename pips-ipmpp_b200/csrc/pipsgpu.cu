@@ -198,6 +198,7 @@ struct pipsgpu_ctx {
     bool xform = true;
     bool panel_staged = false;      // PIPSGPU_PANEL=staged
     bool group_pipe = false;        // PIPSGPU_GROUP_PIPE=1
+    int group_occ = 4;              // PIPSGPU_GROUP_OCC
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream_grp = nullptr;  // group (Schur-term) SYRKs of batch b run here next to the tree levels of batch b + 1
     cudaStream_t stream_hi = nullptr;   // high-priority side stream: look-ahead panels of the dense root LDL^T
@@ -246,7 +247,7 @@ struct pipsgpu_ctx {
         a.W = W.p; a.XY = XY.p;
         a.Dd = Dd.p; a.De = De.p; a.Did = Did.p; a.Die = Die.p;
         a.SC = sc ? sc->A.p : nullptr; a.ldsc = sc ? sc->n : 0; a.stats = stats.p; a.tiles = tiles.p;
-        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0;
+        a.groups = groups.p; a.gmembers = gmembers.p; a.ginv = ginv.p; a.gflags = gflags.p; a.gtiles = gtiles.p; a.panel_staged = panel_staged ? 1 : 0; a.group_pipe = group_pipe ? 1 : 0; a.group_occ = group_occ;
         a.bp_threads = bp_threads;
         return a;
     }
@@ -717,6 +718,7 @@ int pipsgpu_ctx_create(int device, pipsgpu_ctx** out) {
     if (const char* e = std::getenv("PIPSGPU_XFORM")) ctx->xform = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_PANEL")) ctx->panel_staged = std::string(e) == "staged";
     if (const char* e = std::getenv("PIPSGPU_GROUP_PIPE")) ctx->group_pipe = std::string(e) != "0";
+    if (const char* e = std::getenv("PIPSGPU_GROUP_OCC")) ctx->group_occ = std::max(4, std::min(6, std::atoi(e)));
     if (const char* e = std::getenv("PIPSGPU_GROUP_BY_LEVEL")) ctx->group_by_level = std::string(e) != "0";
     if (const char* e = std::getenv("PIPSGPU_BP_THREADS")) ctx->bp_threads = (std::atoi(e) == 128) ? 128 : 256;
     CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));

@@ -53,7 +53,7 @@ struct SymbolicOptions {
     int use_metis = 1;
     int relax = 1;
     double relax_small = 0.8;  // admissible fraction of explicit zeros when merging into a supernode of <= 16 columns
-    double relax_mid = 0.1;    // ... of <= 48 columns
+    double relax_mid = 0.25;   // ... of <= 48 columns (0.1 -> 0.25: -2 % on the C2 / C3 / C4 step, profiles/README.md round 2)
     int subtree_width = 32;  // bottom subtrees with at most this many columns are merged into one front (0 = off)
 };
 

@@ -258,3 +258,27 @@ def test_sparse_root_falls_back_to_the_pivoting_dense_solver(pkg):
     assert status == "SUCCESSFUL_TERMINATION"
     assert abs(obj - lp.meta["expected_objective"]) <= 1e-4
     assert iters <= int(np.ceil(1.1 * lp.meta["expected_iterations"]))
+
+
+@pytest.mark.parametrize("name", ["callback", "T1", "T2"])
+def test_ipm_with_the_device_outer_solve(pkg, name):
+    """whole IPM runs with LinearSystem::solveXYZS going through pipsgpu_kkt_solve (device BiCGStab + device system_mult)
+    instead of the restated host loop: same termination, iteration count +-1, objective 1e-8 relative (north star), and on
+    the reference's own instance the golden objective 14 (TST/pipsipmLinkConsTest.sh:25)."""
+    from oracle.ipm import IPM
+    P = pkg.problem
+    make = {"callback": P.callback_example, "T1": lambda: P.synthetic("T1"), "T2": lambda: P.synthetic("T2")}[name]
+    out = {}
+    for outer in (2, 3):
+        lp = make()
+        gpu = pkg.linsys.CudaRootLinearSystem(lp)
+        run = IPM(lp, gpu, outer_solve=outer)
+        out[outer] = run.solve() + (list(run.ls.stats["bicg_iters"]),)
+        gpu.close()
+    (st2, obj2, it2, k2), (st3, obj3, it3, k3) = out[2], out[3]
+    assert st2 == st3 == "SUCCESSFUL_TERMINATION"
+    assert abs(it2 - it3) <= 1
+    assert abs(obj2 - obj3) <= 1e-8 * max(1.0, abs(obj2))
+    assert len(k3) > 0 and max(k3) <= 75
+    if name == "callback":
+        assert abs(obj3 - lp.meta["expected_objective"]) <= 1e-4

@@ -107,6 +107,43 @@ def test_dense_root_solver(pkg, n0, nneg):
     ctx.close()
 
 
+@pytest.mark.parametrize("n", [57, 300])
+def test_dense_root_solver_positive_definite(pkg, n):
+    """the SOLVER_DENSE_SYM_PSD role (SOL/DensePSDSolver/DeSymPSDSolver.C:24-45: dpotrf / dpotrs): a root
+    without dual rows is the same static LDL^T with n0 = n; inertia (n, 0, 0), solution against numpy"""
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, n, 0, 0, 0)
+    sc.upload(np.tril(S))
+    assert sc.factorize() == (n, 0, 0)
+    B = rng.standard_normal((2, n))
+    assert _rel(sc.solve(B), np.linalg.solve(S, B.T).T) <= 1e-11
+    sc.close()
+    ctx.close()
+
+
+def test_dense_root_solver_saddle_point(pkg):
+    """the SOLVER_DENSE_SYM_INDEF_SADDLE_POINT role (SOL/DenseSymmetricIndefinitSolver/DeSymIndefSolver2.C:17-71: Cholesky of Q,
+    dtrsm, dsyrk, Cholesky of A Q^-1 A^T): [Q A^T; A 0] with a zero (2,2) block is exactly what the static x0-first LDL^T
+    factorises without pivoting (no Bunch-Kaufman fallback: zero perturbed pivots, inertia (nx, ny, 0))"""
+    rng = np.random.default_rng(5)
+    nx, ny = 180, 70
+    M = rng.standard_normal((nx, nx))
+    Q = M @ M.T + nx * np.eye(nx)
+    A = rng.standard_normal((ny, nx))
+    S = np.block([[Q, A.T], [A, np.zeros((ny, ny))]])
+    ctx = pkg.capi.Context(0)
+    sc = pkg.capi.SchurComplement(ctx, nx, 0, ny, 0)
+    sc.upload(np.tril(S))
+    assert sc.factorize() == (nx, ny, 0)
+    B = rng.standard_normal((2, nx + ny))
+    assert _rel(sc.solve(B), np.linalg.solve(S, B.T).T) <= 1e-10
+    sc.close()
+    ctx.close()
+
+
 def test_sc_assembly_helpers(pkg):
     import scipy.sparse as sp
     rng = np.random.default_rng(3)
