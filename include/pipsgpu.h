@@ -50,6 +50,10 @@ int pipsgpu_ctx_synchronize(pipsgpu_ctx* ctx);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the host application's or torch's current
  * stream, so that the caller's own events bracket the work. The context does not destroy a borrowed stream. */
 int pipsgpu_ctx_set_stream(pipsgpu_ctx* ctx, void* cuda_stream);
+/* the cudaStream_t every call of this context is enqueued on (its own, or the one given to pipsgpu_ctx_set_stream) */
+void* pipsgpu_ctx_stream(pipsgpu_ctx* ctx);
+/* CUDA device index of the context (-1 for a null handle) */
+int pipsgpu_ctx_device(pipsgpu_ctx* ctx);
 /* NCCL bootstrap without MPI: rank 0 creates the id, the host program ships the 128 bytes to the other ranks
  * (torch.distributed / MPI_Bcast / a file), every rank calls init_comm. Replaces the MPI communicator the reference
  * passes around (LS/DistributedRootLinearSystem.C:47-57, mpiComm). */

@@ -6,6 +6,8 @@
 //   plugin level     CudaSparseLdlSolver   : DoubleLinearSolver   (what PardisoSolver / Ma27Solver / Ma57Solver are:
 //                                                                  SOL/PardisoSolver/PardisoSolver/PardisoSolver.h:20-40)
 //                    CudaSchurLeafSolver   : CudaSparseLdlSolver  (adds schur_solve, PardisoSchurSolver.h:44-58)
+//                    CudaSchurLeafSolverCompat : DoubleLinearSolver (schur_solve with the reference's exact signature and
+//                                                                  call order; private context per leaf, slow path)
 //                    CudaDenseLdlSolver    : DoubleLinearSolver   (DeSymIndefSolver.h:19-35, the dense root solver)
 //   system level     CudaKktSystem         - owns a pipsgpu_kkt; a subclass of sLinsysRootAug forwards factor2 /
 //                                            solveCompressed to it (batched over all scenario blocks of the rank:
@@ -282,6 +284,107 @@ public:
         PIPSGPU_SHIM_CHECK(pipsgpu_leaf_get_inertia(leaf_, in, &npert));
         inertia_ = {(unsigned)in[0], (unsigned)in[1], (unsigned)in[2]};
     }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Schur leaf solver with the reference's EXACT call sequence and signature (plug-in level only, no system-level wiring):
+//     make_leaf_solver(kkt)  ->  matrixChanged() every iteration  ->  schur_solve(R, A, C, F, G, DenseSymmetricMatrix& SC)
+// (PardisoSchurSolver.h:52-53, called unchanged from sLinsysLeafSchurSlv::addTermToDenseSchurCompl,
+// LS/sLinsysLeafSchurSlv.C:20-35). The border is only known at the first schur_solve - as for
+// PardisoSchurSolver::firstSolveCall (PardisoSchurSolver.C:84-389) - so every such solver owns a private context whose
+// symbolic phase runs at that first call; the Schur term is formed in a device scratch shared by all solvers of the
+// process and added to the caller's host matrix. Compatibility path: one factorisation and one n_S x n_S download per
+// leaf and iteration, no batching over leaves - the system-level wiring below is the fast path.
+// ---------------------------------------------------------------------------------------------------------------
+class CudaSchurLeafSolverCompat : public DoubleLinearSolver {
+public:
+    CudaSchurLeafSolverCompat(const SparseSymmetricMatrix& sgm, int nx, int ny, int nz, CudaContext& shared = CudaContext::instance())
+        : matrix_(sgm), n_((int)sgm.size()), shared_(shared) {
+        assert(nx + ny + nz == n_);
+        PIPSGPU_SHIM_CHECK(pipsgpu_ctx_create(pipsgpu_ctx_device(shared_.get()), &ctx_));
+        PIPSGPU_SHIM_CHECK(pipsgpu_ctx_set_stream(ctx_, pipsgpu_ctx_stream(shared_.get())));   // one stream: scratch ops stay ordered
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_create(ctx_, n_, nx, ny, nz, sgm.krowM(), sgm.jcolM(), sgm.M(), &leaf_));
+    }
+    ~CudaSchurLeafSolverCompat() override {
+        pipsgpu_leaf_destroy(leaf_);
+        pipsgpu_ctx_destroy(ctx_);
+    }
+    void diagonalChanged(int, int) override { matrixChanged(); }
+    void matrixChanged() override { dirty_ = true; }      // the numeric factorisation is fused with the Schur term
+
+    // SC (lower triangle, index order [x0; y0; yl; zl]) -= Bord^T K^-1 Bord with Bord = [R^T A^T C^T | F^T | G^T]
+    void schur_solve(const SparseMatrix& R, const SparseMatrix& A, const SparseMatrix& C, const SparseMatrix& F,
+                     const SparseMatrix& G, DenseSymmetricMatrix& SC) {
+        const int n0 = (int)A.n_columns(), myl = (int)F.n_rows(), mzl = (int)G.n_rows();
+        const int nS = (int)SC.size(), my0 = nS - n0 - myl - mzl;
+        assert(my0 >= 0);
+        if (!committed_) {
+            assert(R.n_rows() == 0 || R.krowM()[R.n_rows()] == 0);   // cross Hessian must be empty (PardisoSchurSolver.C:118)
+            (void)R;
+            PIPSGPU_SHIM_CHECK(pipsgpu_leaf_set_border(leaf_, n0, my0, myl, mzl, A.krowM(), A.jcolM(), A.M(), C.krowM(), C.jcolM(),
+                                                       C.M(), F.krowM(), F.jcolM(), F.M(), G.krowM(), G.jcolM(), G.M()));
+            PIPSGPU_SHIM_CHECK(pipsgpu_ctx_commit(ctx_, 0));
+            committed_ = true;
+        }
+        pipsgpu_sc* scratch = scratch_for(n0, my0, myl, mzl);
+        PIPSGPU_SHIM_CHECK(pipsgpu_sc_zero(scratch));
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_set_values(leaf_, matrix_.M()));
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_add_schur(leaf_, scratch));
+        dirty_ = false;
+        int in[3]; int npert = 0;
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_get_inertia(leaf_, in, &npert));
+        inertia_ = {(unsigned)in[0], (unsigned)in[1], (unsigned)in[2]};
+        host_.resize((size_t)nS * nS);
+        PIPSGPU_SHIM_CHECK(pipsgpu_sc_download(scratch, host_.data()));
+        for (int i = 0; i < nS; ++i) {
+            double* row = SC[i];
+            const double* add = host_.data() + (size_t)i * nS;
+            for (int j = 0; j <= i; ++j) row[j] += add[j];
+        }
+    }
+
+    using DoubleLinearSolver::solve;
+    void solve(Vector<double>& rhs_in) override {
+        auto& rhs = dynamic_cast<DenseVector<double>&>(rhs_in);
+        solve(1, rhs.elements(), nullptr);
+    }
+    void solve(int nrhss, double* rhss, int*) override {
+        if (!committed_) {      // used without a Schur term: plain sparse solver
+            PIPSGPU_SHIM_CHECK(pipsgpu_ctx_commit(ctx_, 0));
+            committed_ = true;
+        }
+        if (dirty_) {
+            PIPSGPU_SHIM_CHECK(pipsgpu_leaf_set_values(leaf_, matrix_.M()));
+            int in[3];
+            PIPSGPU_SHIM_CHECK(pipsgpu_leaf_factorize(leaf_, in));
+            inertia_ = {(unsigned)in[0], (unsigned)in[1], (unsigned)in[2]};
+            dirty_ = false;
+        }
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_solve(leaf_, nrhss, rhss));
+    }
+    [[nodiscard]] bool reports_inertia() const override { return true; }
+    [[nodiscard]] std::tuple<unsigned int, unsigned int, unsigned int> get_inertia() const override { return inertia_; }
+
+private:
+    // one device scratch per Schur-complement shape, shared by every compat solver of the process
+    pipsgpu_sc* scratch_for(int n0, int my0, int myl, int mzl) {
+        struct Entry { int d[4]; pipsgpu_sc* sc; };
+        static std::vector<Entry> table;
+        for (auto& e : table)
+            if (e.d[0] == n0 && e.d[1] == my0 && e.d[2] == myl && e.d[3] == mzl) return e.sc;
+        pipsgpu_sc* sc = nullptr;
+        PIPSGPU_SHIM_CHECK(pipsgpu_sc_create(shared_.get(), n0, my0, myl, mzl, &sc));
+        table.push_back(Entry{{n0, my0, myl, mzl}, sc});
+        return sc;
+    }
+    const SparseSymmetricMatrix& matrix_;
+    const int n_;
+    CudaContext& shared_;
+    pipsgpu_ctx* ctx_ = nullptr;
+    pipsgpu_leaf* leaf_ = nullptr;
+    bool committed_ = false, dirty_ = true;
+    std::vector<double> host_;
+    std::tuple<unsigned int, unsigned int, unsigned int> inertia_{0, 0, 0};
 };
 
 // ---------------------------------------------------------------------------------------------------------------

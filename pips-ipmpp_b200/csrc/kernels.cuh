@@ -235,6 +235,9 @@ void launch_axpby(int64_t n, double a, const double* x, double b, double* y, cud
 void launch_diag_axpy(int n, double alpha, const double* d, const double* x, double* y, cudaStream_t s);   // y += alpha d .* x
 void launch_dot(int64_t n, const double* x, const double* y, double* partial, double* out, cudaStream_t s);   // deterministic
 constexpr int DOT_SCRATCH = 1024;
+struct LeafDiag { int64_t pos_off, dd_off, nz_off; int nx, ny, nz, pad; double reg[3]; };
+void launch_build_dvals(int64_t npos, const LeafDiag* tab, int nl, const double* dd, const double* nz, double regP, double regDy,
+                        double regDz, double* dvals, cudaStream_t s);
 void launch_gather_idx(const double* A, const int64_t* idx, int64_t n, double* out, cudaStream_t s);    // out[e] = A[idx[e]]
 void launch_scatter_idx(double* A, const int64_t* idx, int64_t n, const double* in, cudaStream_t s);    // A[idx[e]] = in[e]
 void launch_absmax_eps(const double* v, int64_t n, double rel, double* eps_out, cudaStream_t s);        // *eps_out = rel * max|v|

@@ -143,4 +143,32 @@ void launch_absmax_eps(const double* v, int64_t n, double rel, double* eps_out, 
     count_launch("absmax_eps_kernel");
 }
 
+// ---- leaf diagonals of one factorisation, assembled on the device (pipsgpu_kkt_factorize) ----
+// dvals[p] of leaf l (positions pos_off .. pos_off + n): [ dd_l + regP | -regDy | nomegainv_l - regDz ] with the leaf's own
+// regularisation added; dd / nz are the caller's concatenated vectors (null = zeros). One thread per position, the leaf
+// is found by bisection of the (ascending) position offsets.
+__global__ void build_dvals_kernel(int64_t npos, const LeafDiag* __restrict__ tab, int nl, const double* __restrict__ dd,
+                                   const double* __restrict__ nz, double regP, double regDy, double regDz, double* __restrict__ dvals) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npos) return;
+    int lo = 0, hi = nl - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab[mid].pos_off <= p) lo = mid; else hi = mid - 1;
+    }
+    const LeafDiag t = tab[lo];
+    const int i = (int)(p - t.pos_off);
+    double v;
+    if (i < t.nx) v = (dd ? dd[t.dd_off + i] : 0.0) + regP + t.reg[0];
+    else if (i < t.nx + t.ny) v = -(regDy + t.reg[1]);
+    else v = (nz ? nz[t.nz_off + (i - t.nx - t.ny)] : 0.0) - (regDz + t.reg[2]);
+    dvals[p] = v;
+}
+void launch_build_dvals(int64_t npos, const LeafDiag* tab, int nl, const double* dd, const double* nz, double regP, double regDy,
+                        double regDz, double* dvals, cudaStream_t s) {
+    if (npos <= 0 || nl <= 0) return;
+    build_dvals_kernel<<<kr_cdiv(npos, 256), 256, 0, s>>>(npos, tab, nl, dd, nz, regP, regDy, regDz, dvals);
+    count_launch("build_dvals_kernel");
+}
+
 }  // namespace pipsgpu

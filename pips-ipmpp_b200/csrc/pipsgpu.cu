@@ -292,11 +292,15 @@ struct pipsgpu_kkt {
     std::unique_ptr<pipsgpu_sc> sc;
     bool ready = false;
     DevBuf<double> dd0, zdiag0, zdiagl, b0, r, t3, bl, tl, b0_in, bl_in, wl;
+    DevBuf<double> dd_in, nz_in;        // the caller's concatenated leaf diagonals of the current factorisation
+    DevBuf<LeafDiag> ldiag;             // per leaf: where its diagonals sit (launch_build_dvals)
+    std::vector<LeafDiag> h_ldiag;
+    double* h_root = nullptr;           // pinned staging of the root diagonals (n0 + mz0 + mzl)
     // device BiCGStab (pipsgpu_kkt_solve): whole-tree vectors [root part (nb0, padded) | leaf part (N)], allocated on first use
     DevBuf<double> kv[9], kc0, kpartial, kscal;
     double* h_scal = nullptr;       // pinned
     int64_t kv_root = 0;            // padded length of the root part
-    ~pipsgpu_kkt() { if (h_scal) cudaFreeHost(h_scal); }
+    ~pipsgpu_kkt() { if (h_scal) cudaFreeHost(h_scal); if (h_root) cudaFreeHost(h_root); }
     bool have_diag = false, have_rhs = false;
     double last_regDy = 0.0;
     int64_t sum_nx = 0, sum_nz = 0, sum_n = 0;
@@ -764,6 +768,9 @@ int pipsgpu_ctx_set_stream(pipsgpu_ctx* ctx, void* stream) {
     ctx->own_stream = false;
     PIPSGPU_CATCH
 }
+
+void* pipsgpu_ctx_stream(pipsgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int pipsgpu_ctx_device(pipsgpu_ctx* ctx) { return ctx ? ctx->device : -1; }
 
 int pipsgpu_ctx_synchronize(pipsgpu_ctx* ctx) {
     PIPSGPU_TRY
@@ -2002,25 +2009,40 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomeg
     cudaStream_t s = ctx->stream;
     const double regP = reg ? reg[0] : 0.0, regDy = reg ? reg[1] : 0.0, regDz = reg ? reg[2] : 0.0;
     CUDA_CHECK(cudaEventRecord(k->ev[0], s));
-    // ---- diagonals down (the only per-iteration H2D payload of the factorisation) ----
+    // ---- diagonals down (the only per-iteration H2D payload of the factorisation): the caller's vectors go to the device as
+    // they are (no host staging loop, the equality rows' constant diagonal is not transferred) and are assembled there ----
     {
-        const double* dd = dd_leaves;
-        const double* nz = nomegainv_leaves;
-        for (auto* lf : k->leaves) {
-            leaf_fill_dvals(lf, dd, nz, regP, regDy, regDz);
-            if (dd) dd += lf->nx;
-            if (nz) nz += lf->nz;
+        const size_t nl = k->leaves.size();
+        if (k->h_ldiag.size() != nl) {
+            k->h_ldiag.resize(nl);
+            int64_t ddo = 0, nzo = 0;
+            for (size_t i = 0; i < nl; ++i) {
+                const pipsgpu_leaf* lf = k->leaves[i];
+                LeafDiag& t = k->h_ldiag[i];
+                t.pos_off = lf->pos_off; t.dd_off = ddo; t.nz_off = nzo; t.nx = lf->nx; t.ny = lf->ny; t.nz = lf->nz; t.pad = 0;
+                ddo += lf->nx; nzo += lf->nz;
+            }
+            k->dd_in.alloc((size_t)k->sum_nx + 1); k->nz_in.alloc((size_t)k->sum_nz + 1);
+            CUDA_CHECK(cudaMallocHost(&k->h_root, sizeof(double) * ((size_t)k->n0 + k->mz0 + k->mzl + 1)));
         }
-        if (ctx->npos > 0)
-            CUDA_CHECK(cudaMemcpyAsync(ctx->dvals.p, ctx->h_dvals, sizeof(double) * (size_t)ctx->npos, cudaMemcpyHostToDevice, s));
-        std::vector<double> h0((size_t)k->n0), hz((size_t)k->mz0), hl((size_t)k->mzl);
+        for (size_t i = 0; i < nl; ++i) { const pipsgpu_leaf* lf = k->leaves[i]; for (int q = 0; q < 3; ++q) k->h_ldiag[i].reg[q] = lf->reg[q]; }
+        k->ldiag.ensure(nl);
+        if (nl) CUDA_CHECK(cudaMemcpyAsync(k->ldiag.p, k->h_ldiag.data(), sizeof(LeafDiag) * nl, cudaMemcpyHostToDevice, s));
+        if (dd_leaves && k->sum_nx > 0)
+            CUDA_CHECK(cudaMemcpyAsync(k->dd_in.p, dd_leaves, sizeof(double) * (size_t)k->sum_nx, cudaMemcpyHostToDevice, s));
+        if (nomegainv_leaves && k->sum_nz > 0)
+            CUDA_CHECK(cudaMemcpyAsync(k->nz_in.p, nomegainv_leaves, sizeof(double) * (size_t)k->sum_nz, cudaMemcpyHostToDevice, s));
+        launch_build_dvals(ctx->npos, k->ldiag.p, (int)nl, dd_leaves ? k->dd_in.p : nullptr, nomegainv_leaves ? k->nz_in.p : nullptr,
+                           regP, regDy, regDz, ctx->dvals.p, s);
+        double* h0 = k->h_root; double* hz = h0 + k->n0; double* hl = hz + k->mz0;
         for (int i = 0; i < k->n0; ++i) h0[i] = (dd0 ? dd0[i] : 0.0) + regP;
         for (int i = 0; i < k->mz0; ++i) hz[i] = (nomegainv0 ? nomegainv0[i] : 0.0) - regDz;
         for (int i = 0; i < k->mzl; ++i) hl[i] = (nomegainv_link ? nomegainv_link[i] : 0.0) - regDz;
-        if (k->n0) CUDA_CHECK(cudaMemcpyAsync(k->dd0.p, h0.data(), sizeof(double) * h0.size(), cudaMemcpyHostToDevice, s));
-        if (k->mz0) CUDA_CHECK(cudaMemcpyAsync(k->zdiag0.p, hz.data(), sizeof(double) * hz.size(), cudaMemcpyHostToDevice, s));
-        if (k->mzl) CUDA_CHECK(cudaMemcpyAsync(k->zdiagl.p, hl.data(), sizeof(double) * hl.size(), cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));   // h0/hz/hl are stack-lifetime staging buffers
+        if (k->n0) CUDA_CHECK(cudaMemcpyAsync(k->dd0.p, h0, sizeof(double) * (size_t)k->n0, cudaMemcpyHostToDevice, s));
+        if (k->mz0) CUDA_CHECK(cudaMemcpyAsync(k->zdiag0.p, hz, sizeof(double) * (size_t)k->mz0, cudaMemcpyHostToDevice, s));
+        if (k->mzl) CUDA_CHECK(cudaMemcpyAsync(k->zdiagl.p, hl, sizeof(double) * (size_t)k->mzl, cudaMemcpyHostToDevice, s));
+        // (kkt_factorize_device ends with a stream synchronisation - the inertia read-back -, so the caller's vectors and the
+        // pinned staging are free again when this call returns)
     }
     k->have_diag = true;
     k->last_regDy = regDy;

@@ -195,6 +195,33 @@ int main() {
     solver->solve(3, multi.data(), nullptr);
     double lin = 0; for (int i = 0; i < n; ++i) lin += std::fabs(multi[2 * n + i] - 3.0 * rhs.elements()[i]);
 
+    // ---- PardisoSchurSolver's exact call sequence: matrixChanged(); schur_solve(R, A, C, F, G, DenseSymmetricMatrix&) ----
+    // (sLinsysLeafSchurSlv.C:20-35 unchanged). Sum over the leaves against the batched device path on a fresh SC.
+    DenseSymmetricMatrix SCh(nS);
+    {
+        std::vector<std::unique_ptr<CudaSchurLeafSolverCompat>> cs;
+        for (auto& l : leaves) cs.push_back(std::make_unique<CudaSchurLeafSolverCompat>(*l.K, l.nx, l.ny, l.nz));
+        for (size_t i = 0; i < leaves.size(); ++i) {
+            DoubleLinearSolver* base = cs[i].get();
+            base->matrixChanged();
+            cs[i]->schur_solve(R.sparse(), leaves[i].A.sparse(), leaves[i].C.sparse(), leaves[i].F.sparse(), leaves[i].G.sparse(), SCh);
+        }
+    }
+    pipsgpu_sc* sc2 = nullptr;
+    PIPSGPU_SHIM_CHECK(pipsgpu_sc_create(CudaContext::instance().get(), n0, my0, myl, mzl, &sc2));
+    PIPSGPU_SHIM_CHECK(pipsgpu_ctx_factorize_leaves(CudaContext::instance().get(), sc2));
+    std::vector<double> sc_dev((size_t)nS * nS);
+    PIPSGPU_SHIM_CHECK(pipsgpu_sc_download(sc2, sc_dev.data()));
+    pipsgpu_sc_destroy(sc2);
+    double sc_num = 0, sc_den = 0;
+    for (int i = 0; i < nS; ++i)
+        for (int j = 0; j <= i; ++j) {
+            const double a = SCh[i][j], b2 = sc_dev[(size_t)i * nS + j];
+            sc_num += (a - b2) * (a - b2); sc_den += b2 * b2;
+        }
+    const double res_compat = std::sqrt(sc_num / std::max(sc_den, 1e-300));
+    std::printf("compat schur_solve(R,A,C,F,G,SC) vs batched Schur complement: rel. Frobenius %.3e\n", res_compat);
+
     // ---- dense root solver through DoubleLinearSolver* ----------------------------------------------------------
     const int nd = 48, nd0 = 20;
     DenseSymmetricMatrix S(nd);
@@ -217,7 +244,7 @@ int main() {
     auto din = ds->get_inertia();
     std::printf("dense solve residual %.3e, inertia (%u,%u,%u)\n", res_dense, std::get<0>(din), std::get<1>(din), std::get<2>(din));
 
-    const bool ok = ok_bicg && res_kkt <= 1e-9 && res_leaf <= 1e-10 && lin <= 1e-9 && res_dense <= 1e-11 &&
+    const bool ok = ok_bicg && res_compat <= 1e-10 && sc_den > 0 && res_kkt <= 1e-9 && res_leaf <= 1e-10 && lin <= 1e-9 && res_dense <= 1e-11 &&
                     in == std::make_tuple((unsigned)lf.nx, (unsigned)(lf.ny + lf.nz), 0u) &&
                     din == std::make_tuple((unsigned)nd0, (unsigned)(nd - nd0), 0u);
     std::printf(ok ? "shim_test PASS\n" : "shim_test FAIL\n");
