@@ -466,7 +466,8 @@ def main():
                       "bound": "tensor", "achieved": schur_fl / t_sk / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
                       "frac": schur_fl / t_sk / 1e12 / dmma_peak, "traffic": traffic.get("schur_kernels"),
                       "peak_source": tensor_src, "algorithmic_flops_per_step": schur_fl, "avg_launch_ms": t_sk * 1e3 / max(nbatches, 1),
-                      "launches_per_step": nbatches, "share_of_step": t_sk * 1e3 / ms_per_step})
+                      "launches_per_step": nbatches, "share_of_step": t_sk * 1e3 / ms_per_step,
+                      "dmma_pipe_active_pct_ncu": traffic.get("schur_dmma_pipe_active_pct")})
     # (3) dense root LDL^T (all panels of one factorisation): F3 = n_S^3 / 3 + 2 n_S^2
     t_root = stage_ms["root_ldlt"] * 1e-3
     if t_root > 0:

@@ -150,7 +150,8 @@ int pipsgpu_sc_destroy(pipsgpu_sc* sc);
  *     happens here, once. If a pivot has to be perturbed or the inertia is not (n0, n - n0, 0) the dense solver (which can
  *     pivot) takes over for that factorisation.
  * The assembly target stays the dense device buffer (leaves add their Schur terms there); entries outside the pattern
- * are ignored. */
+ * are ignored. Calling it again replaces the pattern and redoes the symbolic analysis (DoubleLinearSolver::matrixRebuild,
+ * SOL/DoubleLinearSolver.h:39). */
 int pipsgpu_sc_set_sparse_pattern(pipsgpu_sc* sc, const int* krow, const int* jcol, int threads);
 /* 1 if the last pipsgpu_sc_factorize / pipsgpu_kkt_factorize used the sparse root solver */
 int pipsgpu_sc_uses_sparse_solver(pipsgpu_sc* sc);

@@ -1728,9 +1728,16 @@ pipsgpu_sc::~pipsgpu_sc() {
 int pipsgpu_sc_set_sparse_pattern(pipsgpu_sc* sc, const int* krow, const int* jcol, int threads) {
     PIPSGPU_TRY
     if (!sc || !krow || !jcol) throw Error(PIPSGPU_ERR_INVALID, "pipsgpu_sc_set_sparse_pattern: null argument");
-    if (sc->sp_ctx) throw Error(PIPSGPU_ERR_STATE, "pipsgpu_sc_set_sparse_pattern: pattern already set");
     pipsgpu_ctx* ctx = sc->ctx;
     require_device(ctx);
+    if (sc->sp_ctx) {
+        // a new pattern replaces the old one (DoubleLinearSolver::matrixRebuild, SOL/DoubleLinearSolver.h:39: the sparsified
+        // Schur complement of the reference's preconditioner changes its pattern): the symbolic analysis is redone
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (sc->sp_leaf) pipsgpu_leaf_destroy(sc->sp_leaf);
+        pipsgpu_ctx_destroy(sc->sp_ctx);
+        sc->sp_leaf = nullptr; sc->sp_ctx = nullptr; sc->sp_nnz = 0; sc->used_sparse = false;
+    }
     const int n = sc->n;
     const int64_t nnz = krow[n];
     std::vector<int64_t> idx((size_t)nnz);
