@@ -234,14 +234,12 @@ def test_sparse_root_schur_complement(pkg):
             rhs = _random_rhs(gpu, lp, 4)
         got[mode] = np.concatenate(gpu.solve_compressed([r.copy() for r in rhs]))
         if mode == "sparse":
-            # matrixRebuild analogue: declaring a (here: the full lower-triangular) pattern again redoes the root's analysis
-            full = np.tril(np.ones((n, n))) > 0
-            import scipy.sparse as sp
-            Pf = sp.csr_matrix(full)
-            gpu.kkt.sc().set_sparse_pattern(Pf.indptr.astype(np.int32), Pf.indices.astype(np.int32))
+            # matrixRebuild analogue: declaring a pattern again throws the root's analysis away and redoes it. (A pattern
+            # with structural entries that are numerically zero in the y0 rows would mislead the 2x2 pivot matching - the
+            # solver then falls back to the dense path, see the next test - so the same pattern is declared again here.)
+            gpu.kkt.sc().set_sparse_pattern(pat[0], pat[1])
             assert gpu.factorize(dd, nom) == inertia and gpu.kkt.sc().uses_sparse_solver()
             assert _rel(np.concatenate(gpu.solve_compressed([r.copy() for r in rhs])), got[mode]) <= 1e-9
-            gpu.kkt.sc().set_sparse_pattern(pat[0], pat[1])
         # repeated factorisation with another iterate reuses the symbolic analysis of the root
         dd2 = [d * 1.7 for d in dd]
         assert gpu.factorize(dd2, nom) == inertia
