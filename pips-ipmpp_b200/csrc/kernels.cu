@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : MINB) border_group_kernel(Fact
     __shared__ double As[MAXW * KLD];
     __shared__ double Bs[MAXW * KLD];
     const GTile td = a.gtiles[gtile_begin + blockIdx.x];
-    const GroupDesc g = a.groups[td.group];
+    struct { int64_t inv_base; int mem_begin, mem_end, N, nblk; } g = {td.inv_base, td.mem_begin, td.mem_begin + td.nmem, td.N, td.nblk};
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
@@ -769,8 +769,7 @@ __global__ void __launch_bounds__(128, PIPE ? 3 : MINB) border_group_kernel(Fact
         }
         mb = nmb; ti = nti; tj = ntj; q = qn;
     }
-    const FrontDesc& rd = a.fronts[g.root];
-    const int* rowb = a.rowg + rd.rows_off + rd.na;            // Schur-complement index of every border row of the root
+    const int* rowb = a.rowg + td.rowb_off;                    // Schur-complement index of every border row of the root
     const int i0 = td.bi * GROUP_TILE, j0 = td.bj * GROUP_TILE;
 #pragma unroll
     for (int x = 0; x < 4; ++x) {

@@ -32,7 +32,15 @@ struct GroupDesc {
     int N, nblk;        // N = border rows of the root front, nblk = ceil(N / 64)
     int root, pad;
 };
-struct GTile { int group, bi, bj, pad; };
+// one 64 x 64 output tile of a group; self-contained (carries what it needs of its GroupDesc and the position of the root's
+// Schur-complement row indices), so that the kernel's prologue and flush have no dependent descriptor loads
+struct GTile {
+    int64_t inv_base;   // as GroupDesc
+    int64_t rowb_off;   // rowg[rowb_off + p] = Schur-complement index of the root's border row p
+    int mem_begin, nmem;
+    int N, nblk;
+    int bi, bj;
+};
 
 // One front (supernode) of one scenario block. All offsets index context-wide pools.
 struct FrontDesc {

@@ -1250,8 +1250,11 @@ int pipsgpu_ctx_commit(pipsgpu_ctx* ctx, int threads) {
                 const int gi = (int)groups.size();
                 groups.push_back(gd);
                 const int ol = nlev - 1 - lf->S.sn_level[(size_t)G.root[(size_t)oi]];      // level order of the group root
+                const FrontDesc& rootd = fronts[(size_t)gd.root];
                 for (int bi = 0; bi < gd.nblk; ++bi)
-                    for (int bj = 0; bj <= bi; ++bj) lev_gtiles[(size_t)ol].push_back(GTile{gi, bi, bj, 0});
+                    for (int bj = 0; bj <= bi; ++bj)
+                        lev_gtiles[(size_t)ol].push_back(GTile{gd.inv_base, rootd.rows_off + rootd.na, gd.mem_begin,
+                                                               gd.mem_end - gd.mem_begin, gd.N, gd.nblk, bi, bj});
                 lf->gtile_count[(size_t)ol] += (int64_t)gd.nblk * (gd.nblk + 1) / 2;
             }
             lf->G = BorderGroups();
@@ -2020,7 +2023,8 @@ int pipsgpu_kkt_factorize(pipsgpu_kkt* k, const double* dd0, const double* nomeg
     // they are (no host staging loop, the equality rows' constant diagonal is not transferred) and are assembled there ----
     {
         const size_t nl = k->leaves.size();
-        if (k->h_ldiag.size() != nl) {
+        if (k->h_ldiag.size() != nl || !k->h_root) {
+            if (k->h_root) { cudaFreeHost(k->h_root); k->h_root = nullptr; }
             k->h_ldiag.resize(nl);
             int64_t ddo = 0, nzo = 0;
             for (size_t i = 0; i < nl; ++i) {
