@@ -123,6 +123,56 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_cores(local_rank, world):
+    """NUMA placement of one rank (what an MPI launcher's --bind-to does for the reference): restrict the process to the
+    cores `nvidia-smi topo -m` lists as CPU affinity of its GPU, and inside that set to the rank's share among the GPUs with
+    the same affinity. Pinned staging buffers are then first-touched on the GPU's own NUMA node. Best effort: any parsing
+    problem leaves the affinity untouched. Returns a short description for the bench line."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        aff = {}
+        for line in out.splitlines():
+            m = re.match(r"^GPU(\d+)\s", line)
+            if not m:
+                continue
+            toks = [t for t in line.split() if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t)]
+            if not toks:
+                continue
+            cores = set()
+            for part in toks[0].split(","):      # first purely numeric range list after the link columns = CPU affinity
+                a, _, b = part.partition("-")
+                cores.update(range(int(a), int(b or a) + 1))
+            aff[int(m.group(1))] = sorted(cores)
+        mine = aff.get(local_rank)
+        if not mine:
+            return "unbound (no CPU affinity reported)"
+        avail = sorted(set(mine) & set(os.sched_getaffinity(0)))
+        peers = sorted(g for g, c in aff.items() if c == mine and g < world)
+        if len(avail) >= 2 * len(peers) and local_rank in peers:
+            k = peers.index(local_rank)
+            share = len(avail) // len(peers)
+            avail = avail[k * share:(k + 1) * share]
+        if not avail:
+            return "unbound (empty core set)"
+        os.sched_setaffinity(0, avail)
+        global _BOUND
+        _BOUND = True
+        return f"cores {avail[0]}-{avail[-1]} ({len(avail)}) = CPU affinity of GPU {local_rank}"
+    except Exception as e:      # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
+_BOUND = False
+
+
+def rank_cores(world):
+    """host cores this rank may use: its bound set, or an even share of the box"""
+    if _BOUND:
+        return max(1, len(os.sched_getaffinity(0)))
+    return max(1, (os.cpu_count() or 1) // max(world, 1))
+
+
 def scaling_mode(args):
     if args.scaling != "auto":
         return args.scaling
@@ -159,7 +209,7 @@ def build_problem(pkg, args, rank, world, total):
     P = pkg.problem
     parts = pkg.capi.partition(total, world)
     lo, hi = parts[rank]
-    nproc = args.gen_procs or max(1, (os.cpu_count() or 1) // world)
+    nproc = args.gen_procs or rank_cores(world)
     nproc = max(1, min(nproc, hi - lo))
     if nproc == 1:
         lp = P.synthetic(args.config, n_blocks=total, block_range=(lo, hi))
@@ -252,6 +302,7 @@ def main():
         return 2
     graft.build()
     pkg = graft.load_package()
+    binding = bind_to_gpu_cores(local_rank, world) if (world > 1 and args.impl == "ours") else "unbound (single rank)"
     total_blocks = total_blocks_of(args, world, pkg)
     workload = workload_string(args, pkg, total_blocks, world)
 
@@ -290,7 +341,7 @@ def main():
     stream = torch.cuda.Stream()
     t_setup = time.perf_counter()
     # host threads of the (one-off) symbolic phase: the ranks of one box share its cores
-    sym_threads = max(1, (os.cpu_count() or 1) // world) if world > 1 else 0
+    sym_threads = rank_cores(world) if world > 1 else 0
     sys_ = pkg.linsys.CudaRootLinearSystem(lp, device=local_rank, rank=rank, n_ranks=world, nccl_uid=uid,
                                            threads=sym_threads, stream=stream.cuda_stream, kkts=kkts)
     del kkts
@@ -531,7 +582,7 @@ def main():
                            "l2_policy": "working set (factor panels + solve pool, GBs) exceeds the 126 MB L2; no flush needed",
                            "e2e_policy": "per step: diagonals H2D + factorize + solves x (rhs H2D, solveCompressed, solution D2H) through "
                                          "the C ABI with pinned host buffers, one buffer per solve, refreshed between timed steps",
-                           "host_generation_s": t_gen, "symbolic_setup_s": t_setup},
+                           "host_generation_s": t_gen, "symbolic_setup_s": t_setup, "rank0_cpu_binding": binding},
                 "e2e": {"value": ms_per_step_e2e * 1e-3, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
