@@ -98,14 +98,17 @@ __device__ __forceinline__ ChildRef child_ref(const FactorArgs& a, int c) {
     return r;
 }
 
-constexpr int PV_WARPS = 2;       // fronts per CTA in pivot_kernel (2 x 2 x 32 x 33 doubles of shared memory)
-constexpr int PLD = MAXW + 1;
-
-__global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int begin, int nfronts) {
-    __shared__ double s_l[PV_WARPS][MAXW * PLD];   // A11 on entry, then L11 (strict lower)
-    __shared__ double s_w[PV_WARPS][MAXW * PLD];   // W11 = L11 D (strict lower), then X = L11^-1
-    __shared__ double s_did[PV_WARPS][MAXW], s_die[PV_WARPS][MAXW];
-    __shared__ int8_t s_pt[PV_WARPS][MAXW];
+// One kernel per width class WP = 8 / 16 / 32 (the level lists are grouped by class): the shared-memory tiles and the
+// unrolled register arrays are sized by the class, so the narrow fronts - the bulk: mean width 15 - run at 4 fronts per CTA
+// and 4-15x more resident warps than with 32 x 33 tiles for everybody (the kernel is latency-bound).
+template <int WP>
+__global__ void __launch_bounds__((WP == 32 ? 2 : 4) * 32) pivot_kernel(FactorArgs a, int begin, int nfronts) {
+    constexpr int PV_WARPS = (WP == 32) ? 2 : 4;      // fronts per CTA
+    constexpr int PLD = WP + 1;
+    __shared__ double s_l[PV_WARPS][WP * PLD];   // A11 on entry, then L11 (strict lower)
+    __shared__ double s_w[PV_WARPS][WP * PLD];   // W11 = L11 D (strict lower), then X = L11^-1
+    __shared__ double s_did[PV_WARPS][WP], s_die[PV_WARPS][WP];
+    __shared__ int8_t s_pt[PV_WARPS][WP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fi = blockIdx.x * PV_WARPS + warp;
     if (fi >= nfronts) return;
@@ -121,25 +124,28 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     // assembled pivot block, lane = row: own entries + the children's contributions. All global loads of one source are
     // issued back to back into registers (one warp per front: the kernel is latency-bound).
     {
-        double pv[MAXW];
+        double pv[WP];
 #pragma unroll
-        for (int k = 0; k < MAXW; ++k) pv[k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
+        for (int k = 0; k < WP; ++k) pv[k] = (lane < w && k <= lane) ? F[(size_t)k * m + lane] : 0.0;
         for (int c = fd.child_begin; c < fd.child_end; ++c) {
             const ChildRef ch = child_ref(a, c);
             const int ci = (lane < w) ? ch.inv[lane] : -1;
 #pragma unroll
-            for (int k = 0; k < MAXW; ++k) {
+            for (int k = 0; k < WP; ++k) {
                 const int cj = __shfl_sync(full, ci, k);
                 if (k < w && cj >= 0 && ci >= 0 && lane >= k) pv[k] += ch.C[(size_t)cj * ch.u + ci];
             }
         }
+        if (lane < WP) {
 #pragma unroll
-        for (int k = 0; k < MAXW; ++k)
-            if (k < wp) { Pl[lane * PLD + k] = pv[k]; Pw[lane * PLD + k] = 0.0; }
+            for (int k = 0; k < WP; ++k) { Pl[lane * PLD + k] = pv[k]; Pw[lane * PLD + k] = 0.0; }
+        }
     }
-    pt[lane] = (lane < w) ? a.ptype[fd.col0 + lane] : (int8_t)0;
-    did[lane] = 0.0;
-    die[lane] = 0.0;
+    if (lane < WP) {
+        pt[lane] = (lane < w) ? a.ptype[fd.col0 + lane] : (int8_t)0;
+        did[lane] = 0.0;
+        die[lane] = 0.0;
+    }
     __syncwarp();
     // ---- LDL^T, left-looking: lane i owns row i, lock-step over the pivots ----
     {
@@ -150,12 +156,26 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
             const bool pair = (pt[k] == 1) && (k + 1 < w);
             double r1 = 0.0, r2 = 0.0;
             if (lane >= k && lane < w) {
-                r1 = Pl[lane * PLD + k];
-                for (int j = 0; j < k; ++j) r1 = fma(-Pl[lane * PLD + j], Pw[k * PLD + j], r1);
-                if (pair && lane >= k + 1) {
-                    r2 = Pl[lane * PLD + k + 1];
-                    for (int j = 0; j < k; ++j) r2 = fma(-Pl[lane * PLD + j], Pw[(k + 1) * PLD + j], r2);
+                // four independent partial sums per column: the chain of dependent FMAs (k of them) was the latency of
+                // every pivot step; a 2x2 pivot shares the loads of this lane's row between its two columns
+                const double* lrow = Pl + lane * PLD;
+                const double* w1 = Pw + k * PLD;
+                const double* w2 = Pw + (k + 1) * PLD;      // only read for a pair (k + 1 < w)
+                const bool two = pair && lane >= k + 1;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+                int j = 0;
+                for (; j + 4 <= k; j += 4) {
+                    const double a0 = lrow[j], a1 = lrow[j + 1], a2 = lrow[j + 2], a3 = lrow[j + 3];
+                    s0 = fma(a0, w1[j], s0); s1 = fma(a1, w1[j + 1], s1); s2 = fma(a2, w1[j + 2], s2); s3 = fma(a3, w1[j + 3], s3);
+                    if (two) { t0 = fma(a0, w2[j], t0); t1 = fma(a1, w2[j + 1], t1); t2 = fma(a2, w2[j + 2], t2); t3 = fma(a3, w2[j + 3], t3); }
                 }
+                for (; j < k; ++j) {
+                    const double a0 = lrow[j];
+                    s0 = fma(a0, w1[j], s0);
+                    if (two) t0 = fma(a0, w2[j], t0);
+                }
+                r1 = lrow[k] - ((s0 + s1) + (s2 + s3));
+                if (two) r2 = lrow[k + 1] - ((t0 + t1) + (t2 + t3));
             }
             const int g = fd.col0 + k;
             if (!pair) {
@@ -218,10 +238,10 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     // ---- X = L11^-1 (lane = column c of X, forward substitution; overwrites W11) ----
     for (int i = 0; i < wp; ++i) {
         double acc = 0.0;
-        if (i < w)
+        if (i < w && lane < WP)
             for (int j = 0; j < i; ++j) acc = fma(Pl[i * PLD + j], Pw[j * PLD + lane], acc);
         __syncwarp();
-        Pw[i * PLD + lane] = (i == lane && i < w) ? 1.0 : ((i > lane && i < w) ? -acc : 0.0);
+        if (lane < WP) Pw[i * PLD + lane] = (i == lane && i < w) ? 1.0 : ((i > lane && i < w) ? -acc : 0.0);
         __syncwarp();
     }
     // ---- X to the scratch, row-major [n][kk] with leading dimension wp (zero padded) ----
@@ -229,9 +249,12 @@ __global__ void __launch_bounds__(PV_WARPS * 32) pivot_kernel(FactorArgs a, int 
     if (lane < wp)
         for (int n = 0; n < wp; ++n) X[(size_t)n * wp + lane] = Pw[n * PLD + lane];
 }
-void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s) {
+// fronts level_fronts[begin ..) of ONE width class cls (0: w <= 8, 1: w <= 16, 2: w <= 32)
+void launch_pivot(const FactorArgs& a, int begin, int nfronts, int cls, cudaStream_t s) {
     if (nfronts <= 0) return;
-    pivot_kernel<<<cdiv(nfronts, PV_WARPS), PV_WARPS * 32, 0, s>>>(a, begin, nfronts);
+    if (cls == 0) pivot_kernel<8><<<cdiv(nfronts, 4), 128, 0, s>>>(a, begin, nfronts);
+    else if (cls == 1) pivot_kernel<16><<<cdiv(nfronts, 4), 128, 0, s>>>(a, begin, nfronts);
+    else pivot_kernel<32><<<cdiv(nfronts, 2), 64, 0, s>>>(a, begin, nfronts);
     COUNT_LAUNCH();
 }
 

@@ -172,7 +172,7 @@ cudaError_t init_kernel_attributes();
 // ---- leaf path ----
 void launch_scatter_values(const int64_t* map, const double* val, int64_t nnz, double* L, cudaStream_t s);
 void launch_set_diag(const int64_t* diagpos, const double* dvals, int64_t n, double* kval, cudaStream_t s);
-void launch_pivot(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);             // fronts level_fronts[begin..)
+void launch_pivot(const FactorArgs& a, int begin, int nfronts, int cls, cudaStream_t s);    // fronts level_fronts[begin..) of width class cls
 void launch_small_fronts(const FactorArgs& a, int begin, int nfronts, cudaStream_t s);      // fronts fl_fronts[begin..)
 void launch_big_panel(const FactorArgs& a, int begin, int nfronts, int max_u, cudaStream_t s);   // max_u: tallest front of the range
 void launch_front_update_tiles(const FactorArgs& a, int64_t tile_begin, int64_t ntiles, cudaStream_t s);

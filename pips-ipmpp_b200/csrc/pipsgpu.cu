@@ -404,15 +404,11 @@ void run_factor_range(pipsgpu_ctx* ctx, pipsgpu_sc* sc, int lo, int hi, cudaEven
         }
     };
     for (int lv = 0; lv < ctx->nlevels; ++lv) {   // lv 0 = deepest level; children always sit in earlier launches
-        if (all) {
-            const int begin = ctx->level_ptr[lv * NCLS];
-            launch_pivot(fa, begin, ctx->level_ptr[(lv + 1) * NCLS] - begin, s);
-        } else {
-            for (int c = 0; c < NCLS; ++c) {
-                const int g = lv * NCLS + c;
-                const int begin = first->level_begin[g];
-                launch_pivot(fa, begin, last->level_begin[g] + last->level_count[g] - begin, s);
-            }
+        for (int c = 0; c < NCLS; ++c) {      // one launch per width class (shared-memory tiles sized by the class)
+            const int g = lv * NCLS + c;
+            const int begin = all ? ctx->level_ptr[g] : first->level_begin[g];
+            const int count = all ? ctx->level_ptr[g + 1] - begin : last->level_begin[g] + last->level_count[g] - begin;
+            launch_pivot(fa, begin, count, c, s);
         }
         int begin[2], count[2];
         for (int kind = 0; kind < 2; ++kind) {
