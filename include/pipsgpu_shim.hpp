@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <memory>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "pipsgpu.h"
@@ -94,6 +95,15 @@ private:
     int n_;
     std::vector<int> krow_, jcol_;
     std::vector<double> val_;
+};
+class DenseMatrix : public GeneralMatrix {   // LinearAlgebra/Dense/DenseMatrix.h (row-major m x n block, operator[] = row pointer)
+public:
+    DenseMatrix(int m, int n) : m_(m), n_(n), a_((size_t)m * n, 0.0) {}
+    [[nodiscard]] std::pair<long long, long long> n_rows_columns() const { return {m_, n_}; }
+    double* operator[](int i) { return a_.data() + (size_t)i * n_; }
+private:
+    int m_, n_;
+    std::vector<double> a_;
 };
 class DenseSymmetricMatrix : public AbstractMatrix {   // LinearAlgebra/Dense/DenseSymmetricMatrix.h:71-79 (row-major, lower used)
 public:
@@ -194,6 +204,15 @@ public:
     // (PardisoSolver.C:276-352) and may be ignored
     void solve(int nrhss, double* rhss, int* /*colSparsity*/) override {
         PIPSGPU_SHIM_CHECK(pipsgpu_leaf_solve(leaf_, nrhss, rhss));
+    }
+    // PardisoSolver::solve(GeneralMatrix&) (PardisoSolver.C:230-251): the dense block is handed to the solver as ncols
+    // right-hand sides of length n, right-hand side j contiguous at &rhs[0][0] + j*n, solved in place
+    void solve(GeneralMatrix& rhs_in) override {
+        auto& rhs = dynamic_cast<DenseMatrix&>(rhs_in);
+        const auto [nrows, ncols] = rhs.n_rows_columns();
+        assert(nrows == n_);
+        (void)nrows;
+        PIPSGPU_SHIM_CHECK(pipsgpu_leaf_solve(leaf_, (int)ncols, &rhs[0][0]));
     }
 
     // inertia of the COMPUTED pivots (a wrong-signed / vanishing pivot shows up here even though the factorisation went on

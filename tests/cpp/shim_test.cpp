@@ -194,6 +194,12 @@ int main() {
     for (int k = 0; k < 3; ++k) for (int i = 0; i < n; ++i) multi[k * n + i] = (k + 1) * b[i];
     solver->solve(3, multi.data(), nullptr);
     double lin = 0; for (int i = 0; i < n; ++i) lin += std::fabs(multi[2 * n + i] - 3.0 * rhs.elements()[i]);
+    // solve(GeneralMatrix&): two right-hand sides handed over as a dense block (PardisoSolver.C:230-251)
+    DenseMatrix blockrhs(n, 2);
+    for (int i = 0; i < n; ++i) { (&blockrhs[0][0])[i] = b[i]; (&blockrhs[0][0])[n + i] = -2.0 * b[i]; }
+    solver->solve(blockrhs);
+    for (int i = 0; i < n; ++i)
+        lin += std::fabs((&blockrhs[0][0])[i] - rhs.elements()[i]) + std::fabs((&blockrhs[0][0])[n + i] + 2.0 * rhs.elements()[i]);
 
     // ---- PardisoSchurSolver's exact call sequence: matrixChanged(); schur_solve(R, A, C, F, G, DenseSymmetricMatrix&) ----
     // (sLinsysLeafSchurSlv.C:20-35 unchanged). Sum over the leaves against the batched device path on a fresh SC.
