@@ -285,7 +285,8 @@ def cpu_reference(pkg, args, total_blocks, sample_blocks, steps, warmup):
     return dict(value=value, unit=UNIT, cores=threads, kind="port",
                 sample=f"{sample} of {total_blocks} blocks measured per step (1 factorize + 1 solveCompressed); leaf part x{scale:.1f}, "
                        f"dense root part unscaled, {args.solves} solves/iteration; C multifrontal LDL^T + Schur terms "
-                       f"(oracle/mf_ldlt.c) + LAPACK dsytrf root, {threads} host threads",
+                       f"(oracle/mf_ldlt.c, front updates {'through OpenBLAS dgemm (BLAS-3)' if mf.uses_blas() else 'scalar'}) "
+                       f"+ LAPACK dsytrf root, {threads} host threads",
                 t_leaf_factor_sample=tlf, t_root_factor=trf, t_leaf_solve_sample=tls, t_root_solve=trs,
                 measured_seconds_per_step=tlf + trf + tls + trs, sample_blocks=sample, sample_scale=scale)
 

@@ -30,13 +30,50 @@ class _MfSym(C.Structure):
                 ("Coff", C.c_void_p), ("ptype", C.c_void_p), ("sgn", C.c_void_p)]
 
 
+_BLAS = None      # keeps the OpenBLAS handle alive
+
+
+def _attach_blas(L):
+    """hand scipy's bundled OpenBLAS dgemm (LP64 build, scipy.libs/libscipy_openblas-*.so) to the C code, pinned to one
+    thread per call (the blocks are spread over host threads by MfBackend). MF_ORACLE_BLAS=0 keeps the scalar loops."""
+    global _BLAS
+    if os.environ.get("MF_ORACLE_BLAS", "1") == "0":
+        return False
+    try:
+        import glob
+        import scipy
+        cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas-*.so"))
+        if not cands:
+            return False
+        B = C.CDLL(cands[0])
+        fn = getattr(B, "scipy_cblas_dgemm")
+        L.mf_set_dgemm(C.cast(fn, C.c_void_p))
+        _BLAS = B
+        return True
+    except Exception:      # noqa: BLE001
+        return False
+
+
 def lib():
     global _LIB
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.mf_factorize.restype = C.c_int
         _LIB.mf_solve.restype = C.c_int
+        _LIB.mf_has_dgemm.restype = C.c_int
+        _attach_blas(_LIB)
     return _LIB
+
+
+def uses_blas():
+    return bool(lib().mf_has_dgemm())
+
+
+def blas_threads(n):
+    """thread count of the OpenBLAS instance behind the leaf updates AND scipy's LAPACK: 1 while the leaves are spread over
+    the host threads (the dgemm calls must not oversubscribe the cores), all cores again for the root's dsytrf"""
+    if _BLAS is not None and hasattr(_BLAS, "scipy_openblas_set_num_threads"):
+        _BLAS.scipy_openblas_set_num_threads(C.c_int(max(1, int(n))))
 
 
 def _p(a):
@@ -206,7 +243,9 @@ class MfBackend:
 
         import time
         t0 = time.perf_counter()
+        blas_threads(1)
         list(self.pool.map(work, range(nth)))
+        blas_threads(os.cpu_count() or 1)
         SCb = np.sum(acc, axis=0)
         self.t_leaf_factor = time.perf_counter() - t0      # leaf LDL^T + Schur terms (scales with the number of blocks)
         t0 = time.perf_counter()

@@ -23,6 +23,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Optional BLAS-3 front updates (the CPU arm of bench.py must be a fair stand-in for PARDISO / MA57, which use BLAS-3
+ * kernels inside their fronts): oracle/mf.py hands over the address of a CBLAS dgemm (scipy's bundled OpenBLAS, loaded at
+ * run time; single-threaded per call - the blocks are distributed over host threads). Without it the scalar loops run. */
+typedef void (*cblas_dgemm_fn)(int layout, int transa, int transb, int m, int n, int k, double alpha, const double* a, int lda,
+                               const double* b, int ldb, double beta, double* c, int ldc);
+static cblas_dgemm_fn g_dgemm = 0;
+void mf_set_dgemm(void* fn) { g_dgemm = (cblas_dgemm_fn)fn; }
+int mf_has_dgemm(void) { return g_dgemm != 0; }
+enum { MF_COL_MAJOR = 102, MF_NO_TRANS = 111, MF_TRANS = 112, MF_JB = 192 };
+
 typedef struct {
     int n, nB, ns;
     const int* sn_col;
@@ -58,6 +68,11 @@ int mf_factorize(const mf_sym* S, int64_t nnzK, const int64_t* kmap, const doubl
     }
     double* W = (double*)malloc(sizeof(double) * (size_t)maxm * (size_t)(maxw > 0 ? maxw : 1));
     if (!W) return -1;
+    double* T = 0;      /* BLAS path: one block column of the update, row-major T[i][j] */
+    if (g_dgemm) {
+        T = (double*)malloc(sizeof(double) * (size_t)(maxm > 0 ? maxm : 1) * MF_JB);
+        if (!T) { free(W); return -1; }
+    }
 
     for (int s = 0; s < ns; ++s) {
         const int c0 = S->sn_col[s];
@@ -123,6 +138,28 @@ int mf_factorize(const mf_sym* S, int64_t nnzK, const int64_t* kmap, const doubl
         /* ---- contribution block: C(i,j) -= sum_k L(i,k) W(j,k), j < na ; border x border goes to SCb ---- */
         double* Cs = C + S->Coff[s];
         const int* rows = S->rowidx + S->sn_rowptr[s];
+        if (g_dgemm && u >= 48) {
+            /* U = L21 W21^T by block columns of MF_JB: T^T (jb x ni, column-major) = W21(j-block) * L21(i >= j0)^T, i.e.
+             * T[i][j] row-major with leading dimension jb - rows of the Schur complement are then updated contiguously */
+            const double* L21 = F + w;       /* u x w, ld m */
+            const double* W21 = W + w;       /* u x w, ld m */
+            for (int j0 = 0; j0 < u; j0 += MF_JB) {
+                const int jb = (u - j0 < MF_JB) ? u - j0 : MF_JB;
+                const int ni = u - j0;
+                g_dgemm(MF_COL_MAJOR, MF_NO_TRANS, MF_TRANS, jb, ni, w, 1.0, W21 + j0, m, L21 + j0, m, 0.0, T, jb);
+                for (int ii = 0; ii < ni; ++ii) {
+                    const int i = j0 + ii;
+                    const double* Ti = T + (size_t)ii * jb;
+                    const int jend = (ii < jb) ? ii + 1 : jb;      /* j <= i */
+                    double* scrow = (SCb && i >= na) ? SCb + (size_t)(rows[i] - n) * S->nB : 0;
+                    for (int jj = 0; jj < jend; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < na) Cs[(size_t)j * u + i] -= Ti[jj];
+                        else if (scrow) scrow[rows[j] - n] -= Ti[jj];
+                    }
+                }
+            }
+        } else
         for (int j = 0; j < u; ++j) {
             for (int kk = 0; kk < w; ++kk) {
                 const double wj = W[(size_t)kk * m + w + j];
@@ -157,6 +194,7 @@ int mf_factorize(const mf_sym* S, int64_t nnzK, const int64_t* kmap, const doubl
         }
     }
     free(W);
+    free(T);
     if (inertia) { inertia[0] = pos; inertia[1] = neg; inertia[2] = zero; }
     if (n_perturbed) *n_perturbed = npert;
     return 0;
