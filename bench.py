@@ -527,7 +527,8 @@ def main():
                       "bound": "tensor", "achieved": cnt["F3"] / t_root / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
                       "frac": cnt["F3"] / t_root / 1e12 / dmma_peak, "traffic": traffic.get("root_ldlt"),
                       "peak_source": tensor_src, "algorithmic_flops_per_launch_set": cnt["F3"], "avg_launch_ms": t_root * 1e3,
-                      "launches_per_step": 1, "share_of_step": stage_ms["root_ldlt"] / ms_per_step})
+                      "launches_per_step": 1, "share_of_step": stage_ms["root_ldlt"] / ms_per_step,
+                      "dmma_pipe_active_pct_ncu_trailing_gemm": traffic.get("root_dmma_pipe_active_pct_trailing_gemm")})
     # (4) leaf factorisation as a whole (pivot / panel / tile kernels of every level + the Schur kernels): B1 + B2
     t_leaf = stage_ms["leaf_ldlt_schur"] * 1e-3
     nlev = max(s["nlevels"] for s in leaf_stats)
