@@ -115,12 +115,12 @@ struct SolveArgs {
 };
 
 // ---- streaming persistent solve (psolve.cu): one launch = K^-1 for every block of the GPU ----
-constexpr int PS_WARPS = 8;      // warps per CTA, one CTA per SM
+constexpr int PS_WARPS = 9;      // warps per CTA, one CTA per SM (9 x 24 KB of staging + 12 KB static = 224 KB)
 constexpr int PS_BUF = 1184;     // doubles per staging buffer (9.25 KB, holds 32 rows of a 32-wide front), two per warp
 constexpr int PS_HDR = 96;       // chunk header: three 32-wide rows of D^-1 coefficients
 constexpr int PS_XA = 128;       // max rows per chunk
 constexpr int PS_SMAX = 512;     // max columns of a subtree unit (its right-hand-side slice lives in shared memory)
-constexpr int PS_NOUT = 384;     // rows above a unit that are accumulated in shared memory (the rest: global atomics)
+constexpr int PS_NOUT = 128;     // rows above a unit that are accumulated in shared memory (the rest: global atomics); fronts have <= ~80 ancestor rows
 constexpr int PS_WARP_DOUBLES = 2 * PS_BUF + PS_SMAX + PS_NOUT;
 struct SolveFront {              // one per front, fronts of a unit contiguous and in postorder
     int64_t blob;                // offset (doubles, even) of the front's chunks in the solve pool
